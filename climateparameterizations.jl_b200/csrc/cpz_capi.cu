@@ -1,0 +1,365 @@
+// C ABI of libcpz.so (see include/cpz.h). Host-side orchestration: device buffers, launches, error reporting.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "cpz_adjoint.cuh"
+#include "cpz_closure.cuh"
+#include "cpz_internal.h"
+#include "cpz_solve.cuh"
+
+namespace cpz {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return CPZ_ERR_CUDA;
+}
+
+static int ensure(DevBuf& b, size_t floats) {
+  if (floats <= b.cap) return CPZ_OK;
+  if (b.p) CPZ_CUDA(cudaFree(b.p));
+  b.p = nullptr; b.cap = 0;
+  CPZ_CUDA(cudaMalloc(&b.p, std::max<size_t>(floats, 4) * sizeof(float)));
+  b.cap = floats;
+  return CPZ_OK;
+}
+static void release(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr; b.cap = 0;
+}
+
+static int n_saved_of(const TimeD& tm) { return tm.save_stride <= 0 ? 1 : tm.n_steps / tm.save_stride + 1; }
+// checkpoints: step 0, every ckpt_stride-th step, and the final step (once)
+static int n_ckpt_of(const TimeD& tm) {
+  int n = tm.n_steps / tm.ckpt_stride + 1;
+  if (tm.n_steps % tm.ckpt_stride != 0) ++n;
+  return n;
+}
+
+// ---- forward launch ---------------------------------------------------------------------------------------------
+template <int CT, int NT, bool WS>
+static int launch_solve_t(cpz_model* m, const SolveArgs& a) {
+  const SolveSmem L = solve_smem_layout(m->fwd.M, CT, m->tab.n_stages);
+  const size_t smem = (size_t)L.total_floats * sizeof(float);
+  if (smem > m->ctx->smem_optin) return fail(CPZ_ERR_INVALID, "forward kernel needs %zu B shared memory, device allows %zu", smem, m->ctx->smem_optin);
+  auto kern = solve_kernel<CT, NT, WS>;
+  CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int n_tiles = (a.ncol + CT - 1) / CT;
+  kern<<<n_tiles, NT, smem, m->ctx->stream>>>(m->fwd.M, m->tab, m->tm, a);
+  CPZ_CUDA(cudaGetLastError());
+  m->ctx->launches++;
+  return CPZ_OK;
+}
+
+static int launch_solve(cpz_model* m, const SolveArgs& a) {
+  if (m->fwd.M.w_in_smem) return launch_solve_t<32, 256, true>(m, a);
+  return launch_solve_t<32, 256, false>(m, a);
+}
+
+static int check_model(const cpz_model* m) {
+  if (!m || !m->ctx) return fail(CPZ_ERR_INVALID, "null model handle");
+  return CPZ_OK;
+}
+
+static int bind_device(const cpz_ctx* c) {
+  CPZ_CUDA(cudaSetDevice(c->device));
+  return CPZ_OK;
+}
+
+static size_t solve_other_smem(const cpz_model_desc& d, int CT, int n_stages) {
+  const int S = d.n_fields * d.Nz, nbc = d.n_fields == 3 ? 6 : 2;
+  return ((size_t)S * CT + (size_t)CT * (S + 4) + (size_t)n_stages * S * CT + (size_t)nbc * CT + CT + 4) * sizeof(float);
+}
+
+static int rebuild_plans(cpz_model* m) {
+  std::string err;
+  fill_tableau(m->desc.integrator, m->tab);
+  m->tm.dt = m->desc.dt; m->tm.t0 = m->desc.t0; m->tm.n_steps = m->desc.n_steps; m->tm.n_substeps = m->desc.n_substeps;
+  m->tm.save_stride = m->desc.save_stride; m->tm.ckpt_stride = m->desc.ckpt_stride;
+  PlanOptions fo;
+  fo.CT = m->CT; fo.NT = m->NT; fo.keep_all = false;
+  fo.smem_budget = m->ctx->smem_optin;
+  fo.other_smem_bytes = solve_other_smem(m->desc, m->CT, m->tab.n_stages);
+  if (!build_plan(m->desc, fo, m->fwd, err)) return fail(CPZ_ERR_INVALID, "forward plan: %s", err.c_str());
+  PlanOptions bo;
+  bo.CT = m->CT; bo.NT = m->NT; bo.keep_all = true;
+  bo.smem_budget = m->ctx->smem_optin;
+  bo.other_smem_bytes = adjoint_other_smem(m->desc.n_fields * m->desc.Nz, m->desc.n_fields == 3 ? 6 : 2, m->CT);
+  m->has_bwd = build_plan(m->desc, bo, m->bwd, m->bwd_err);
+  return CPZ_OK;
+}
+
+}  // namespace cpz
+
+using namespace cpz;
+
+extern "C" {
+
+int cpz_version(void) { return CPZ_VERSION_MAJOR * 100 + CPZ_VERSION_MINOR; }
+const char* cpz_last_error(void) { return g_err; }
+
+size_t cpz_sizeof_model_desc(void) { return sizeof(cpz_model_desc); }
+size_t cpz_sizeof_closure_desc(void) { return sizeof(cpz_closure_desc); }
+
+int cpz_device_count(int* n) {
+  if (!n) return fail(CPZ_ERR_INVALID, "null pointer");
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) { cudaGetLastError(); c = 0; }
+  *n = c;
+  return CPZ_OK;
+}
+
+int cpz_ctx_create(int device, void* stream, cpz_ctx** out) {
+  if (!out) return fail(CPZ_ERR_INVALID, "null out pointer");
+  *out = nullptr;
+  int cnt = 0;
+  cudaError_t e = cudaGetDeviceCount(&cnt);
+  if (e != cudaSuccess || cnt == 0) {
+    cudaGetLastError();
+    return fail(CPZ_ERR_CUDA, "no CUDA device available (%s); libcpz has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= cnt) return fail(CPZ_ERR_INVALID, "device %d out of range [0,%d)", device, cnt);
+  CPZ_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CPZ_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(CPZ_ERR_CUDA, "device %d is sm_%d%d; libcpz is built for sm_100a only", device, prop.major, prop.minor);
+  cpz_ctx* c = new (std::nothrow) cpz_ctx();
+  if (!c) return fail(CPZ_ERR_INVALID, "out of host memory");
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->smem_optin = prop.sharedMemPerBlockOptin;
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+  } else {
+    cudaError_t es = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (es != cudaSuccess) { delete c; return cuda_fail(es, "cudaStreamCreateWithFlags"); }
+    c->own_stream = true;
+  }
+  *out = c;
+  return CPZ_OK;
+}
+
+int cpz_ctx_destroy(cpz_ctx* ctx) {
+  if (!ctx) return CPZ_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return CPZ_OK;
+}
+
+int cpz_ctx_set_allreduce(cpz_ctx* ctx, cpz_allreduce_fn fn, void* user, int rank, int world_size) {
+  if (!ctx) return fail(CPZ_ERR_INVALID, "null ctx");
+  if (world_size < 1 || rank < 0 || rank >= world_size) return fail(CPZ_ERR_INVALID, "bad rank/world_size");
+  ctx->allreduce = fn; ctx->allreduce_user = user; ctx->rank = rank; ctx->world = world_size;
+  return CPZ_OK;
+}
+
+int cpz_ctx_synchronize(cpz_ctx* ctx) {
+  if (!ctx) return fail(CPZ_ERR_INVALID, "null ctx");
+  CPZ_CUDA(cudaSetDevice(ctx->device));
+  CPZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CPZ_OK;
+}
+
+int cpz_ctx_stream(cpz_ctx* ctx, void** stream_out) {
+  if (!ctx || !stream_out) return fail(CPZ_ERR_INVALID, "null pointer");
+  *stream_out = (void*)ctx->stream;
+  return CPZ_OK;
+}
+
+int cpz_ctx_launch_count(cpz_ctx* ctx, uint64_t* n) {
+  if (!ctx || !n) return fail(CPZ_ERR_INVALID, "null pointer");
+  *n = ctx->launches;
+  return CPZ_OK;
+}
+
+int cpz_model_create(cpz_ctx* ctx, const cpz_model_desc* desc, cpz_model** out) {
+  if (!ctx || !desc || !out) return fail(CPZ_ERR_INVALID, "null pointer");
+  *out = nullptr;
+  std::string err;
+  if (!validate_desc(*desc, err)) return fail(CPZ_ERR_INVALID, "%s", err.c_str());
+  int rc = bind_device(ctx);
+  if (rc) return rc;
+  cpz_model* m = new (std::nothrow) cpz_model();
+  if (!m) return fail(CPZ_ERR_INVALID, "out of host memory");
+  m->ctx = ctx;
+  m->desc = *desc;
+  m->P = count_params(*desc);
+  rc = rebuild_plans(m);
+  if (rc) { delete m; return rc; }
+  const size_t pf = std::max<size_t>(m->P, 4);
+  cudaError_t e = cudaMalloc(&m->d_theta, pf * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_m, pf * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_v, pf * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemsetAsync(m->d_theta, 0, pf * sizeof(float), ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(m->d_m, 0, pf * sizeof(float), ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(m->d_v, 0, pf * sizeof(float), ctx->stream);
+  if (e != cudaSuccess) { cpz_model_destroy(m); return cuda_fail(e, "model allocation"); }
+  *out = m;
+  return CPZ_OK;
+}
+
+int cpz_model_destroy(cpz_model* m) {
+  if (!m) return CPZ_OK;
+  if (m->ctx) { cudaSetDevice(m->ctx->device); cudaStreamSynchronize(m->ctx->stream); }
+  if (m->d_theta) cudaFree(m->d_theta);
+  if (m->d_m) cudaFree(m->d_m);
+  if (m->d_v) cudaFree(m->d_v);
+  DevBuf* bufs[] = {&m->b_x0, &m->b_bcs, &m->b_q, &m->b_traj, &m->b_tgt, &m->b_ckpt, &m->b_scr, &m->b_part, &m->b_red, &m->b_out, &m->b_w};
+  for (DevBuf* b : bufs) release(*b);
+  delete m;
+  return CPZ_OK;
+}
+
+int cpz_model_n_params(const cpz_model* m, size_t* P) {
+  if (!m || !P) return fail(CPZ_ERR_INVALID, "null pointer");
+  *P = m->P;
+  return CPZ_OK;
+}
+
+int cpz_model_n_saved(const cpz_model* m, int32_t* n) {
+  if (!m || !n) return fail(CPZ_ERR_INVALID, "null pointer");
+  *n = n_saved_of(m->tm);
+  return CPZ_OK;
+}
+
+int cpz_set_theta(cpz_model* m, const float* theta, size_t P) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (P != m->P) return fail(CPZ_ERR_INVALID, "theta length %zu != model parameters %zu", P, m->P);
+  if (P == 0) return CPZ_OK;
+  if (!theta) return fail(CPZ_ERR_INVALID, "null theta");
+  if ((rc = bind_device(m->ctx))) return rc;
+  CPZ_CUDA(cudaMemcpyAsync(m->d_theta, theta, P * sizeof(float), cudaMemcpyHostToDevice, m->ctx->stream));
+  CPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  return CPZ_OK;
+}
+
+int cpz_get_theta(cpz_model* m, float* theta, size_t P) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (P != m->P) return fail(CPZ_ERR_INVALID, "theta length %zu != model parameters %zu", P, m->P);
+  if (P == 0) return CPZ_OK;
+  if (!theta) return fail(CPZ_ERR_INVALID, "null theta");
+  if ((rc = bind_device(m->ctx))) return rc;
+  CPZ_CUDA(cudaMemcpyAsync(theta, m->d_theta, P * sizeof(float), cudaMemcpyDeviceToHost, m->ctx->stream));
+  CPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  return CPZ_OK;
+}
+
+int cpz_model_set_time(cpz_model* m, int32_t integrator, float dt, float t0, int32_t n_steps, int32_t n_substeps,
+                       int32_t save_stride, int32_t ckpt_stride) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  cpz_model_desc d = m->desc;
+  d.integrator = integrator; d.dt = dt; d.t0 = t0; d.n_steps = n_steps; d.n_substeps = n_substeps;
+  d.save_stride = save_stride; d.ckpt_stride = ckpt_stride;
+  std::string err;
+  if (!validate_desc(d, err)) return fail(CPZ_ERR_INVALID, "%s", err.c_str());
+  const bool replan = d.integrator != m->desc.integrator;
+  m->desc = d;
+  if (replan) return rebuild_plans(m);
+  fill_tableau(d.integrator, m->tab);
+  m->tm.dt = dt; m->tm.t0 = t0; m->tm.n_steps = n_steps; m->tm.n_substeps = n_substeps;
+  m->tm.save_stride = save_stride; m->tm.ckpt_stride = ckpt_stride;
+  return CPZ_OK;
+}
+
+// ---- RHS ------------------------------------------------------------------------------------------------------------
+int cpz_rhs_dev(cpz_model* m, const float* x, const float* bcs, const float* diurnal_Q, float t, float* dxdt, size_t ncol) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (ncol == 0) return CPZ_OK;
+  if (!x || !bcs || !dxdt) return fail(CPZ_ERR_INVALID, "null array");
+  if ((m->desc.flags & CPZ_FLAG_DIURNAL) && !diurnal_Q) return fail(CPZ_ERR_INVALID, "diurnal model needs diurnal_Q");
+  if (ncol > (size_t)INT32_MAX / 512) return fail(CPZ_ERR_INVALID, "ncol too large");
+  if ((rc = bind_device(m->ctx))) return rc;
+  SolveArgs a{};
+  a.theta = m->d_theta; a.x0 = x; a.bcs = bcs; a.Q = diurnal_Q; a.dxdt = dxdt; a.ncol = (int)ncol;
+  a.rhs_only = 1; a.t_rhs = t; a.n_saved = 1; a.n_ckpt = 0;
+  return launch_solve(m, a);
+}
+
+static int upload_inputs(cpz_model* m, const float* x0, const float* bcs, const float* Q, size_t ncol) {
+  const size_t S = (size_t)m->fwd.M.S, nbc = (size_t)m->fwd.M.nbc;
+  int rc;
+  if ((rc = ensure(m->b_x0, ncol * S))) return rc;
+  if ((rc = ensure(m->b_bcs, ncol * nbc))) return rc;
+  cudaStream_t st = m->ctx->stream;
+  CPZ_CUDA(cudaMemcpyAsync(m->b_x0.p, x0, ncol * S * sizeof(float), cudaMemcpyHostToDevice, st));
+  CPZ_CUDA(cudaMemcpyAsync(m->b_bcs.p, bcs, ncol * nbc * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (Q) {
+    if ((rc = ensure(m->b_q, ncol))) return rc;
+    CPZ_CUDA(cudaMemcpyAsync(m->b_q.p, Q, ncol * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  return CPZ_OK;
+}
+
+int cpz_rhs(cpz_model* m, const float* x, const float* bcs, const float* diurnal_Q, float t, float* dxdt, size_t ncol) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (ncol == 0) return CPZ_OK;
+  if (!x || !bcs || !dxdt) return fail(CPZ_ERR_INVALID, "null array");
+  if ((rc = bind_device(m->ctx))) return rc;
+  if ((rc = upload_inputs(m, x, bcs, diurnal_Q, ncol))) return rc;
+  const size_t S = (size_t)m->fwd.M.S;
+  if ((rc = ensure(m->b_traj, ncol * S))) return rc;
+  if ((rc = cpz_rhs_dev(m, m->b_x0.p, m->b_bcs.p, diurnal_Q ? m->b_q.p : nullptr, t, m->b_traj.p, ncol))) return rc;
+  CPZ_CUDA(cudaMemcpyAsync(dxdt, m->b_traj.p, ncol * S * sizeof(float), cudaMemcpyDeviceToHost, m->ctx->stream));
+  CPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  return CPZ_OK;
+}
+
+// ---- forward solve ----------------------------------------------------------------------------------------------------
+int cpz_solve_dev(cpz_model* m, const float* x0, const float* bcs, const float* diurnal_Q, float* traj, size_t ncol) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (ncol == 0) return CPZ_OK;
+  if (!x0 || !bcs || !traj) return fail(CPZ_ERR_INVALID, "null array");
+  if ((m->desc.flags & CPZ_FLAG_DIURNAL) && !diurnal_Q) return fail(CPZ_ERR_INVALID, "diurnal model needs diurnal_Q");
+  if (ncol > (size_t)INT32_MAX / 512) return fail(CPZ_ERR_INVALID, "ncol too large");
+  if ((rc = bind_device(m->ctx))) return rc;
+  SolveArgs a{};
+  a.theta = m->d_theta; a.x0 = x0; a.bcs = bcs; a.Q = diurnal_Q; a.traj = traj; a.ncol = (int)ncol;
+  a.n_saved = n_saved_of(m->tm); a.n_ckpt = 0; a.rhs_only = 0;
+  return launch_solve(m, a);
+}
+
+int cpz_solve(cpz_model* m, const float* x0, const float* bcs, const float* diurnal_Q, float* traj, size_t ncol) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (ncol == 0) return CPZ_OK;
+  if (!x0 || !bcs || !traj) return fail(CPZ_ERR_INVALID, "null array");
+  if ((rc = bind_device(m->ctx))) return rc;
+  if ((rc = upload_inputs(m, x0, bcs, diurnal_Q, ncol))) return rc;
+  const size_t n = ncol * (size_t)n_saved_of(m->tm) * (size_t)m->fwd.M.S;
+  if ((rc = ensure(m->b_traj, n))) return rc;
+  if ((rc = cpz_solve_dev(m, m->b_x0.p, m->b_bcs.p, diurnal_Q ? m->b_q.p : nullptr, m->b_traj.p, ncol))) return rc;
+  CPZ_CUDA(cudaMemcpyAsync(traj, m->b_traj.p, n * sizeof(float), cudaMemcpyDeviceToHost, m->ctx->stream));
+  CPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  return CPZ_OK;
+}
+
+#include "cpz_capi_train.inc"
+
+}  // extern "C"

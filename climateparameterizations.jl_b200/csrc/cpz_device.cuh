@@ -1,0 +1,418 @@
+// Device building blocks of the NDE column engine (sm_100a).
+//
+// Data layout inside a CTA ("column tile" of CT columns):
+//   every per-column vector lives in shared memory FEATURE-MAJOR: v[row][c], c = column in tile fastest.
+//   - elementwise / stencil work maps lanes to consecutive columns  -> conflict-free LDS/STS
+//   - the MLP runs as a small dense contraction out[N][CT] = act(W^T in[K][CT] + b): a thread owns a
+//     4-column x TO-output register tile, reads 4 columns of one input row as one LDS.128 (broadcast within
+//     the column group) and TO weights of one W row (W is [K][N], Flux's column-major out x in).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cpz_model.h"
+
+namespace cpz {
+
+// ---- flags / enums mirrored from include/cpz.h (kept numeric here to avoid including the C header in device code)
+enum { RHS_TRAIN = 0, RHS_INFER = 1, RHS_FC = 2 };
+enum {
+  F_MPP = 1, F_CA = 2, F_ZERO_WEIGHTS = 4, F_SMOOTH_NN = 8, F_SMOOTH_RI = 16, F_DIURNAL = 32, F_CA_LITERAL_U = 64,
+  F_DIURNAL_UNSHIFTED = 128
+};
+enum { ACT_ID = 0, ACT_RELU = 1, ACT_MISH = 2, ACT_SWISH = 3, ACT_LEAKY = 4, ACT_TANH = 5 };
+
+// ---- activations (NNlib 0.7.20 definitions), FP32-accurate (no fast-math intrinsics) -------------------------
+__device__ __forceinline__ float act_fwd(int act, float x) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(x, 0.f);
+    case ACT_MISH: {  // x*tanh(softplus(x)) = x*n/(n+2), n = e^x(e^x+2)
+      if (x > 20.f) return x;
+      float e = expf(x);
+      float n = e * (e + 2.f);
+      return x * (n / (n + 2.f));
+    }
+    case ACT_SWISH: return x / (1.f + expf(-x));
+    case ACT_LEAKY: return fmaxf(0.01f * x, x);
+    case ACT_TANH: return tanhf(x);
+    default: return x;
+  }
+}
+
+// derivative d act / d z at the pre-activation z
+__device__ __forceinline__ float act_grad(int act, float z) {
+  switch (act) {
+    case ACT_RELU: return z > 0.f ? 1.f : 0.f;
+    case ACT_MISH: {
+      if (z > 20.f) return 1.f;
+      float e = expf(z);
+      float n = e * (e + 2.f);
+      float t = n / (n + 2.f);
+      float sg = e / (1.f + e);
+      return t + z * (1.f - t * t) * sg;
+    }
+    case ACT_SWISH: {
+      float sg = 1.f / (1.f + expf(-z));
+      return sg + z * sg * (1.f - sg);
+    }
+    case ACT_LEAKY: return z > 0.f ? 1.f : 0.01f;
+    case ACT_TANH: {
+      float t = tanhf(z);
+      return 1.f - t * t;
+    }
+    default: return 1.f;
+  }
+}
+
+// ---- async bulk copies (TMA engine, non-tensor form: UBLKCP) --------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared, completion on an mbarrier. dst/src 16-byte aligned, bytes % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared -> global, bulk-group completion.
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// ---- dense layer: one 4-column x TO-output register tile --------------------------------------------------------
+// in:  [K][CT] shared, out: [N][CT] shared (post-activation), zout (optional): [N][CT] pre-activation.
+// WS: weights come from the shared arena (row stride Npad, zero padded) else straight from theta in global.
+template <int TO, bool WS, int CT, bool SAVE_Z>
+__device__ __forceinline__ void gemm_tile_fwd(const GemmD& g, const float* __restrict__ in, float* __restrict__ out,
+                                              float* __restrict__ zout, const float* __restrict__ W,
+                                              const float* __restrict__ bias, int cg, int og) {
+  const int j0 = og * TO;
+  const int K = g.K, N = g.N;
+  const int ldw = WS ? g.Npad : N;
+  float acc[TO][4];
+  int jo[TO];
+#pragma unroll
+  for (int o = 0; o < TO; ++o) {
+    jo[o] = WS ? (j0 + o) : min(j0 + o, N - 1);
+    const float bv = WS ? bias[jo[o]] : __ldg(bias + jo[o]);
+    acc[o][0] = bv; acc[o][1] = bv; acc[o][2] = bv; acc[o][3] = bv;
+  }
+  const float* xp = in + 4 * cg;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float4 xv = *reinterpret_cast<const float4*>(xp + k * CT);
+    float w[TO];
+    if constexpr (WS && (TO % 4 == 0)) {
+#pragma unroll
+      for (int o = 0; o < TO; o += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(W + k * ldw + j0 + o);
+        w[o] = wv.x; w[o + 1] = wv.y; w[o + 2] = wv.z; w[o + 3] = wv.w;
+      }
+    } else if constexpr (WS && (TO % 2 == 0)) {
+#pragma unroll
+      for (int o = 0; o < TO; o += 2) {
+        const float2 wv = *reinterpret_cast<const float2*>(W + k * ldw + j0 + o);
+        w[o] = wv.x; w[o + 1] = wv.y;
+      }
+    } else if constexpr (WS) {
+#pragma unroll
+      for (int o = 0; o < TO; ++o) w[o] = W[k * ldw + jo[o]];
+    } else {
+#pragma unroll
+      for (int o = 0; o < TO; ++o) w[o] = __ldg(W + (size_t)k * ldw + jo[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < TO; ++o) {
+      acc[o][0] = fmaf(w[o], xv.x, acc[o][0]);
+      acc[o][1] = fmaf(w[o], xv.y, acc[o][1]);
+      acc[o][2] = fmaf(w[o], xv.z, acc[o][2]);
+      acc[o][3] = fmaf(w[o], xv.w, acc[o][3]);
+    }
+  }
+  const int act = g.act;
+#pragma unroll
+  for (int o = 0; o < TO; ++o) {
+    if (j0 + o < N) {
+      if constexpr (SAVE_Z) {
+        *reinterpret_cast<float4*>(zout + (j0 + o) * CT + 4 * cg) = make_float4(acc[o][0], acc[o][1], acc[o][2], acc[o][3]);
+      }
+      float4 r;
+      r.x = act_fwd(act, acc[o][0]);
+      r.y = act_fwd(act, acc[o][1]);
+      r.z = act_fwd(act, acc[o][2]);
+      r.w = act_fwd(act, acc[o][3]);
+      *reinterpret_cast<float4*>(out + (j0 + o) * CT + 4 * cg) = r;
+    }
+  }
+}
+
+// One phase = the gemms [g0,g1) of the plan, run over a flattened (gemm, output group, column group) tile space.
+// X: state tile [S][CT]; arena: activations [rows][CT]; zarena: pre-activations (same row offsets) when SAVE_Z.
+template <bool WS, int CT, int NT, bool SAVE_Z>
+__device__ __forceinline__ void run_phase(const ModelD& M, int p, const float* __restrict__ X, float* __restrict__ arena,
+                                          float* __restrict__ zarena, const float* __restrict__ wsm,
+                                          const float* __restrict__ theta) {
+  constexpr int NCG = CT / 4;
+  const int g0 = M.phase[p].g0, g1 = M.phase[p].g1, n_tiles = M.phase[p].n_tiles;
+  for (int tile = threadIdx.x; tile < n_tiles; tile += NT) {
+    int gi = g0;
+    while (gi + 1 < g1 && tile >= M.gemm[gi + 1].tile_begin) ++gi;
+    const GemmD& g = M.gemm[gi];
+    const int local = tile - g.tile_begin;
+    const int cg = local % NCG, og = local / NCG;
+    const float* in = g.in_off < 0 ? X : arena + g.in_off * CT;
+    float* out = arena + g.out_off * CT;
+    float* zo = SAVE_Z ? zarena + g.out_off * CT : nullptr;
+    const float* W = WS ? wsm + g.sw_off : theta + g.w_off;
+    const float* B = WS ? wsm + g.sb_off : theta + g.b_off;
+    switch (g.TO) {
+      case 1: gemm_tile_fwd<1, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
+      case 2: gemm_tile_fwd<2, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
+      case 3: gemm_tile_fwd<3, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
+      case 4: gemm_tile_fwd<4, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
+      case 5: gemm_tile_fwd<5, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
+      case 6: gemm_tile_fwd<6, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
+      default: gemm_tile_fwd<8, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
+    }
+  }
+}
+
+// Copy theta into the shared weight arena in the plan's padded layout (rows of Npad floats, zero padded).
+template <int NT>
+__device__ __forceinline__ void load_weights_smem(const ModelD& M, float* __restrict__ wsm, const float* __restrict__ theta) {
+  for (int i = threadIdx.x; i < M.smem_w_floats; i += NT) wsm[i] = 0.f;
+  __syncthreads();
+  for (int gi = 0; gi < M.n_gemm; ++gi) {
+    const GemmD& g = M.gemm[gi];
+    const int K = g.K, N = g.N, Np = g.Npad;
+    for (int i = threadIdx.x; i < K * N; i += NT) {
+      const int k = i / N, j = i - k * N;
+      wsm[g.sw_off + k * Np + j] = __ldg(theta + g.w_off + i);
+    }
+    for (int j = threadIdx.x; j < N; j += NT) wsm[g.sb_off + j] = __ldg(theta + g.b_off + j);
+  }
+}
+
+// ---- per-column boundary data ------------------------------------------------------------------------------------
+// bcf[q][0/1][CT]: effective boundary-face fluxes (bottom, top) for field q after the variant's shift rule.
+// For the diurnal case the top wT entry is recomputed every stage from Q and t.
+__device__ __forceinline__ void bc_effective(const ModelD& M, const float* __restrict__ bc /*nbc raw values*/, float* out6) {
+  if (M.variant == RHS_FC) {
+    out6[0] = bc[0]; out6[1] = bc[1];
+    return;
+  }
+  const bool mpp = (M.flags & F_MPP) || M.variant == RHS_INFER;
+  const bool shift = M.variant == RHS_INFER || (M.flags & F_ZERO_WEIGHTS);
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    float b = bc[2 * q], t = bc[2 * q + 1];
+    if (mpp && shift) { b -= M.rc.z0[q]; t -= M.rc.z0[q]; }
+    else if (M.flags & F_ZERO_WEIGHTS) { b = 0.f; t = 0.f; }
+    out6[2 * q] = b; out6[2 * q + 1] = t;
+  }
+}
+
+__device__ __forceinline__ float diurnal_top_eff(const ModelD& M, float Q, float t) {
+  // s_wT(Q sin(2 pi t tau / period)/(alpha g))   NDE_training.jl:72-73, data_containers.jl:135
+  float top = (Q * sinf(M.rc.di_w * t) * M.rc.di_amp - M.rc.mu_wT) * M.rc.inv_sig_wT;
+  const bool mpp = (M.flags & F_MPP) || M.variant == RHS_INFER;
+  const bool shift = M.variant == RHS_INFER || (M.flags & F_ZERO_WEIGHTS);
+  if (mpp && shift) {
+    if (!(M.variant == RHS_INFER && (M.flags & F_DIURNAL_UNSHIFTED))) top -= M.rc.z0[2];
+  } else if (M.flags & F_ZERO_WEIGHTS) {
+    top = 0.f;
+  }
+  return top;
+}
+
+// width-3 running mean of filtering_operators.jl:1-15 applied to v[0..n) at index i (v row-strided by CT)
+__device__ __forceinline__ float filt3(const float* __restrict__ v, int i, int n, int stride) {
+  if (i == 0) return (v[0] + v[stride]) * 0.5f;
+  if (i == n - 1) return (v[(n - 2) * stride] + v[(n - 1) * stride]) * 0.5f;
+  return (v[(i - 1) * stride] + v[i * stride] + v[(i + 1) * stride]) * (1.f / 3.f);
+}
+
+// Richardson number at face k (0..N) of column c from the state tile (u,v,T rows), boundary faces have zero gradient.
+__device__ __forceinline__ float ri_face(const ModelD& M, const float* __restrict__ X, int k, int c, int CT_, float eps) {
+  const int N = M.Nz;
+  float Gu = 0.f, Gv = 0.f, GT = 0.f;
+  if (k > 0 && k < N) {
+    Gu = M.rc.Nf * (X[k * CT_ + c] - X[(k - 1) * CT_ + c]);
+    Gv = M.rc.Nf * (X[(N + k) * CT_ + c] - X[(N + k - 1) * CT_ + c]);
+    GT = M.rc.Nf * (X[(2 * N + k) * CT_ + c] - X[(2 * N + k - 1) * CT_ + c]);
+  }
+  const float su = M.rc.sig_u * (Gu + eps), sv = M.rc.sig_v * (Gv + eps);
+  return M.rc.BzC * (GT + eps) / (su * su + sv * sv);
+}
+
+// ---- face phase: E_q[k][c] for all faces k = 0..N ------------------------------------------------------------------
+// E is the total (NN + diffusive [+ boundary]) flux whose cell-difference gives the tendency.
+// nn rows come from the activation arena (M.nn_off), or are zero when the model has no nets.
+template <int CT, int NT>
+__device__ __forceinline__ void faces_phase(const ModelD& M, const float* __restrict__ X, const float* __restrict__ arena,
+                                            float* __restrict__ E, const float* __restrict__ bcf /*[nbc][CT]*/) {
+  const int N = M.Nz;
+  const int nfaces = N + 1;
+  const bool has_nn = M.n_nets > 0;
+  if (M.variant == RHS_FC) {
+    const float* nn = has_nn ? arena + M.nn_off[0] * CT : nullptr;
+    const bool ca = M.flags & F_CA;
+    for (int i = threadIdx.x; i < nfaces * CT; i += NT) {
+      const int k = i / CT, c = i - k * CT;
+      float e;
+      if (k == 0) e = bcf[c];
+      else if (k == N) e = bcf[CT + c];
+      else {
+        e = has_nn ? nn[(k - 1) * CT + c] : 0.f;
+        if (ca) {
+          const float G = M.rc.Nf * (X[k * CT + c] - X[(k - 1) * CT + c]);
+          e -= fminf(0.f, M.rc.K_ca * G);
+        }
+      }
+      E[i] = e;
+    }
+    return;
+  }
+  const bool mpp = (M.flags & F_MPP) || M.variant == RHS_INFER;
+  const bool smooth_nn = M.variant == RHS_TRAIN && (M.flags & F_SMOOTH_NN);
+  const bool smooth_ri = M.variant == RHS_TRAIN && (M.flags & F_SMOOTH_RI);
+  const float eps = M.variant == RHS_TRAIN ? M.rc.eps : 0.f;
+  for (int i = threadIdx.x; i < nfaces * CT; i += NT) {
+    const int k = i / CT, c = i - k * CT;
+    float e[3];
+    if (k == 0 || k == N) {
+      const int tb = k == 0 ? 0 : 1;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) e[q] = bcf[(2 * q + tb) * CT + c];
+    } else {
+      float nn[3] = {0.f, 0.f, 0.f};
+      if (has_nn) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const float* r = arena + M.nn_off[q] * CT + c;
+          nn[q] = smooth_nn ? filt3(r, k - 1, N - 1, CT) : r[(k - 1) * CT];
+        }
+      }
+      const float Gu = M.rc.Nf * (X[k * CT + c] - X[(k - 1) * CT + c]);
+      const float Gv = M.rc.Nf * (X[(N + k) * CT + c] - X[(N + k - 1) * CT + c]);
+      const float GT = M.rc.Nf * (X[(2 * N + k) * CT + c] - X[(2 * N + k - 1) * CT + c]);
+      if (mpp) {
+        float Ri;
+        if (smooth_ri) {
+          const float r0 = ri_face(M, X, k - 1, c, CT, eps), r1 = ri_face(M, X, k, c, CT, eps),
+                      r2 = ri_face(M, X, k + 1, c, CT, eps);
+          // interior faces 1..N-1 of an (N+1)-vector never hit the filter's shrinking end rows
+          Ri = (r0 + r1 + r2) * (1.f / 3.f);
+        } else {
+          const float su = M.rc.sig_u * (Gu + eps), sv = M.rc.sig_v * (Gv + eps);
+          Ri = M.rc.BzC * (GT + eps) / (su * su + sv * sv);
+        }
+        const float nu = M.rc.nu0 + M.rc.nu_m * 0.5f * (1.f - tanhf((Ri - M.rc.Ric) * M.rc.inv_dRi));
+        float nuT = nu * M.rc.inv_Pr;
+        if (M.variant == RHS_INFER && (M.flags & F_CA)) {
+          const float test = (M.flags & F_CA_LITERAL_U) ? Gu : GT;
+          nuT = test > 0.f ? nu * M.rc.inv_Pr : M.rc.kappa;
+        }
+        e[0] = nn[0] - M.rc.c[0] * nu * Gu;
+        e[1] = nn[1] - M.rc.c[1] * nu * Gv;
+        e[2] = nn[2] - M.rc.c[2] * nuT * GT;
+      } else if (M.flags & F_CA) {
+        e[0] = nn[0]; e[1] = nn[1];
+        e[2] = nn[2] - M.rc.c[2] * M.rc.kappa * fminf(0.f, GT);
+      } else {
+        e[0] = nn[0]; e[1] = nn[1]; e[2] = nn[2];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) E[(q * nfaces + k) * CT + c] = e[q];
+  }
+}
+
+// tendency of field q at level k, column c from the face fluxes and the stage input X
+__device__ __forceinline__ float tendency(const ModelD& M, const float* __restrict__ E, const float* __restrict__ X, int q,
+                                          int k, int c, int CT_) {
+  const int N = M.Nz, nfaces = N + 1;
+  const float dE = E[(q * nfaces + k + 1) * CT_ + c] - E[(q * nfaces + k) * CT_ + c];
+  if (M.variant == RHS_FC) return -M.rc.A[2] * M.rc.Nf * dE;
+  float r = -M.rc.A[q] * M.rc.Nf * dE;
+  if (q == 0) r += M.rc.cor_u_s * X[(N + k) * CT_ + c] + M.rc.cor_u_m;
+  else if (q == 1) r -= M.rc.cor_v_s * X[k * CT_ + c] + M.rc.cor_v_m;
+  return r;
+}
+
+// ---- tile <-> global transposes --------------------------------------------------------------------------------------
+// Load columns [col0, col0+CT) of a [ncol][S] global array into dst[S][CT] through `stage` ([CT][S+4] floats),
+// using one bulk async copy per column. Columns past ncol replicate the last valid one (keeps the math finite).
+template <int CT, int NT>
+__device__ __forceinline__ void load_tile(float* __restrict__ dst, float* __restrict__ stage, uint64_t* bar, uint32_t& parity,
+                                          const float* __restrict__ src, size_t row_stride, int S, int col0, int ncol) {
+  const int SP = S + 4;
+  if (threadIdx.x == 0) mbar_expect_tx(bar, (uint32_t)(CT * S * sizeof(float)));
+  __syncthreads();
+  if (threadIdx.x < CT) {
+    const int col = min(col0 + (int)threadIdx.x, ncol - 1);
+    bulk_g2s(stage + threadIdx.x * SP, src + (size_t)col * row_stride, (uint32_t)(S * sizeof(float)), bar);
+  }
+  mbar_wait(bar, parity);
+  parity ^= 1u;
+  const int S4 = S / 4;
+  for (int i = threadIdx.x; i < S4 * CT; i += NT) {
+    const int c = i % CT, s4 = i / CT;
+    const float4 v = *reinterpret_cast<const float4*>(stage + c * SP + 4 * s4);
+    dst[(4 * s4 + 0) * CT + c] = v.x;
+    dst[(4 * s4 + 1) * CT + c] = v.y;
+    dst[(4 * s4 + 2) * CT + c] = v.z;
+    dst[(4 * s4 + 3) * CT + c] = v.w;
+  }
+}
+
+// Store src[S][CT] as rows of a [ncol][row_stride] global array (one bulk async copy per valid column).
+// The caller must __syncthreads() before (src complete) — this function syncs internally before issuing and the
+// issuing threads must call bulk_wait_read0() before `stage` is overwritten again.
+template <int CT, int NT>
+__device__ __forceinline__ void store_tile(const float* __restrict__ src, float* __restrict__ stage, float* __restrict__ dstg,
+                                           size_t row_stride, int S, int col0, int ncol) {
+  const int SP = S + 4;
+  const int S4 = S / 4;
+  for (int i = threadIdx.x; i < S4 * CT; i += NT) {
+    const int c = i % CT, s4 = i / CT;
+    float4 v;
+    v.x = src[(4 * s4 + 0) * CT + c];
+    v.y = src[(4 * s4 + 1) * CT + c];
+    v.z = src[(4 * s4 + 2) * CT + c];
+    v.w = src[(4 * s4 + 3) * CT + c];
+    *reinterpret_cast<float4*>(stage + c * SP + 4 * s4) = v;
+  }
+  fence_proxy_async();
+  __syncthreads();
+  if (threadIdx.x < CT && col0 + (int)threadIdx.x < ncol) {
+    bulk_s2g(dstg + (size_t)(col0 + threadIdx.x) * row_stride, stage + threadIdx.x * SP, (uint32_t)(S * sizeof(float)));
+  }
+  if (threadIdx.x < CT) bulk_commit();
+}
+
+}  // namespace cpz

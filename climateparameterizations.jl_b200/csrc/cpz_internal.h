@@ -1,0 +1,59 @@
+// Internal host-side structures behind the opaque handles of include/cpz.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+#include "../../include/cpz.h"
+#include "cpz_plan.h"
+
+struct cpz_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cpz_allreduce_fn allreduce = nullptr;
+  void* allreduce_user = nullptr;
+  int rank = 0, world = 1;
+  uint64_t launches = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+};
+
+struct DevBuf {
+  float* p = nullptr;
+  size_t cap = 0;  // floats
+};
+
+struct cpz_model {
+  cpz_ctx* ctx = nullptr;
+  cpz_model_desc desc;
+  size_t P = 0;
+  cpz::Plan fwd;  // forward plan (aliasing arena, free TO)
+  cpz::Plan bwd;  // adjoint plan (all activations kept)
+  bool has_bwd = false;
+  std::string bwd_err;
+  TableauD tab;
+  TimeD tm;
+  int CT = 32, NT = 256;
+  // parameters and optimiser state (device)
+  float* d_theta = nullptr;
+  float* d_m = nullptr;
+  float* d_v = nullptr;
+  float beta_pow[2] = {0.f, 0.f};  // 0 = uninitialised (set to (beta1,beta2) on the first step)
+  // grow-only device scratch
+  DevBuf b_x0, b_bcs, b_q, b_traj, b_tgt, b_ckpt, b_scr, b_part, b_red, b_out, b_w;
+};
+
+namespace cpz {
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+}  // namespace cpz
+
+#define CPZ_CUDA(call)                                        \
+  do {                                                        \
+    cudaError_t e__ = (call);                                 \
+    if (e__ != cudaSuccess) return cpz::cuda_fail(e__, #call); \
+  } while (0)

@@ -1,0 +1,349 @@
+// Host-side planner (see cpz_plan.h).
+#include "cpz_plan.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace cpz {
+
+size_t count_params(const cpz_model_desc& d) {
+  size_t P = 0;
+  for (int n = 0; n < d.n_nets; ++n)
+    for (int l = 0; l < d.nets[n].n_layers; ++l)
+      P += (size_t)d.nets[n].sizes[l] * d.nets[n].sizes[l + 1] + d.nets[n].sizes[l + 1];
+  return P;
+}
+
+bool validate_desc(const cpz_model_desc& d, std::string& err) {
+  if (d.Nz < 4 || d.Nz > 64 || d.Nz % 4 != 0) { err = "Nz must be a multiple of 4 in [4,64]"; return false; }
+  if (d.n_fields != 1 && d.n_fields != 3) { err = "n_fields must be 1 or 3"; return false; }
+  if (d.n_fields == 1) {
+    if (d.variant != CPZ_RHS_FREE_CONVECTION) { err = "n_fields=1 requires CPZ_RHS_FREE_CONVECTION"; return false; }
+    if (d.n_nets != 0 && d.n_nets != 1) { err = "T-only model takes 0 or 1 net"; return false; }
+  } else {
+    if (d.variant != CPZ_RHS_TRAIN && d.variant != CPZ_RHS_INFER) { err = "n_fields=3 requires CPZ_RHS_TRAIN or CPZ_RHS_INFER"; return false; }
+    if (d.n_nets != 0 && d.n_nets != 3) { err = "u/v/T model takes 0 or 3 nets (uw, vw, wT)"; return false; }
+    // train_NDE asserts !(mPP && CA) for the training RHS (NDE_training.jl:171)
+    if (d.variant == CPZ_RHS_TRAIN && (d.flags & CPZ_FLAG_MPP) && (d.flags & CPZ_FLAG_CA)) {
+      err = "training RHS: modified_pacanowski_philander and convective_adjustment are mutually exclusive (NDE_training.jl:171)";
+      return false;
+    }
+  }
+  const int S = d.n_fields * d.Nz;
+  for (int n = 0; n < d.n_nets; ++n) {
+    const cpz_net_desc& nd = d.nets[n];
+    if (nd.n_layers < 1 || nd.n_layers > CPZ_MAX_LAYERS) { err = "net n_layers out of range"; return false; }
+    if (nd.sizes[0] != S) { err = "net input size must be n_fields*Nz"; return false; }
+    if (nd.sizes[nd.n_layers] != d.Nz - 1) { err = "net output size must be Nz-1 (interior faces)"; return false; }
+    for (int l = 0; l <= nd.n_layers; ++l)
+      if (nd.sizes[l] < 1 || nd.sizes[l] > 4096) { err = "layer width out of range [1,4096]"; return false; }
+    for (int l = 0; l < nd.n_layers; ++l)
+      if (nd.act[l] < 0 || nd.act[l] > CPZ_ACT_TANH) { err = "unknown activation"; return false; }
+  }
+  if (d.integrator < CPZ_INT_EULER || d.integrator > CPZ_INT_TSIT5) { err = "unknown integrator"; return false; }
+  if (d.n_steps < 1 || d.n_substeps < 1 || d.ckpt_stride < 1 || d.save_stride < 0) { err = "bad time-stepping fields"; return false; }
+  if (!(d.dt > 0.f)) { err = "dt must be positive"; return false; }
+  for (int i = 0; i < 6; ++i)
+    if (!(d.sigma[i] != 0.f)) { err = "sigma must be non-zero"; return false; }
+  if (!(d.H > 0.f) || !(d.tau > 0.f)) { err = "H and tau must be positive"; return false; }
+  return true;
+}
+
+void fill_tableau(int integrator, TableauD& t) {
+  std::memset(&t, 0, sizeof(t));
+  if (integrator == CPZ_INT_EULER) {
+    t.n_stages = 1;
+    t.b[0] = 1.f;
+  } else if (integrator == CPZ_INT_RK4) {
+    t.n_stages = 4;
+    t.a[1][0] = 0.5f; t.a[2][1] = 0.5f; t.a[3][2] = 1.f;
+    t.b[0] = (float)(1.0 / 6); t.b[1] = (float)(1.0 / 3); t.b[2] = (float)(1.0 / 3); t.b[3] = (float)(1.0 / 6);
+    t.c[1] = 0.5f; t.c[2] = 0.5f; t.c[3] = 1.f;
+  } else {
+    // Tsit5 (Tsitouras 2011; OrdinaryDiffEq.jl). The 7th (FSAL) stage has b7 = 0 and is not part of the step map.
+    t.n_stages = 6;
+    const double a[6][5] = {
+        {0, 0, 0, 0, 0},
+        {0.161, 0, 0, 0, 0},
+        {-0.008480655492356989, 0.335480655492357, 0, 0, 0},
+        {2.8971530571054935, -6.359448489975075, 4.3622954328695815, 0, 0},
+        {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 0},
+        {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383}};
+    const double b[6] = {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774};
+    const double c[6] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0};
+    for (int i = 0; i < 6; ++i) {
+      for (int j = 0; j < 5; ++j) t.a[i][j] = (float)a[i][j];
+      t.b[i] = (float)b[i];
+      t.c[i] = (float)c[i];
+    }
+  }
+}
+
+namespace {
+
+int lds_count(int TO, bool ws) {
+  if (!ws) return TO;
+  if (TO % 4 == 0) return TO / 4;
+  if (TO % 2 == 0) return TO / 2;
+  return TO;
+}
+
+// Estimated issue cycles of one phase on the busiest SM sub-partition for a uniform TO.
+double phase_cost(const std::vector<std::pair<int, int>>& kn /*(K,N) per gemm*/, int TO, int NCG, int NT, bool ws) {
+  long tiles = 0;
+  double per_tile = 0;
+  for (auto& g : kn) {
+    const int n_og = (g.second + TO - 1) / TO;
+    tiles += (long)n_og * NCG;
+    per_tile = std::max(per_tile, (double)g.first * (4.0 * TO + 1 + lds_count(TO, ws)) + 12.0 * TO);
+  }
+  const int warps = NT / 32;
+  double smsp[4] = {0, 0, 0, 0};
+  for (int w = 0; w < warps; ++w) {
+    const long first = (long)w * 32;
+    if (first >= tiles) break;
+    const long cnt = (tiles - first + NT - 1) / NT;  // tiles of the first lane of the warp = the warp's maximum
+    smsp[w % 4] += cnt * per_tile;
+  }
+  return std::max(std::max(smsp[0], smsp[1]), std::max(smsp[2], smsp[3]));
+}
+
+}  // namespace
+
+bool build_plan(const cpz_model_desc& d, const PlanOptions& opt, Plan& out, std::string& err) {
+  if (!validate_desc(d, err)) return false;
+  if (opt.CT % 4 != 0 || opt.CT < 4) { err = "CT must be a positive multiple of 4"; return false; }
+  Plan pl;
+  ModelD& M = pl.M;
+  std::memset(&M, 0, sizeof(M));
+  const int N = d.Nz;
+  M.Nz = N; M.nf = d.n_fields; M.S = d.n_fields * N;
+  M.variant = d.variant; M.flags = (int)d.flags;
+  M.n_nets = d.n_nets;
+  M.nbc = d.n_fields == 3 ? 6 : 2;
+  M.P = (int)count_params(d);
+  const int NCG = opt.CT / 4;
+
+  // ---- folded constants (double -> float once) ----
+  RhsC& rc = M.rc;
+  const double H = d.H, tau = d.tau;
+  const double mu[6] = {d.mu[0], d.mu[1], d.mu[2], d.mu[3], d.mu[4], d.mu[5]};
+  const double sg[6] = {d.sigma[0], d.sigma[1], d.sigma[2], d.sigma[3], d.sigma[4], d.sigma[5]};
+  for (int q = 0; q < 3; ++q) {
+    rc.A[q] = (float)(tau / H * sg[3 + q] / sg[q]);
+    rc.c[q] = (float)(sg[q] / sg[3 + q] / H);
+    rc.z0[q] = (float)(-mu[3 + q] / sg[3 + q]);
+  }
+  rc.cor_u_s = (float)((double)d.f * tau * sg[1] / sg[0]);
+  rc.cor_u_m = (float)((double)d.f * tau * mu[1] / sg[0]);
+  rc.cor_v_s = (float)((double)d.f * tau * sg[0] / sg[1]);
+  rc.cor_v_m = (float)((double)d.f * tau * mu[0] / sg[1]);
+  rc.BzC = (float)(H * (double)d.g * (double)d.alpha * sg[2]);
+  rc.sig_u = d.sigma[0]; rc.sig_v = d.sigma[1];
+  rc.nu0 = d.nu0; rc.nu_m = d.nu_m; rc.Ric = d.Ric;
+  rc.inv_dRi = (float)(1.0 / (double)d.dRi);
+  rc.inv_Pr = (float)(1.0 / (double)d.Pr);
+  rc.kappa = d.kappa; rc.eps = d.eps; rc.K_ca = d.K_ca;
+  rc.Nf = (float)N;
+  rc.di_w = (float)(2.0 * M_PI * tau / (double)(d.diurnal_period > 0.f ? d.diurnal_period : 86400.f));
+  rc.di_amp = (float)(1.0 / ((double)d.alpha * (double)d.g));
+  rc.mu_wT = d.mu[5];
+  rc.inv_sig_wT = (float)(1.0 / sg[5]);
+
+  // ---- theta offsets (destructure order: nets concatenated; per layer vec(W) then b) ----
+  struct L { int net, layer, K, Nn, act, w_off, b_off; };
+  std::vector<std::vector<L>> nets(d.n_nets);
+  int off = 0, maxL = 0;
+  bool same_depth = true;
+  for (int n = 0; n < d.n_nets; ++n) {
+    for (int l = 0; l < d.nets[n].n_layers; ++l) {
+      L x{n, l, d.nets[n].sizes[l], d.nets[n].sizes[l + 1], d.nets[n].act[l], off, 0};
+      off += x.K * x.Nn;
+      x.b_off = off;
+      off += x.Nn;
+      nets[n].push_back(x);
+    }
+    maxL = std::max(maxL, d.nets[n].n_layers);
+    if (d.nets[n].n_layers != d.nets[0].n_layers) same_depth = false;
+  }
+  if (d.n_nets * maxL > CPZ_MAX_GEMM) { err = "too many layers"; return false; }
+
+  const int flux_rows = d.n_fields * (N + 1);
+
+  // ---- activation arena + phase schedule ----
+  auto plan_schedule = [&](bool layer_major, std::vector<std::vector<int>>& phases /*gemm ids*/, std::vector<GemmD>& gemms,
+                           int& arena_rows, int nn_off[3], int& flux_off) {
+    phases.clear(); gemms.clear();
+    nn_off[0] = nn_off[1] = nn_off[2] = -1;
+    if (d.n_nets == 0) { arena_rows = flux_rows; flux_off = 0; return; }
+    auto mk = [&](const L& x) {
+      GemmD g; std::memset(&g, 0, sizeof(g));
+      g.K = x.K; g.N = x.Nn; g.act = x.act; g.w_off = x.w_off; g.b_off = x.b_off; g.net = x.net; g.layer = x.layer;
+      return g;
+    };
+    if (opt.keep_all) {
+      // every (net, layer) output keeps its own rows; phases layer-major when depths agree, else net-major
+      int row = 0;
+      std::vector<std::vector<int>> out_row(d.n_nets);
+      for (int n = 0; n < d.n_nets; ++n)
+        for (auto& x : nets[n]) { out_row[n].push_back(row); row += x.Nn; }
+      flux_off = row; row += flux_rows;
+      arena_rows = row;
+      for (int n = 0; n < d.n_nets; ++n) nn_off[n] = out_row[n].back();
+      if (same_depth) {
+        for (int l = 0; l < maxL; ++l) {
+          std::vector<int> ph;
+          for (int n = 0; n < d.n_nets; ++n) {
+            GemmD g = mk(nets[n][l]);
+            g.in_off = l == 0 ? -1 : out_row[n][l - 1];
+            g.out_off = out_row[n][l];
+            ph.push_back((int)gemms.size()); gemms.push_back(g);
+          }
+          phases.push_back(ph);
+        }
+      } else {
+        for (int n = 0; n < d.n_nets; ++n)
+          for (int l = 0; l < (int)nets[n].size(); ++l) {
+            GemmD g = mk(nets[n][l]);
+            g.in_off = l == 0 ? -1 : out_row[n][l - 1];
+            g.out_off = out_row[n][l];
+            phases.push_back({(int)gemms.size()}); gemms.push_back(g);
+          }
+      }
+      return;
+    }
+    if (layer_major) {
+      int width[2] = {0, 0};
+      for (int l = 0; l < maxL; ++l) {
+        int w = 0;
+        for (int n = 0; n < d.n_nets; ++n) w += nets[n][l].Nn;
+        width[l & 1] = std::max(width[l & 1], w);
+      }
+      const int nn_par = (maxL - 1) & 1, other = nn_par ^ 1;
+      width[other] = std::max(width[other], flux_rows);
+      const int base[2] = {0, width[0]};
+      arena_rows = width[0] + width[1];
+      flux_off = base[other];
+      for (int l = 0; l < maxL; ++l) {
+        std::vector<int> ph;
+        int o = base[l & 1], oprev = l > 0 ? base[(l - 1) & 1] : 0;
+        for (int n = 0; n < d.n_nets; ++n) {
+          GemmD g = mk(nets[n][l]);
+          g.in_off = l == 0 ? -1 : oprev;
+          g.out_off = o;
+          if (l == maxL - 1) nn_off[n] = o;
+          o += g.N;
+          if (l > 0) oprev += nets[n][l - 1].Nn;
+          ph.push_back((int)gemms.size()); gemms.push_back(g);
+        }
+        phases.push_back(ph);
+      }
+    } else {
+      // net-major: final outputs persist in rows [0, n_nets*(N-1)), hidden layers ping-pong behind them
+      const int nn_rows = d.n_nets * (N - 1);
+      int width[2] = {0, 0};
+      for (int n = 0; n < d.n_nets; ++n)
+        for (int l = 0; l + 1 < (int)nets[n].size(); ++l) width[l & 1] = std::max(width[l & 1], nets[n][l].Nn);
+      if (width[0] + width[1] < flux_rows) width[0] = flux_rows - width[1];
+      const int base[2] = {nn_rows, nn_rows + width[0]};
+      arena_rows = nn_rows + width[0] + width[1];
+      flux_off = nn_rows;
+      for (int n = 0; n < d.n_nets; ++n) {
+        nn_off[n] = n * (N - 1);
+        const int Ln = (int)nets[n].size();
+        for (int l = 0; l < Ln; ++l) {
+          GemmD g = mk(nets[n][l]);
+          g.in_off = l == 0 ? -1 : base[(l - 1) & 1];
+          g.out_off = l == Ln - 1 ? nn_off[n] : base[l & 1];
+          phases.push_back({(int)gemms.size()}); gemms.push_back(g);
+        }
+      }
+    }
+  };
+
+  // weights in shared memory?
+  auto weight_floats = [&](const std::vector<GemmD>& gemms) {
+    size_t f = 0;
+    for (auto& g : gemms) { f = (f + 3) & ~(size_t)3; f += (size_t)g.K * g.Npad; f = (f + 3) & ~(size_t)3; f += g.Npad; }
+    return (f + 3) & ~(size_t)3;
+  };
+
+  std::vector<std::vector<int>> phases;
+  std::vector<GemmD> gemms;
+  int arena_rows = 0, nn_off[3], flux_off = 0;
+  bool chosen = false;
+  const int arena_mult = opt.keep_all ? 2 : 1;  // adjoint keeps pre-activations too
+  for (int attempt = 0; attempt < 2 && !chosen; ++attempt) {
+    const bool layer_major = attempt == 0 && same_depth;
+    if (attempt == 0 && !same_depth) continue;
+    plan_schedule(layer_major, phases, gemms, arena_rows, nn_off, flux_off);
+    // choose TO per phase
+    for (auto& ph : phases) {
+      std::vector<std::pair<int, int>> kn;
+      for (int gi : ph) kn.push_back({gemms[gi].K, gemms[gi].N});
+      int best = 4; double bc = 1e300;
+      const int cand_f[] = {1, 2, 3, 4, 5, 6, 8};
+      const int cand_b[] = {4, 8};
+      const int* cand = opt.keep_all ? cand_b : cand_f;
+      const int nc = opt.keep_all ? 2 : 7;
+      for (int ci = 0; ci < nc; ++ci) {
+        const double c1 = phase_cost(kn, cand[ci], NCG, opt.NT, true);
+        if (c1 < bc) { bc = c1; best = cand[ci]; }
+      }
+      int tb = 0;
+      for (int gi : ph) {
+        GemmD& g = gemms[gi];
+        g.TO = best;
+        g.n_og = (g.N + best - 1) / best;
+        g.Npad = g.n_og * best;
+        g.tile_begin = tb;
+        tb += g.n_og * NCG;
+      }
+    }
+    const size_t arena_b = (size_t)arena_rows * opt.CT * sizeof(float) * arena_mult;
+    const size_t wb = weight_floats(gemms) * sizeof(float);
+    if (arena_b + opt.other_smem_bytes <= opt.smem_budget || attempt == 1 || opt.keep_all) {
+      pl.layer_major = layer_major;
+      pl.arena_bytes = arena_b;
+      M.w_in_smem = (arena_b + opt.other_smem_bytes + wb <= opt.smem_budget) ? 1 : 0;
+      if (opt.keep_all && !M.w_in_smem) {
+        // adjoint tiles use float4 weight rows either way; nothing else to change
+      }
+      pl.smem_weight_bytes = M.w_in_smem ? wb : 0;
+      chosen = true;
+    }
+  }
+  if (pl.arena_bytes + opt.other_smem_bytes > opt.smem_budget) {
+    err = "model does not fit the shared-memory budget for this column tile";
+    return false;
+  }
+  // shared weight offsets
+  {
+    size_t f = 0;
+    for (auto& g : gemms) {
+      f = (f + 3) & ~(size_t)3; g.sw_off = (int)f; f += (size_t)g.K * g.Npad;
+      f = (f + 3) & ~(size_t)3; g.sb_off = (int)f; f += g.Npad;
+    }
+    M.smem_w_floats = M.w_in_smem ? (int)((f + 3) & ~(size_t)3) : 0;
+  }
+  M.n_gemm = (int)gemms.size();
+  M.n_phase = (int)phases.size();
+  if (M.n_gemm > CPZ_MAX_GEMM || M.n_phase > CPZ_MAX_PHASE) { err = "too many layers"; return false; }
+  for (int i = 0; i < M.n_gemm; ++i) M.gemm[i] = gemms[i];
+  for (int p = 0; p < M.n_phase; ++p) {
+    M.phase[p].g0 = phases[p].front();
+    M.phase[p].g1 = phases[p].back() + 1;
+    int nt = 0;
+    for (int gi : phases[p]) nt += gemms[gi].n_og * NCG;
+    M.phase[p].n_tiles = nt;
+  }
+  M.arena_floats = arena_rows;
+  for (int n = 0; n < 3; ++n) M.nn_off[n] = nn_off[n];
+  M.flux_off = flux_off;
+  out = pl;
+  return true;
+}
+
+}  // namespace cpz

@@ -129,6 +129,8 @@ typedef int (*cpz_allreduce_fn)(void* user, float* buf, size_t n, void* stream);
 int cpz_version(void);                                   /* major*100+minor */
 const char* cpz_last_error(void);                        /* thread-local message of the last failure */
 int cpz_device_count(int* n);                            /* usable CUDA devices (0 is not an error here) */
+size_t cpz_sizeof_model_desc(void);                      /* sizeof(cpz_model_desc) the library was built with (ABI check) */
+size_t cpz_sizeof_closure_desc(void);
 /* Create a context on CUDA device `device`. `stream` is a cudaStream_t to enqueue on (e.g. torch's current
  * stream) or NULL for a library-owned non-blocking stream. */
 int cpz_ctx_create(int device, void* stream, cpz_ctx** out);
