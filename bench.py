@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the NDE column engine (BASELINE.json: column-steps/s at Nz=32).
+
+Workload at every N: BASELINE config 2 per GPU — wind_mixing u/v/T NDE forward solve (inference RHS, mPP base,
+3 x (96->50 mish->20 mish->31) nets, Tsit5 fixed step with the sub-steps explicit diffusion needs), 4,096 synthetic
+columns x 1,152 steps, every frame saved (1.81 GB of trajectory per solve, larger than L2) — weak scaling: columns
+shard across ranks with no data-path collective. One bench "step" = one full solve of the rank's column batch.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0). `value` = device-resident throughput, `e2e` = through the host-pointer C ABI call
+(pinned host buffers, H2D + D2H inside the timed region). Extra objects: roofline (HBM, the contract's key),
+roofline_compute (FP32 SIMT pipe, the roof that actually binds this kernel), adjoint (fwd+adjoint training step,
+BASELINE config 3 slice), nn_free (the HBM-fair mPP-only variant), cpu_baseline (the oracle on host cores).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+NCOL = 4096
+NSTEPS = 1152
+FP32_LANES_PER_SM = 128
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), d.get("sm_max_mhz", 1965.0), "measured"
+    return 6650.0, 1965.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+                for i, nm in enumerate(names):
+                    if r[5 + i].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:  # noqa: BLE001
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(syn, RHS_INFER, n_steps):
+    d = syn.wind_mixing_desc(variant=RHS_INFER, net="uvT_small", n_steps=n_steps, save_stride=1)
+    theta = syn.theta_init(d, seed=42, scale=1e-5)
+    return d, theta
+
+
+def flops_per_colstep(d):
+    mlp = 2 * sum(n.macs for n in d.nets)
+    return (mlp + 1200) * d.rhs_evals_per_step
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path. The Julia reference cannot run here (no julia
+    binary, no LES data), so this times the oracle port (restated-reference CPU) with all host threads on a bounded
+    sample of the same workload."""
+    if rank != 0:
+        return
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cpzload
+    cpzload.load()
+    from cpz_b200 import synthetic as syn
+    from cpz_b200.desc import RHS_INFER
+    from oracle import nde
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ncol_s, nsteps_s = 512, 12
+    d, theta = build_workload(syn, RHS_INFER, nsteps_s)
+    x0, bcs = syn.columns(d, ncol_s)
+    th, x, b = torch.tensor(theta), torch.tensor(x0), torch.tensor(bcs)
+    times = []
+    with torch.no_grad():
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            nde.solve(d, th, x, b, None)
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+    tot = sum(times)
+    val = ncol_s * nsteps_s * len(times) / tot
+    sample = f"{ncol_s} columns x {nsteps_s} steps (x{d.n_substeps} sub-steps, Tsit5) per step, FP32 torch-CPU oracle batched over columns"
+    line = {
+        "impl": "reference", "metric": "column-steps/sec (forward)", "value": val, "unit": "column-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE config 2 (wind_mixing u/v/T forward, Nz=32, small nets, Tsit5) — bounded sample",
+                   "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "column-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "column-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference Julia path cannot run in this image (no julia, no LES data); restated-reference CPU oracle timed instead",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(syn, RHS_INFER):
+    """Bounded oracle run on the host cores (about 10-30 s)."""
+    import torch
+    from oracle import nde
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ncol_s, nsteps_s = 512, 12
+    d, theta = build_workload(syn, RHS_INFER, nsteps_s)
+    x0, bcs = syn.columns(d, ncol_s)
+    th, x, b = torch.tensor(theta), torch.tensor(x0), torch.tensor(bcs)
+    with torch.no_grad():
+        nde.solve(d, th, x, b, None)  # warm-up
+        reps, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < 10.0 and reps < 20:
+            nde.solve(d, th, x, b, None)
+            reps += 1
+        el = time.perf_counter() - t0
+    return {"value": ncol_s * nsteps_s * reps / el, "unit": "column-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{reps} x ({ncol_s} columns x {nsteps_s} steps x {d.n_substeps} sub-steps), FP32 torch-CPU oracle batched over columns"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip adjoint / nn_free / cpu_baseline side measurements")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import cpzload
+    cpzload.load()
+    from cpz_b200 import engine, synthetic as syn
+    from cpz_b200.desc import RHS_INFER, RHS_TRAIN
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # kernels are launched on a torch-owned stream so that torch.cuda.Event brackets them
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    ctx = engine.Context(local_rank, tstream.cuda_stream)
+    d, theta = build_workload(syn, RHS_INFER, NSTEPS)
+    model = engine.Model(ctx, d, theta)
+    S, n_saved = d.S, d.n_saved
+    x0, bcs = syn.columns(d, NCOL, seed=1000 + rank)
+    x0_d, bcs_d = torch.tensor(x0, device="cuda"), torch.tensor(bcs, device="cuda")
+    traj_d = torch.empty((NCOL, n_saved, S), dtype=torch.float32, device="cuda")
+
+    # ---- device-resident timing (value) ----
+    for _ in range(args.warmup):
+        model.solve_dev(x0_d, bcs_d, traj_d)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_all0 = torch.cuda.Event(enable_timing=True); t_all1 = torch.cuda.Event(enable_timing=True)
+    t_all0.record()
+    for e0, e1 in evs:
+        e0.record()
+        model.solve_dev(x0_d, bcs_d, traj_d)
+        e1.record()
+    t_all1.record()
+    barrier()
+    launches = ctx.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = t_all0.elapsed_time(t_all1)
+    kern_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in evs]))
+    t = torch.tensor([ms_total], device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    colsteps_per_step = NCOL * NSTEPS * world
+    value = colsteps_per_step * args.steps / (ms_total * 1e-3)
+
+    # ---- end-to-end through the host-pointer C ABI (pinned host buffers; H2D + D2H inside the timed region) ----
+    x0_h = torch.tensor(x0).pin_memory(); bcs_h = torch.tensor(bcs).pin_memory()
+    traj_h = torch.empty((NCOL, n_saved, S), dtype=torch.float32).pin_memory()
+    e2e_steps = max(1, min(args.steps, 3))
+    model.solve(x0_h.numpy(), bcs_h.numpy(), out=traj_h.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        model.solve(x0_h.numpy(), bcs_h.numpy(), out=traj_h.numpy())  # synchronous on return
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = colsteps_per_step * e2e_steps / float(t.item())
+    checksum = float(traj_h[:, -1].double().abs().mean())
+
+    hbm_peak, sm_max_mhz, peak_src = peaks()
+    bytes_per_colstep = 4 * S * (n_saved / NSTEPS) + (4 * S + 4 * d.n_bc) / NSTEPS
+    ach_gbs = bytes_per_colstep * NCOL * NSTEPS / (kern_ms * 1e-3) / 1e9
+    fl = flops_per_colstep(d)
+    ach_tf = fl * NCOL * NSTEPS / (kern_ms * 1e-3) / 1e12
+    n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    sm_mhz = (clocks or {}).get("sm_mhz") or sm_max_mhz
+    peak_tf_max = n_sm * FP32_LANES_PER_SM * 2 * sm_max_mhz * 1e6 / 1e12
+    peak_tf_obs = n_sm * FP32_LANES_PER_SM * 2 * sm_mhz * 1e6 / 1e12
+
+    line = {
+        "metric": "column-steps/sec (forward)", "value": value, "unit": "column-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE config 2: wind_mixing u/v/T NDE forward solve, 4096 synthetic columns x 1152 steps per GPU, all frames saved",
+                   "Nz": 32, "columns_per_gpu": NCOL, "n_steps": NSTEPS, "n_substeps": d.n_substeps, "integrator": d.integrator,
+                   "rhs_evals_per_step": d.rhs_evals_per_step, "nets": "3 x (96->50 mish->20 mish->31), P=19563",
+                   "rhs": "inference (solve_NDE_mutating), mPP base, zero_weights BCs",
+                   "l2": "no explicit flush: each solve writes a 1.81 GB trajectory (> 126 MB L2)", "parallelism": f"columns x{world}"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "e2e": {"value": e2e_val, "unit": "column-steps/s", "h2d_bytes_per_step": int(x0_h.numel() * 4 + bcs_h.numel() * 4),
+                "d2h_bytes_per_step": int(traj_h.numel() * 4), "steps": e2e_steps, "final_state_checksum": checksum},
+        "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "solve_kernel<32,256,true>",
+                     "kernel_ms": kern_ms, "algorithmic_bytes_per_colstep": bytes_per_colstep,
+                     "note": "this workload is FP32-pipe bound (AI ~ 1200 flop/B): see roofline_compute"},
+        "roofline_compute": {"bound": "fp32_simt", "achieved": ach_tf, "unit": "TFLOP/s", "peak_at_max_clock": peak_tf_max,
+                             "peak_at_observed_clock": peak_tf_obs, "frac": ach_tf / peak_tf_obs, "flop_per_colstep": fl,
+                             "stage_evals_per_s": value * d.rhs_evals_per_step},
+    }
+    if rank == 0 and not args.no_extras:
+        try:
+            line["cpu_baseline"] = cpu_baseline(syn, RHS_INFER)
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -243,6 +243,34 @@ int cpz_model_n_saved(const cpz_model* m, int32_t* n) {
   return CPZ_OK;
 }
 
+int cpz_model_describe(const cpz_model* m, char* buf, size_t buf_len) {
+  if (!m || !buf || buf_len == 0) return fail(CPZ_ERR_INVALID, "null pointer");
+  std::string s;
+  char line[512];
+  auto dump = [&](const char* name, const Plan& pl, size_t other) {
+    const ModelD& M = pl.M;
+    snprintf(line, sizeof(line), "%s plan: CT=%d NT=%d %s weights_in_smem=%d weight_smem=%zuB arena=%zuB other=%zuB arena_rows=%d flux_off=%d\n",
+             name, m->CT, m->NT, pl.layer_major ? "layer-major" : "net-major", M.w_in_smem, pl.smem_weight_bytes, pl.arena_bytes, other,
+             M.arena_floats, M.flux_off);
+    s += line;
+    for (int p = 0; p < M.n_phase; ++p) {
+      snprintf(line, sizeof(line), "  phase %d: tiles=%d:", p, M.phase[p].n_tiles);
+      s += line;
+      for (int g = M.phase[p].g0; g < M.phase[p].g1; ++g) {
+        const GemmD& G = M.gemm[g];
+        snprintf(line, sizeof(line), " [net%d L%d K=%d N=%d TO=%d Npad=%d act=%d in=%d out=%d]", G.net, G.layer, G.K, G.N, G.TO, G.Npad, G.act, G.in_off, G.out_off);
+        s += line;
+      }
+      s += "\n";
+    }
+  };
+  dump("forward", m->fwd, solve_other_smem(m->desc, m->CT, m->tab.n_stages));
+  if (m->has_bwd) dump("adjoint", m->bwd, adjoint_other_smem(m->desc.n_fields * m->desc.Nz, m->desc.n_fields == 3 ? 6 : 2, m->CT));
+  else s += "adjoint plan: unavailable (" + m->bwd_err + ")\n";
+  snprintf(buf, buf_len, "%s", s.c_str());
+  return CPZ_OK;
+}
+
 int cpz_set_theta(cpz_model* m, const float* theta, size_t P) {
   int rc = check_model(m);
   if (rc) return rc;

@@ -22,19 +22,23 @@ enum {
 };
 enum { ACT_ID = 0, ACT_RELU = 1, ACT_MISH = 2, ACT_SWISH = 3, ACT_LEAKY = 4, ACT_TANH = 5 };
 
-// ---- activations (NNlib 0.7.20 definitions), FP32-accurate (no fast-math intrinsics) -------------------------
+// ---- activations (NNlib 0.7.20 definitions) -----------------------------------------------------------------------
+// exp via MUFU.EX2 (__expf, <= 2+|1.16x| ulp) and division via MUFU.RCP (__fdividef, 2 ulp): errors ~1e-6 relative,
+// an order of magnitude inside the 1e-5 RHS tolerance, at a quarter of the instruction count of expf + IEEE divide.
 __device__ __forceinline__ float act_fwd(int act, float x) {
   switch (act) {
     case ACT_RELU: return fmaxf(x, 0.f);
     case ACT_MISH: {  // x*tanh(softplus(x)) = x*n/(n+2), n = e^x(e^x+2)
-      if (x > 20.f) return x;
-      float e = expf(x);
-      float n = e * (e + 2.f);
-      return x * (n / (n + 2.f));
+      const float e = __expf(fminf(x, 20.f));
+      const float n = e * (e + 2.f);
+      return x * __fdividef(n, n + 2.f);
     }
-    case ACT_SWISH: return x / (1.f + expf(-x));
+    case ACT_SWISH: return __fdividef(x, 1.f + __expf(-x));
     case ACT_LEAKY: return fmaxf(0.01f * x, x);
-    case ACT_TANH: return tanhf(x);
+    case ACT_TANH: {  // 1 - 2/(e^{2x}+1)
+      const float e = __expf(2.f * fminf(x, 40.f));
+      return 1.f - __fdividef(2.f, e + 1.f);
+    }
     default: return x;
   }
 }
@@ -44,20 +48,20 @@ __device__ __forceinline__ float act_grad(int act, float z) {
   switch (act) {
     case ACT_RELU: return z > 0.f ? 1.f : 0.f;
     case ACT_MISH: {
-      if (z > 20.f) return 1.f;
-      float e = expf(z);
-      float n = e * (e + 2.f);
-      float t = n / (n + 2.f);
-      float sg = e / (1.f + e);
+      const float e = __expf(fminf(z, 20.f));
+      const float n = e * (e + 2.f);
+      const float t = __fdividef(n, n + 2.f);
+      const float sg = __fdividef(e, 1.f + e);
       return t + z * (1.f - t * t) * sg;
     }
     case ACT_SWISH: {
-      float sg = 1.f / (1.f + expf(-z));
+      const float sg = __fdividef(1.f, 1.f + __expf(-z));
       return sg + z * sg * (1.f - sg);
     }
     case ACT_LEAKY: return z > 0.f ? 1.f : 0.01f;
     case ACT_TANH: {
-      float t = tanhf(z);
+      const float e = __expf(2.f * fminf(z, 40.f));
+      const float t = 1.f - __fdividef(2.f, e + 1.f);
       return 1.f - t * t;
     }
     default: return 1.f;
@@ -103,69 +107,107 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// ---- dense layer: one 4-column x TO-output register tile --------------------------------------------------------
+// ---- dense layer: one 4-column x TO-output register tile (TO even) ---------------------------------------------
 // in:  [K][CT] shared, out: [N][CT] shared (post-activation), zout (optional): [N][CT] pre-activation.
 // WS: weights come from the shared arena (row stride Npad, zero padded) else straight from theta in global.
+// The accumulators are output PAIRS (float2) per column so the inner loop is FFMA2 (packed FP32, sm_100):
+//   acc[p][c] += (w[2p], w[2p+1]) * x[c]     -> FFMA2 R, R.F32x2, R.F32 (scalar broadcast), R.F32x2
+// per k: 1 LDS.128 (4 columns of the input row) + TO/2 LDS.64 (or TO/4 LDS.128) of the weight row, 2*TO FFMA2.
 template <int TO, bool WS, int CT, bool SAVE_Z>
 __device__ __forceinline__ void gemm_tile_fwd(const GemmD& g, const float* __restrict__ in, float* __restrict__ out,
                                               float* __restrict__ zout, const float* __restrict__ W,
                                               const float* __restrict__ bias, int cg, int og) {
+  static_assert(TO % 2 == 0, "TO must be even");
+  constexpr int TP = TO / 2;
   const int j0 = og * TO;
   const int K = g.K, N = g.N;
-  const int ldw = WS ? g.Npad : N;
-  float acc[TO][4];
-  int jo[TO];
+  float2 acc[TP][4];
+  if constexpr (WS) {
 #pragma unroll
-  for (int o = 0; o < TO; ++o) {
-    jo[o] = WS ? (j0 + o) : min(j0 + o, N - 1);
-    const float bv = WS ? bias[jo[o]] : __ldg(bias + jo[o]);
-    acc[o][0] = bv; acc[o][1] = bv; acc[o][2] = bv; acc[o][3] = bv;
-  }
-  const float* xp = in + 4 * cg;
-#pragma unroll 4
-  for (int k = 0; k < K; ++k) {
-    const float4 xv = *reinterpret_cast<const float4*>(xp + k * CT);
-    float w[TO];
-    if constexpr (WS && (TO % 4 == 0)) {
-#pragma unroll
-      for (int o = 0; o < TO; o += 4) {
-        const float4 wv = *reinterpret_cast<const float4*>(W + k * ldw + j0 + o);
-        w[o] = wv.x; w[o + 1] = wv.y; w[o + 2] = wv.z; w[o + 3] = wv.w;
-      }
-    } else if constexpr (WS && (TO % 2 == 0)) {
-#pragma unroll
-      for (int o = 0; o < TO; o += 2) {
-        const float2 wv = *reinterpret_cast<const float2*>(W + k * ldw + j0 + o);
-        w[o] = wv.x; w[o + 1] = wv.y;
-      }
-    } else if constexpr (WS) {
-#pragma unroll
-      for (int o = 0; o < TO; ++o) w[o] = W[k * ldw + jo[o]];
-    } else {
-#pragma unroll
-      for (int o = 0; o < TO; ++o) w[o] = __ldg(W + (size_t)k * ldw + jo[o]);
+    for (int p = 0; p < TP; ++p) {
+      const float2 bv = *reinterpret_cast<const float2*>(bias + j0 + 2 * p);
+      acc[p][0] = bv; acc[p][1] = bv; acc[p][2] = bv; acc[p][3] = bv;
     }
+    const float* xp = in + 4 * cg;
+    const float* wp = W + j0;
+    const int ldw = g.Npad;
+#pragma unroll 2
+    for (int k = 0; k < K; ++k) {
+      const float4 xv = *reinterpret_cast<const float4*>(xp);
+      float2 w[TP];
+      if constexpr (TO % 4 == 0) {
 #pragma unroll
-    for (int o = 0; o < TO; ++o) {
-      acc[o][0] = fmaf(w[o], xv.x, acc[o][0]);
-      acc[o][1] = fmaf(w[o], xv.y, acc[o][1]);
-      acc[o][2] = fmaf(w[o], xv.z, acc[o][2]);
-      acc[o][3] = fmaf(w[o], xv.w, acc[o][3]);
+        for (int p = 0; p < TP; p += 2) {
+          const float4 wv = *reinterpret_cast<const float4*>(wp + 2 * p);
+          w[p] = make_float2(wv.x, wv.y);
+          w[p + 1] = make_float2(wv.z, wv.w);
+        }
+      } else {
+#pragma unroll
+        for (int p = 0; p < TP; ++p) w[p] = *reinterpret_cast<const float2*>(wp + 2 * p);
+      }
+      const float2 x0 = make_float2(xv.x, xv.x), x1 = make_float2(xv.y, xv.y), x2 = make_float2(xv.z, xv.z),
+                   x3 = make_float2(xv.w, xv.w);
+#pragma unroll
+      for (int p = 0; p < TP; ++p) {
+        acc[p][0] = __ffma2_rn(w[p], x0, acc[p][0]);
+        acc[p][1] = __ffma2_rn(w[p], x1, acc[p][1]);
+        acc[p][2] = __ffma2_rn(w[p], x2, acc[p][2]);
+        acc[p][3] = __ffma2_rn(w[p], x3, acc[p][3]);
+      }
+      xp += CT;
+      wp += ldw;
+    }
+  } else {
+    int jo[TO];
+#pragma unroll
+    for (int o = 0; o < TO; ++o) jo[o] = min(j0 + o, N - 1);
+#pragma unroll
+    for (int p = 0; p < TP; ++p) {
+      const float2 bv = make_float2(__ldg(bias + jo[2 * p]), __ldg(bias + jo[2 * p + 1]));
+      acc[p][0] = bv; acc[p][1] = bv; acc[p][2] = bv; acc[p][3] = bv;
+    }
+    const float* xp = in + 4 * cg;
+    const float* wp = W;
+#pragma unroll 2
+    for (int k = 0; k < K; ++k) {
+      const float4 xv = *reinterpret_cast<const float4*>(xp);
+      float2 w[TP];
+#pragma unroll
+      for (int p = 0; p < TP; ++p) w[p] = make_float2(__ldg(wp + jo[2 * p]), __ldg(wp + jo[2 * p + 1]));
+      const float2 x0 = make_float2(xv.x, xv.x), x1 = make_float2(xv.y, xv.y), x2 = make_float2(xv.z, xv.z),
+                   x3 = make_float2(xv.w, xv.w);
+#pragma unroll
+      for (int p = 0; p < TP; ++p) {
+        acc[p][0] = __ffma2_rn(w[p], x0, acc[p][0]);
+        acc[p][1] = __ffma2_rn(w[p], x1, acc[p][1]);
+        acc[p][2] = __ffma2_rn(w[p], x2, acc[p][2]);
+        acc[p][3] = __ffma2_rn(w[p], x3, acc[p][3]);
+      }
+      xp += CT;
+      wp += N;
     }
   }
   const int act = g.act;
 #pragma unroll
-  for (int o = 0; o < TO; ++o) {
-    if (j0 + o < N) {
-      if constexpr (SAVE_Z) {
-        *reinterpret_cast<float4*>(zout + (j0 + o) * CT + 4 * cg) = make_float4(acc[o][0], acc[o][1], acc[o][2], acc[o][3]);
+  for (int p = 0; p < TP; ++p) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = j0 + 2 * p + h;
+      if (j < N) {
+        float4 z;
+        z.x = h ? acc[p][0].y : acc[p][0].x;
+        z.y = h ? acc[p][1].y : acc[p][1].x;
+        z.z = h ? acc[p][2].y : acc[p][2].x;
+        z.w = h ? acc[p][3].y : acc[p][3].x;
+        if constexpr (SAVE_Z) *reinterpret_cast<float4*>(zout + j * CT + 4 * cg) = z;
+        float4 r;
+        r.x = act_fwd(act, z.x);
+        r.y = act_fwd(act, z.y);
+        r.z = act_fwd(act, z.z);
+        r.w = act_fwd(act, z.w);
+        *reinterpret_cast<float4*>(out + j * CT + 4 * cg) = r;
       }
-      float4 r;
-      r.x = act_fwd(act, acc[o][0]);
-      r.y = act_fwd(act, acc[o][1]);
-      r.z = act_fwd(act, acc[o][2]);
-      r.w = act_fwd(act, acc[o][3]);
-      *reinterpret_cast<float4*>(out + (j0 + o) * CT + 4 * cg) = r;
     }
   }
 }
@@ -190,13 +232,12 @@ __device__ __forceinline__ void run_phase(const ModelD& M, int p, const float* _
     const float* W = WS ? wsm + g.sw_off : theta + g.w_off;
     const float* B = WS ? wsm + g.sb_off : theta + g.b_off;
     switch (g.TO) {
-      case 1: gemm_tile_fwd<1, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
       case 2: gemm_tile_fwd<2, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
-      case 3: gemm_tile_fwd<3, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
       case 4: gemm_tile_fwd<4, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
-      case 5: gemm_tile_fwd<5, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
       case 6: gemm_tile_fwd<6, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
-      default: gemm_tile_fwd<8, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
+      case 8: gemm_tile_fwd<8, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
+      case 10: gemm_tile_fwd<10, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
+      default: gemm_tile_fwd<12, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
     }
   }
 }
@@ -266,7 +307,14 @@ __device__ __forceinline__ float ri_face(const ModelD& M, const float* __restric
     GT = M.rc.Nf * (X[(2 * N + k) * CT_ + c] - X[(2 * N + k - 1) * CT_ + c]);
   }
   const float su = M.rc.sig_u * (Gu + eps), sv = M.rc.sig_v * (Gv + eps);
-  return M.rc.BzC * (GT + eps) / (su * su + sv * sv);
+  return __fdividef(M.rc.BzC * (GT + eps), su * su + sv * sv);
+}
+
+// nu = nu0 + nu_m*(1 - tanh(y))/2 with y = (Ri - Ric)/dRi, evaluated as nu0 + nu_m/(1 + e^{2y}) (identical function,
+// no cancellation for large y). NDE_training.jl:54,125
+__device__ __forceinline__ float nu_of_ri(const ModelD& M, float Ri) {
+  const float y2 = 2.f * (Ri - M.rc.Ric) * M.rc.inv_dRi;
+  return M.rc.nu0 + __fdividef(M.rc.nu_m, 1.f + __expf(y2));
 }
 
 // ---- face phase: E_q[k][c] for all faces k = 0..N ------------------------------------------------------------------
@@ -329,9 +377,9 @@ __device__ __forceinline__ void faces_phase(const ModelD& M, const float* __rest
           Ri = (r0 + r1 + r2) * (1.f / 3.f);
         } else {
           const float su = M.rc.sig_u * (Gu + eps), sv = M.rc.sig_v * (Gv + eps);
-          Ri = M.rc.BzC * (GT + eps) / (su * su + sv * sv);
+          Ri = __fdividef(M.rc.BzC * (GT + eps), su * su + sv * sv);
         }
-        const float nu = M.rc.nu0 + M.rc.nu_m * 0.5f * (1.f - tanhf((Ri - M.rc.Ric) * M.rc.inv_dRi));
+        const float nu = nu_of_ri(M, Ri);
         float nuT = nu * M.rc.inv_Pr;
         if (M.variant == RHS_INFER && (M.flags & F_CA)) {
           const float test = (M.flags & F_CA_LITERAL_U) ? Gu : GT;

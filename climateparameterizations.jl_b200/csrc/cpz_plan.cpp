@@ -86,8 +86,7 @@ namespace {
 int lds_count(int TO, bool ws) {
   if (!ws) return TO;
   if (TO % 4 == 0) return TO / 4;
-  if (TO % 2 == 0) return TO / 2;
-  return TO;
+  return TO / 2;
 }
 
 // Estimated issue cycles of one phase on the busiest SM sub-partition for a uniform TO.
@@ -97,7 +96,9 @@ double phase_cost(const std::vector<std::pair<int, int>>& kn /*(K,N) per gemm*/,
   for (auto& g : kn) {
     const int n_og = (g.second + TO - 1) / TO;
     tiles += (long)n_og * NCG;
-    per_tile = std::max(per_tile, (double)g.first * (4.0 * TO + 1 + lds_count(TO, ws)) + 12.0 * TO);
+    // per k: 2*TO FFMA2 occupy the FMA pipe for 4*TO cycles; issue slots = 2*TO + loads + 2
+    const double per_k = std::max(4.0 * TO, 2.0 * TO + 1 + lds_count(TO, ws) + 2) + 2.0;
+    per_tile = std::max(per_tile, (double)g.first * per_k + 14.0 * TO + 40.0);
   }
   const int warps = NT / 32;
   double smsp[4] = {0, 0, 0, 0};
@@ -284,10 +285,10 @@ bool build_plan(const cpz_model_desc& d, const PlanOptions& opt, Plan& out, std:
       std::vector<std::pair<int, int>> kn;
       for (int gi : ph) kn.push_back({gemms[gi].K, gemms[gi].N});
       int best = 4; double bc = 1e300;
-      const int cand_f[] = {1, 2, 3, 4, 5, 6, 8};
-      const int cand_b[] = {4, 8};
+      const int cand_f[] = {2, 4, 6, 8, 10, 12};
+      const int cand_b[] = {4, 8, 12};
       const int* cand = opt.keep_all ? cand_b : cand_f;
-      const int nc = opt.keep_all ? 2 : 7;
+      const int nc = opt.keep_all ? 3 : 6;
       for (int ci = 0; ci < nc; ++ci) {
         const double c1 = phase_cost(kn, cand[ci], NCG, opt.NT, true);
         if (c1 < bc) { bc = c1; best = cand[ci]; }

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libcpz.so")
 EXPORTS = [
     "cpz_version", "cpz_last_error", "cpz_device_count", "cpz_sizeof_model_desc", "cpz_sizeof_closure_desc", "cpz_ctx_create", "cpz_ctx_destroy", "cpz_ctx_set_allreduce",
     "cpz_ctx_synchronize", "cpz_ctx_stream", "cpz_ctx_launch_count", "cpz_model_create", "cpz_model_destroy",
-    "cpz_model_n_params", "cpz_model_n_saved", "cpz_set_theta", "cpz_get_theta", "cpz_model_set_time", "cpz_rhs",
+    "cpz_model_n_params", "cpz_model_n_saved", "cpz_model_describe", "cpz_set_theta", "cpz_get_theta", "cpz_model_set_time", "cpz_rhs",
     "cpz_rhs_dev", "cpz_solve", "cpz_solve_dev", "cpz_loss_grad", "cpz_loss_grad_dev", "cpz_train_step",
     "cpz_train_step_dev", "cpz_adam_get_state", "cpz_adam_set_state", "cpz_closure_step", "cpz_closure_step_dev",
 ]
@@ -56,6 +56,7 @@ def lib() -> C.CDLL:
     L.cpz_model_destroy.argtypes = [vp]
     L.cpz_model_n_params.argtypes = [vp, C.POINTER(sz)]
     L.cpz_model_n_saved.argtypes = [vp, C.POINTER(i32)]
+    L.cpz_model_describe.argtypes = [vp, C.c_char_p, sz]
     L.cpz_set_theta.argtypes = [vp, vp, sz]
     L.cpz_get_theta.argtypes = [vp, vp, sz]
     L.cpz_model_set_time.argtypes = [vp, i32, f32, f32, i32, i32, i32, i32]
@@ -198,6 +199,11 @@ class Model:
                 setattr(d, k, v)
         _check(lib().cpz_model_set_time(self._h, INTEGRATOR[d.integrator], d.dt, d.t0, d.n_steps, d.n_substeps,
                                         d.save_stride, d.ckpt_stride))
+
+    def describe(self) -> str:
+        buf = C.create_string_buffer(8192)
+        _check(lib().cpz_model_describe(self._h, buf, 8192))
+        return buf.value.decode()
 
     @property
     def n_saved(self) -> int:

@@ -151,6 +151,8 @@ int cpz_model_n_saved(const cpz_model* m, int32_t* n);   /* frames a solve write
  * (NDE_training.jl:11-13,37; nets concatenated uw,vw,wT). HOST pointers. */
 int cpz_set_theta(cpz_model* m, const float* theta, size_t P);
 int cpz_get_theta(cpz_model* m, float* theta, size_t P);
+/* human-readable plan (tile shapes, phases, shared-memory use) of the forward and adjoint kernels */
+int cpz_model_describe(const cpz_model* m, char* buf, size_t buf_len);
 /* change time-stepping fields (n_steps, n_substeps, dt, t0, save_stride, ckpt_stride, integrator) without rebuilding */
 int cpz_model_set_time(cpz_model* m, int32_t integrator, float dt, float t0, int32_t n_steps, int32_t n_substeps,
                        int32_t save_stride, int32_t ckpt_stride);
