@@ -1,5 +1,669 @@
+// Discrete-adjoint kernel: reverse sweep of the fixed-step Runge–Kutta solve with step checkpoints.
+//
+// For x_{n+1} = x_n + h sum_i b_i k_i, k_i = f(X_i, theta), X_i = x_n + h sum_{j<i} a_ij k_j the exact reverse is
+//   kbar_i = h (b_i xbar_{n+1} + sum_{j>i} a_ji Xbar_j),   Xbar_i = (df/dX)^T(X_i) kbar_i,
+//   thetabar += (df/dtheta)^T(X_i) kbar_i,                  xbar_n = xbar_{n+1} + sum_i Xbar_i.
+// One CTA owns CT columns: weights, activations (a and z), x, xbar, the stage input and the stage cotangent live in
+// shared memory; the six stage slots (k_j while needed, then Xbar_j) live in an L2-resident global scratch slab.
+// Replaces Zygote/DiffEqSensitivity's InterpolatingAdjoint(autojacvec=ZygoteVJP()) used at
+// wind_mixing/src/NDE_training.jl:291,304 and free_convection/src/solve.jl:4-5 (continuous adjoint there, exact
+// discrete adjoint here).
 #pragma once
 #include "cpz_device.cuh"
+#include "cpz_solve.cuh"
+
 namespace cpz {
-inline size_t adjoint_other_smem(int S, int nbc, int CT) { return ((size_t)4 * S * CT + (size_t)CT * (S + 4) + nbc * CT + CT + 64) * sizeof(float); }
+
+struct AdjArgs {
+  const float* theta;
+  const float* bcs;
+  const float* Q;
+  const float* targets;  // [ncol][n_saved][S]
+  const float* ckpt;     // [n_tiles][n_ckpt][S][CT]
+  float* kslots;         // [grid][n_stages][S][CT]
+  float* segx;           // [grid][seg_len][S][CT]
+  float* gpart;          // [grid][P]   (zeroed by the host)
+  float* lpart;          // [grid][8]   (zeroed by the host)
+  int ncol, n_saved, n_ckpt, n_tiles, seg_len;
+  float w[6];
+  float inv_prof, inv_grad;  // 1/(Nz*n_saved*ncol_global), 1/((Nz+1)*n_saved*ncol_global)
+};
+
+struct AdjSmem {
+  int w, xs, xbar, xin, xb, arena, zarena, bcf, qs, red, total_floats;
+};
+__host__ __device__ inline AdjSmem adjoint_smem_layout(const ModelD& M, int CT) {
+  AdjSmem L;
+  int o = 0;
+  L.w = o; o += M.w_in_smem ? M.smem_w_floats : 0;
+  L.xs = o; o += M.S * CT;
+  L.xbar = o; o += M.S * CT;
+  L.xin = o; o += CT * (M.S + 4);  // stage input; doubles as transpose staging
+  L.xb = o; o += M.S * CT;         // kbar_i, then Xbar_i; target frame at step boundaries
+  L.arena = o; o += M.arena_floats * CT;
+  L.zarena = o; o += M.flux_off * CT;  // pre-activations / deltas of every layer output row
+  L.bcf = o; o += M.nbc * CT;
+  L.qs = o; o += CT;
+  L.red = o; o += 64;
+  L.total_floats = o + 4;
+  return L;
 }
+inline size_t adjoint_other_smem(int S, int nbc, int CT) {
+  return ((size_t)3 * S * CT + (size_t)CT * (S + 4) + (size_t)nbc * CT + CT + 64 + 4) * sizeof(float);
+}
+
+// ---- VJP of the face fluxes ------------------------------------------------------------------------------------------
+// Reads kbar [S][CT] and the stage input X; writes the cotangent of the last-layer NN outputs into `nnbar` rows
+// (zarena at M.nn_off) and the cotangent of the face gradients Gbar_q[face][c] into `gbar` (arena flux rows).
+template <int CT, int NT>
+__device__ __forceinline__ void faces_vjp(const ModelD& M, const float* __restrict__ X, const float* __restrict__ kbar,
+                                          float* __restrict__ zarena, float* __restrict__ gbar) {
+  const int N = M.Nz, nfaces = N + 1;
+  const bool has_nn = M.n_nets > 0;
+  if (M.variant == RHS_FC) {
+    const float AN = M.rc.A[2] * M.rc.Nf;
+    float* nb = has_nn ? zarena + M.nn_off[0] * CT : nullptr;
+    for (int i = threadIdx.x; i < nfaces * CT; i += NT) {
+      const int f = i / CT, c = i - f * CT;
+      float g = 0.f;
+      if (f > 0 && f < N) {
+        const float eb = AN * (kbar[f * CT + c] - kbar[(f - 1) * CT + c]);
+        if (has_nn) nb[(f - 1) * CT + c] = eb;
+        if (M.flags & F_CA) {
+          const float G = M.rc.Nf * (X[f * CT + c] - X[(f - 1) * CT + c]);
+          if (M.rc.K_ca * G < 0.f) g = -M.rc.K_ca * eb;
+        }
+      }
+      gbar[i] = g;
+    }
+    return;
+  }
+  const bool mpp = (M.flags & F_MPP) || M.variant == RHS_INFER;
+  const float eps = M.variant == RHS_TRAIN ? M.rc.eps : 0.f;
+  for (int i = threadIdx.x; i < nfaces * CT; i += NT) {
+    const int f = i / CT, c = i - f * CT;
+    float gb[3] = {0.f, 0.f, 0.f};
+    if (f > 0 && f < N) {
+      float eb[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        eb[q] = M.rc.A[q] * M.rc.Nf * (kbar[(q * N + f) * CT + c] - kbar[(q * N + f - 1) * CT + c]);
+        if (has_nn) zarena[(M.nn_off[q] + f - 1) * CT + c] = eb[q];
+      }
+      const float Gu = M.rc.Nf * (X[f * CT + c] - X[(f - 1) * CT + c]);
+      const float Gv = M.rc.Nf * (X[(N + f) * CT + c] - X[(N + f - 1) * CT + c]);
+      const float GT = M.rc.Nf * (X[(2 * N + f) * CT + c] - X[(2 * N + f - 1) * CT + c]);
+      if (mpp) {
+        const float gu = Gu + eps, gv = Gv + eps, gT = GT + eps;
+        const float su = M.rc.sig_u * gu, sv = M.rc.sig_v * gv;
+        const float S2 = su * su + sv * sv;
+        const float iS2 = __fdividef(1.f, S2);
+        const float Ri = M.rc.BzC * gT * iS2;
+        const float y2 = 2.f * (Ri - M.rc.Ric) * M.rc.inv_dRi;
+        const float s = __fdividef(1.f, 1.f + __expf(y2));
+        const float nu = M.rc.nu0 + M.rc.nu_m * s;
+        float nuT = nu * M.rc.inv_Pr, dnuT = M.rc.inv_Pr;
+        if (M.variant == RHS_INFER && (M.flags & F_CA)) {
+          const float test = (M.flags & F_CA_LITERAL_U) ? Gu : GT;
+          if (!(test > 0.f)) { nuT = M.rc.kappa; dnuT = 0.f; }
+        }
+        const float Du = -eb[0], Dv = -eb[1], DT = -eb[2];  // cotangents of the diffusive fluxes
+        gb[0] = M.rc.c[0] * nu * Du;
+        gb[1] = M.rc.c[1] * nu * Dv;
+        gb[2] = M.rc.c[2] * nuT * DT;
+        const float nub = M.rc.c[0] * Gu * Du + M.rc.c[1] * Gv * Dv + dnuT * M.rc.c[2] * GT * DT;
+        // s(1-s) underflows cleanly to 0 for |y| large; inf*0 cannot occur because s is in [0,1]
+        const float Rib = nub * (-2.f * M.rc.inv_dRi * M.rc.nu_m * s * (1.f - s));
+        gb[2] += Rib * M.rc.BzC * iS2;
+        const float t = -Rib * Ri * iS2 * 2.f;
+        gb[0] += t * M.rc.sig_u * su;
+        gb[1] += t * M.rc.sig_v * sv;
+      } else if (M.flags & F_CA) {
+        if (GT < 0.f) gb[2] = -M.rc.c[2] * M.rc.kappa * eb[2];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) gbar[(q * nfaces + f) * CT + c] = gb[q];
+  }
+}
+
+// Direct (non-MLP) part of Xbar_i = (df/dX)^T kbar_i, written IN PLACE over kbar (each thread owns (k,c) of all fields).
+template <int CT, int NT>
+__device__ __forceinline__ void centres_vjp(const ModelD& M, float* __restrict__ kbar_xb, const float* __restrict__ gbar) {
+  const int N = M.Nz, nfaces = N + 1;
+  for (int it = threadIdx.x; it < N * CT; it += NT) {
+    const int k = it / CT, c = it - k * CT;
+    if (M.variant == RHS_FC) {
+      const float g0 = (k >= 1) ? gbar[k * CT + c] : 0.f;
+      const float g1 = (k + 1 <= N - 1) ? gbar[(k + 1) * CT + c] : 0.f;
+      kbar_xb[k * CT + c] = M.rc.Nf * (g0 - g1);
+      continue;
+    }
+    const float kbu = kbar_xb[k * CT + c], kbv = kbar_xb[(N + k) * CT + c];
+    float r[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const float g0 = (k >= 1) ? gbar[(q * nfaces + k) * CT + c] : 0.f;
+      const float g1 = (k + 1 <= N - 1) ? gbar[(q * nfaces + k + 1) * CT + c] : 0.f;
+      r[q] = M.rc.Nf * (g0 - g1);
+    }
+    r[0] -= M.rc.cor_v_s * kbv;  // dv/dt = ... - cor_v_s*u
+    r[1] += M.rc.cor_u_s * kbu;  // du/dt = ... + cor_u_s*v
+#pragma unroll
+    for (int q = 0; q < 3; ++q) kbar_xb[(q * N + k) * CT + c] = r[q];
+  }
+}
+
+// ---- MLP backward tiles ------------------------------------------------------------------------------------------------
+// Backward-data for one gemm: abar[k][c] = sum_j W[k][j] delta[j][c] on a 4-row x 4-column tile.
+// Returns the tile in acc (pairs over columns); the caller applies act' or accumulates into Xbar.
+template <bool WS, int CT>
+__device__ __forceinline__ void bwd_data_tile(const GemmD& g, const float* __restrict__ W, const float* __restrict__ delta,
+                                              int k0, int cg, float2 (&acc)[4][2]) {
+  const int K = g.K, N = g.N;
+  const int ldw = WS ? g.Npad : N;
+  int kr[4];
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) kr[kk] = min(k0 + kk, K - 1) * ldw;
+  const float* dp = delta + 4 * cg;
+  const int N4 = WS ? (N & ~3) : 0;
+  for (int j = 0; j < N4; j += 4) {
+    float4 d[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) d[jj] = *reinterpret_cast<const float4*>(dp + (j + jj) * CT);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float4 wv = *reinterpret_cast<const float4*>(W + kr[kk] + j);
+      const float wj[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        acc[kk][0] = __ffma2_rn(make_float2(d[jj].x, d[jj].y), make_float2(wj[jj], wj[jj]), acc[kk][0]);
+        acc[kk][1] = __ffma2_rn(make_float2(d[jj].z, d[jj].w), make_float2(wj[jj], wj[jj]), acc[kk][1]);
+      }
+    }
+  }
+  for (int j = N4; j < N; ++j) {
+    const float4 d = *reinterpret_cast<const float4*>(dp + j * CT);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float wv = WS ? W[kr[kk] + j] : __ldg(W + kr[kk] + j);
+      acc[kk][0] = __ffma2_rn(make_float2(d.x, d.y), make_float2(wv, wv), acc[kk][0]);
+      acc[kk][1] = __ffma2_rn(make_float2(d.z, d.w), make_float2(wv, wv), acc[kk][1]);
+    }
+  }
+}
+
+// Weight gradient of one gemm on a 4(k) x 4(j) tile: dW[k][j] += sum_c a[k][c] delta[j][c]; RED into gpart (destructure
+// order, W is [K][N] row-major there).
+template <int CT>
+__device__ __forceinline__ void bwd_weight_tile(const GemmD& g, const float* __restrict__ a, const float* __restrict__ delta,
+                                                int k0, int j0, float* __restrict__ gW) {
+  const int K = g.K, N = g.N;
+  float2 acc[4][4];
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) acc[kk][jj] = make_float2(0.f, 0.f);
+  int kr[4], jr[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) { kr[t] = min(k0 + t, K - 1) * CT; jr[t] = min(j0 + t, N - 1) * CT; }
+#pragma unroll 2
+  for (int c = 0; c < CT; c += 4) {
+    float4 av[4], dv[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      av[t] = *reinterpret_cast<const float4*>(a + kr[t] + c);
+      dv[t] = *reinterpret_cast<const float4*>(delta + jr[t] + c);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        acc[kk][jj] = __ffma2_rn(make_float2(av[kk].x, av[kk].y), make_float2(dv[jj].x, dv[jj].y), acc[kk][jj]);
+        acc[kk][jj] = __ffma2_rn(make_float2(av[kk].z, av[kk].w), make_float2(dv[jj].z, dv[jj].w), acc[kk][jj]);
+      }
+  }
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+      if (k0 + kk < K && j0 + jj < N) atomicAdd(gW + (size_t)(k0 + kk) * N + j0 + jj, acc[kk][jj].x + acc[kk][jj].y);
+}
+
+// Backward through layer index `l` of every net that has it: weight/bias gradients, then delta of the previous layer
+// (or the accumulation of W_0 delta_0 into Xbar for l == 0). One block barrier must follow.
+template <bool WS, int CT, int NT>
+__device__ __forceinline__ void mlp_backward_layer(const ModelD& M, int l, const float* __restrict__ Xin,
+                                                   const float* __restrict__ arena, float* __restrict__ zarena,
+                                                   float* __restrict__ xb, const float* __restrict__ wsm,
+                                                   const float* __restrict__ theta, float* __restrict__ gpart) {
+  constexpr int NCG = CT / 4;
+  // (a) backward-data
+  if (l == 0) {
+    const int S = M.S;
+    const int nkg = (S + 3) / 4;
+    for (int tile = threadIdx.x; tile < nkg * NCG; tile += NT) {
+      const int cg = tile % NCG, k0 = (tile / NCG) * 4;
+      float2 acc[4][2];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) { acc[kk][0] = make_float2(0.f, 0.f); acc[kk][1] = make_float2(0.f, 0.f); }
+      for (int gi = 0; gi < M.n_gemm; ++gi) {
+        const GemmD& g = M.gemm[gi];
+        if (g.layer != 0) continue;
+        const float* W = WS ? wsm + g.sw_off : theta + g.w_off;
+        bwd_data_tile<WS, CT>(g, W, zarena + g.out_off * CT, k0, cg, acc);
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        if (k0 + kk < S) {
+          float4* p = reinterpret_cast<float4*>(xb + (k0 + kk) * CT + 4 * cg);
+          float4 v = *p;
+          v.x += acc[kk][0].x; v.y += acc[kk][0].y; v.z += acc[kk][1].x; v.w += acc[kk][1].y;
+          *p = v;
+        }
+      }
+    }
+  } else {
+    for (int gi = 0; gi < M.n_gemm; ++gi) {
+      const GemmD& g = M.gemm[gi];
+      if (g.layer != l) continue;
+      // the producer of this gemm's input is the gemm of the same net at layer l-1
+      int gp = -1;
+      for (int gj = 0; gj < M.n_gemm; ++gj)
+        if (M.gemm[gj].net == g.net && M.gemm[gj].layer == l - 1) gp = gj;
+      const int actp = M.gemm[gp].act;
+      const float* W = WS ? wsm + g.sw_off : theta + g.w_off;
+      const int nkg = (g.K + 3) / 4;
+      float* zprev = zarena + g.in_off * CT;
+      for (int tile = threadIdx.x; tile < nkg * NCG; tile += NT) {
+        const int cg = tile % NCG, k0 = (tile / NCG) * 4;
+        float2 acc[4][2];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) { acc[kk][0] = make_float2(0.f, 0.f); acc[kk][1] = make_float2(0.f, 0.f); }
+        bwd_data_tile<WS, CT>(g, W, zarena + g.out_off * CT, k0, cg, acc);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if (k0 + kk < g.K) {
+            float4* p = reinterpret_cast<float4*>(zprev + (k0 + kk) * CT + 4 * cg);
+            const float4 z = *p;
+            float4 d;
+            d.x = acc[kk][0].x * act_grad(actp, z.x);
+            d.y = acc[kk][0].y * act_grad(actp, z.y);
+            d.z = acc[kk][1].x * act_grad(actp, z.z);
+            d.w = acc[kk][1].y * act_grad(actp, z.w);
+            *p = d;
+          }
+        }
+      }
+    }
+  }
+  // (b) weight and bias gradients of layer l (read delta_l and a_{l-1}; neither is written by (a))
+  for (int gi = 0; gi < M.n_gemm; ++gi) {
+    const GemmD& g = M.gemm[gi];
+    if (g.layer != l) continue;
+    const float* a = g.in_off < 0 ? Xin : arena + g.in_off * CT;
+    const float* delta = zarena + g.out_off * CT;
+    const int nkg = (g.K + 3) / 4, njg = (g.N + 3) / 4;
+    for (int tile = threadIdx.x; tile < nkg * njg; tile += NT) {
+      const int jg = tile % njg, kg = tile / njg;
+      bwd_weight_tile<CT>(g, a, delta, kg * 4, jg * 4, gpart + g.w_off);
+    }
+    for (int j = threadIdx.x; j < g.N; j += NT) {
+      float s = 0.f;
+      for (int c = 0; c < CT; c += 4) {
+        const float4 d = *reinterpret_cast<const float4*>(delta + j * CT + c);
+        s += (d.x + d.y) + (d.z + d.w);
+      }
+      atomicAdd(gpart + g.b_off + j, s);
+    }
+  }
+}
+
+// NOTE on (a)/(b) hazards for l > 0: (a) overwrites z_{l-1} (rows of layer l-1) with delta_{l-1}; (b) of layer l reads
+// a_{l-1} from the ARENA (post-activation copy), not from zarena, so the two never touch the same rows.
+
+template <int CT, int NT>
+__device__ __forceinline__ int last_layer_of(const ModelD& M) {
+  int L = 0;
+  for (int gi = 0; gi < M.n_gemm; ++gi) L = max(L, M.gemm[gi].layer);
+  return L;
+}
+
+// loss terms at one saved frame: accumulates the 6 squared-error sums and adds d(loss)/dx to xbar.
+// x: state tile, tg: target tile (same layout). Invalid columns (c >= nvalid) contribute nothing.
+template <int CT, int NT>
+__device__ __forceinline__ void loss_frame(const ModelD& M, const AdjArgs& a, const float* __restrict__ x,
+                                           const float* __restrict__ tg, float* __restrict__ xbar, int nvalid,
+                                           float (&lsum)[6]) {
+  const int N = M.Nz;
+  for (int it = threadIdx.x; it < N * CT; it += NT) {
+    const int k = it / CT, c = it - k * CT;
+    if (c >= nvalid) continue;
+    for (int q = 0; q < M.nf; ++q) {
+      const int wq = M.nf == 1 ? 2 : q;
+      const int e = (q * N + k) * CT + c;
+      const float d = x[e] - tg[e];
+      lsum[wq] = fmaf(d, d, lsum[wq]);
+      float gx = a.w[wq] * 2.f * a.inv_prof * d;
+      if (M.nf == 3 && a.w[3 + q] != 0.f) {
+        // gradient loss: g[f] = Nf (d[f]-d[f-1]) on interior faces f=1..N-1; this thread owns face f=k (if k>=1)
+        float g0 = 0.f, g1 = 0.f;
+        if (k >= 1) {
+          g0 = M.rc.Nf * (d - (x[e - CT] - tg[e - CT]));
+          lsum[3 + q] = fmaf(g0, g0, lsum[3 + q]);
+        }
+        if (k + 1 <= N - 1) g1 = M.rc.Nf * ((x[e + CT] - tg[e + CT]) - d);
+        gx += a.w[3 + q] * 2.f * a.inv_grad * M.rc.Nf * (g0 - g1);
+      }
+      xbar[e] += gx;
+    }
+  }
+}
+
+// x_in = xs + h * sum_{j<i} a_ij k_j  (k_j from the global slots)
+template <int CT, int NT>
+__device__ __forceinline__ void stage_input(const TableauD& tab, int i, float h, const float* __restrict__ xs,
+                                            const float* __restrict__ slots, int SC, float* __restrict__ xin) {
+  for (int e4 = threadIdx.x; e4 < SC / 4; e4 += NT) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < i; ++j) {
+      const float aij = tab.a[i][j];
+      if (aij != 0.f) {
+        const float4 kv = __ldcg(reinterpret_cast<const float4*>(slots + (size_t)j * SC) + e4);
+        acc.x = fmaf(aij, kv.x, acc.x); acc.y = fmaf(aij, kv.y, acc.y);
+        acc.z = fmaf(aij, kv.z, acc.z); acc.w = fmaf(aij, kv.w, acc.w);
+      }
+    }
+    const float4 xv = reinterpret_cast<const float4*>(xs)[e4];
+    reinterpret_cast<float4*>(xin)[e4] = make_float4(fmaf(h, acc.x, xv.x), fmaf(h, acc.y, xv.y), fmaf(h, acc.z, xv.z),
+                                                     fmaf(h, acc.w, xv.w));
+  }
+}
+
+template <int CT, int NT, bool WS>
+__global__ void __launch_bounds__(NT, 1) adjoint_kernel(const __grid_constant__ ModelD M, const __grid_constant__ TableauD tab,
+                                                        const TimeD tm, const __grid_constant__ AdjArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const AdjSmem L = adjoint_smem_layout(M, CT);
+  float* wsm = smem + L.w;
+  float* xs = smem + L.xs;
+  float* xbar = smem + L.xbar;
+  float* xin = smem + L.xin;
+  float* xb = smem + L.xb;
+  float* arena = smem + L.arena;
+  float* zarena = smem + L.zarena;
+  float* bcf = smem + L.bcf;
+  float* qs = smem + L.qs;
+  float* red = smem + L.red;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + ((L.total_floats - 4 + 1) & ~1));
+  const int S = M.S, N = M.Nz, SC = S * CT, ns = tab.n_stages;
+  const float h = tm.dt / (float)tm.n_substeps;
+  float* slots = a.kslots + (size_t)blockIdx.x * ns * SC;
+  float* segx = a.segx + (size_t)blockIdx.x * a.seg_len * SC;
+  float* gpart = a.gpart + (size_t)blockIdx.x * M.P;
+  float* gflux = arena + M.flux_off * CT;
+  uint32_t parity = 0;
+  float lsum[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int Lmax = M.n_gemm > 0 ? last_layer_of<CT, NT>(M) : -1;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (WS) load_weights_smem<NT>(M, wsm, a.theta);
+  __syncthreads();
+
+  auto load_state = [&](float* dst, const float* src) {  // tile-native [S][CT] copy from global
+    for (int i = threadIdx.x; i < SC / 4; i += NT) reinterpret_cast<float4*>(dst)[i] = __ldcg(reinterpret_cast<const float4*>(src) + i);
+  };
+  auto store_state = [&](float* dst, const float* src) {
+    for (int i = threadIdx.x; i < SC / 4; i += NT) __stcg(reinterpret_cast<float4*>(dst) + i, reinterpret_cast<const float4*>(src)[i]);
+  };
+  auto frame_of = [&](int step) -> int {  // saved-frame index of a step, or -1
+    if (tm.save_stride <= 0) return step == tm.n_steps ? 0 : -1;
+    return (step % tm.save_stride == 0) ? step / tm.save_stride : -1;
+  };
+
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const int col0 = tile * CT;
+    const int nvalid = min(CT, a.ncol - col0);
+    __syncthreads();
+    if (threadIdx.x < CT) {
+      const int col = min(col0 + (int)threadIdx.x, a.ncol - 1);
+      float raw[6], eff[6];
+      for (int j = 0; j < M.nbc; ++j) raw[j] = __ldg(a.bcs + (size_t)col * M.nbc + j);
+      bc_effective(M, raw, eff);
+      for (int j = 0; j < M.nbc; ++j) bcf[j * CT + threadIdx.x] = eff[j];
+      qs[threadIdx.x] = (a.Q != nullptr) ? __ldg(a.Q + col) : 0.f;
+    }
+    for (int i = threadIdx.x; i < SC; i += NT) xbar[i] = 0.f;
+    const float* ck = a.ckpt + (size_t)tile * a.n_ckpt * SC;
+    load_state(xs, ck + (size_t)(a.n_ckpt - 1) * SC);  // x_N
+    __syncthreads();
+    {
+      const int fr = frame_of(tm.n_steps);
+      if (fr >= 0) {
+        load_tile<CT, NT>(xb, xin, bar, parity, a.targets + (size_t)fr * S, (size_t)a.n_saved * S, S, col0, a.ncol);
+        __syncthreads();
+        loss_frame<CT, NT>(M, a, xs, xb, xbar, nvalid, lsum);
+        __syncthreads();
+      }
+    }
+    const int cs = tm.ckpt_stride;
+    const int nseg = (tm.n_steps + cs - 1) / cs;
+    for (int seg = nseg - 1; seg >= 0; --seg) {
+      const int n0 = seg * cs, n1 = min(n0 + cs, tm.n_steps);
+      const int R = (n1 - n0) * tm.n_substeps;
+      load_state(xs, ck + (size_t)seg * SC);
+      __syncthreads();
+      // ---- forward recompute of the segment's Runge–Kutta step starts (all but the last need a forward step)
+      store_state(segx, xs);
+      for (int r = 0; r + 1 < R; ++r) {
+        const float tb = tm.t0 + (float)(n0 + r / tm.n_substeps) * tm.dt + (float)(r % tm.n_substeps) * h;
+        for (int i = 0; i < ns; ++i) {
+          const float* in = xs;
+          if (i > 0) { stage_input<CT, NT>(tab, i, h, xs, slots, SC, xin); __syncthreads(); in = xin; }
+          rhs_eval<CT, NT, WS>(M, in, arena, wsm, a.theta, bcf, qs, tb + tab.c[i] * h);
+          for (int it = threadIdx.x; it < N * CT; it += NT) {
+            const int k = it / CT, c = it - k * CT;
+            for (int q = 0; q < M.nf; ++q) __stcg(slots + (size_t)i * SC + (q * N + k) * CT + c, tendency(M, gflux, in, q, k, c, CT));
+          }
+          __syncthreads();
+        }
+        for (int e4 = threadIdx.x; e4 < SC / 4; e4 += NT) {  // x += h sum b_i k_i
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < ns; ++i) {
+            const float bi = tab.b[i];
+            const float4 kv = __ldcg(reinterpret_cast<const float4*>(slots + (size_t)i * SC) + e4);
+            acc.x = fmaf(bi, kv.x, acc.x); acc.y = fmaf(bi, kv.y, acc.y); acc.z = fmaf(bi, kv.z, acc.z); acc.w = fmaf(bi, kv.w, acc.w);
+          }
+          float4 xv = reinterpret_cast<float4*>(xs)[e4];
+          xv.x = fmaf(h, acc.x, xv.x); xv.y = fmaf(h, acc.y, xv.y); xv.z = fmaf(h, acc.z, xv.z); xv.w = fmaf(h, acc.w, xv.w);
+          reinterpret_cast<float4*>(xs)[e4] = xv;
+          __stcg(reinterpret_cast<float4*>(segx + (size_t)(r + 1) * SC) + e4, xv);
+        }
+        __syncthreads();
+      }
+      // ---- reverse sweep over the segment
+      for (int r = R - 1; r >= 0; --r) {
+        if (R > 1) { load_state(xs, segx + (size_t)r * SC); __syncthreads(); }
+        const int nstep = n0 + r / tm.n_substeps, sub = r % tm.n_substeps;
+        const float tb = tm.t0 + (float)nstep * tm.dt + (float)sub * h;
+        // (a) forward stages 0..ns-2 -> k_i into the slots
+        for (int i = 0; i + 1 < ns; ++i) {
+          const float* in = xs;
+          if (i > 0) { stage_input<CT, NT>(tab, i, h, xs, slots, SC, xin); __syncthreads(); in = xin; }
+          rhs_eval<CT, NT, WS>(M, in, arena, wsm, a.theta, bcf, qs, tb + tab.c[i] * h);
+          for (int it = threadIdx.x; it < N * CT; it += NT) {
+            const int k = it / CT, c = it - k * CT;
+            for (int q = 0; q < M.nf; ++q) __stcg(slots + (size_t)i * SC + (q * N + k) * CT + c, tendency(M, gflux, in, q, k, c, CT));
+          }
+          __syncthreads();
+        }
+        // (b) reverse stages
+        for (int i = ns - 1; i >= 0; --i) {
+          const float* in = xs;
+          if (i > 0) { stage_input<CT, NT>(tab, i, h, xs, slots, SC, xin); in = xin; }
+          // kbar_i = h (b_i xbar + sum_{j>i} a_ji Xbar_j)   (slots j>i hold Xbar_j)
+          for (int e4 = threadIdx.x; e4 < SC / 4; e4 += NT) {
+            const float bi = tab.b[i];
+            const float4 xv = reinterpret_cast<const float4*>(xbar)[e4];
+            float4 acc = make_float4(bi * xv.x, bi * xv.y, bi * xv.z, bi * xv.w);
+            for (int j = i + 1; j < ns; ++j) {
+              const float aji = tab.a[j][i];
+              if (aji != 0.f) {
+                const float4 kv = __ldcg(reinterpret_cast<const float4*>(slots + (size_t)j * SC) + e4);
+                acc.x = fmaf(aji, kv.x, acc.x); acc.y = fmaf(aji, kv.y, acc.y); acc.z = fmaf(aji, kv.z, acc.z); acc.w = fmaf(aji, kv.w, acc.w);
+              }
+            }
+            reinterpret_cast<float4*>(xb)[e4] = make_float4(h * acc.x, h * acc.y, h * acc.z, h * acc.w);
+          }
+          if (M.flags & F_DIURNAL) {
+            if (threadIdx.x < CT) bcf[(M.nbc - 1) * CT + threadIdx.x] = diurnal_top_eff(M, qs[threadIdx.x], tb + tab.c[i] * h);
+          }
+          __syncthreads();
+          // MLP forward keeping z and a (the last layer's outputs are not needed: F is linear in them)
+          for (int p = 0; p < M.n_phase; ++p) {
+            if (M.gemm[M.phase[p].g0].layer == Lmax && M.gemm[M.phase[p].g1 - 1].layer == Lmax) continue;
+            run_phase<WS, CT, NT, true>(M, p, in, arena, zarena, wsm, a.theta);
+            __syncthreads();
+          }
+          faces_vjp<CT, NT>(M, in, xb, zarena, gflux);
+          __syncthreads();
+          centres_vjp<CT, NT>(M, xb, gflux);
+          __syncthreads();
+          for (int l = Lmax; l >= 0; --l) {
+            mlp_backward_layer<WS, CT, NT>(M, l, in, arena, zarena, xb, wsm, a.theta, gpart);
+            __syncthreads();
+          }
+          store_state(slots + (size_t)i * SC, xb);  // slot i now holds Xbar_i
+          __syncthreads();
+        }
+        // xbar_n = xbar_{n+1} + sum_i Xbar_i
+        for (int e4 = threadIdx.x; e4 < SC / 4; e4 += NT) {
+          float4 acc = reinterpret_cast<float4*>(xbar)[e4];
+          for (int i = 0; i < ns; ++i) {
+            const float4 kv = __ldcg(reinterpret_cast<const float4*>(slots + (size_t)i * SC) + e4);
+            acc.x += kv.x; acc.y += kv.y; acc.z += kv.z; acc.w += kv.w;
+          }
+          reinterpret_cast<float4*>(xbar)[e4] = acc;
+        }
+        __syncthreads();
+        if (sub == 0) {
+          const int fr = frame_of(nstep);
+          if (fr >= 0) {
+            load_tile<CT, NT>(xb, xin, bar, parity, a.targets + (size_t)fr * S, (size_t)a.n_saved * S, S, col0, a.ncol);
+            __syncthreads();
+            loss_frame<CT, NT>(M, a, xs, xb, xbar, nvalid, lsum);
+            __syncthreads();
+          }
+        }
+      }
+    }
+  }
+  // block reduction of the six loss sums
+  for (int q = 0; q < 6; ++q) {
+    float v = lsum[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int wdx = 0; wdx < NT / 32; ++wdx) s += red[wdx];
+      a.lpart[(size_t)blockIdx.x * 8 + q] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- small reductions -----------------------------------------------------------------------------------------------
+// out[p] = sum over slabs of part[slab][p]   (fixed order: deterministic)
+__global__ void reduce_slabs_kernel(const float* __restrict__ part, int n_slabs, int P, float* __restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float s = 0.f;
+  for (int t = 0; t < n_slabs; ++t) s += part[(size_t)t * P + p];
+  out[p] = s;
+}
+
+// pack[0..P) = grad (unnormalised here: normalisation is folded into the loss cotangent), pack[P..P+6) = raw squared-error
+// sums, pack[P+6] = column count, pack[P+7] = 0.
+__global__ void pack_loss_kernel(const float* __restrict__ lpart, int n_slabs, float ncol, float* __restrict__ pack_tail) {
+  const int q = threadIdx.x;
+  if (q < 6) {
+    float s = 0.f;
+    for (int t = 0; t < n_slabs; ++t) s += lpart[(size_t)t * 8 + q];
+    pack_tail[q] = s;
+  } else if (q == 6) {
+    pack_tail[6] = ncol;
+  } else if (q == 7) {
+    pack_tail[7] = 0.f;
+  }
+}
+
+// loss_out[0..6) = w_q * sum_q * inv_norm_q ; loss_out[6] = total
+struct W6 { float w[6]; };
+__global__ void finalize_loss_kernel(const float* __restrict__ pack_tail, const W6 w6, float inv_prof,
+                                     float inv_grad, float* __restrict__ loss_out) {
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    const float inv_ncol = 1.f / pack_tail[6];
+    for (int q = 0; q < 6; ++q) {
+      const float v = w6.w[q] * pack_tail[q] * (q < 3 ? inv_prof : inv_grad) * inv_ncol;
+      loss_out[q] = v;
+      tot += v;
+    }
+    loss_out[6] = tot;
+  }
+}
+
+// Loss-only path: six squared-error sums of a device trajectory against targets ([ncol][n_saved][S] both).
+// One block per column; partial sums to lpart[col][8].
+__global__ void loss_traj_kernel(const float* __restrict__ traj, const float* __restrict__ tgt, int n_saved, int S, int Nz,
+                                 int nf, float Nf, float* __restrict__ lpart) {
+  __shared__ float red[6][8];
+  const size_t base = (size_t)blockIdx.x * n_saved * S;
+  float ls[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i = threadIdx.x; i < n_saved * S; i += blockDim.x) {
+    const int s = i % S, q = s / Nz, k = s - q * Nz;
+    const int wq = nf == 1 ? 2 : q;
+    const float d = traj[base + i] - tgt[base + i];
+    ls[wq] = fmaf(d, d, ls[wq]);
+    if (nf == 3 && k >= 1) {
+      const float g = Nf * (d - (traj[base + i - 1] - tgt[base + i - 1]));
+      ls[3 + q] = fmaf(g, g, ls[3 + q]);
+    }
+  }
+  for (int q = 0; q < 6; ++q) {
+    float v = ls[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[threadIdx.x][w];
+    lpart[(size_t)blockIdx.x * 8 + threadIdx.x] = t;
+  }
+}
+
+// grad[p] *= scale
+__global__ void scale_kernel(float* __restrict__ g, int P, const float* __restrict__ pack_tail) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P) g[p] *= 1.f / pack_tail[6];
+}
+
+// Flux 0.11 ADAM: m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; theta -= lr * m/(1-bp1) / (sqrt(v/(1-bp2)) + eps)
+__global__ void adam_kernel(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
+                            int P, float lr, float b1, float b2, float eps, float bp1, float bp2) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const float gp = g[p];
+  const float mp = b1 * m[p] + (1.f - b1) * gp;
+  const float vp = b2 * v[p] + (1.f - b2) * gp * gp;
+  m[p] = mp;
+  v[p] = vp;
+  theta[p] -= mp / (1.f - bp1) / (sqrtf(vp / (1.f - bp2)) + eps) * lr;
+}
+
+}  // namespace cpz

@@ -388,6 +388,6 @@ int cpz_solve(cpz_model* m, const float* x0, const float* bcs, const float* diur
   return CPZ_OK;
 }
 
-#include "cpz_capi_train.inc"
-
 }  // extern "C"
+
+#include "cpz_capi_train.inc"

@@ -275,7 +275,6 @@ bool build_plan(const cpz_model_desc& d, const PlanOptions& opt, Plan& out, std:
   std::vector<GemmD> gemms;
   int arena_rows = 0, nn_off[3], flux_off = 0;
   bool chosen = false;
-  const int arena_mult = opt.keep_all ? 2 : 1;  // adjoint keeps pre-activations too
   for (int attempt = 0; attempt < 2 && !chosen; ++attempt) {
     const bool layer_major = attempt == 0 && same_depth;
     if (attempt == 0 && !same_depth) continue;
@@ -303,7 +302,8 @@ bool build_plan(const cpz_model_desc& d, const PlanOptions& opt, Plan& out, std:
         tb += g.n_og * NCG;
       }
     }
-    const size_t arena_b = (size_t)arena_rows * opt.CT * sizeof(float) * arena_mult;
+    // the adjoint also keeps a pre-activation/delta row for every layer output row (flux_off rows)
+    const size_t arena_b = (size_t)(arena_rows + (opt.keep_all ? flux_off : 0)) * opt.CT * sizeof(float);
     const size_t wb = weight_floats(gemms) * sizeof(float);
     if (arena_b + opt.other_smem_bytes <= opt.smem_budget || attempt == 1 || opt.keep_all) {
       pl.layer_major = layer_major;

@@ -4,6 +4,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from typing import Optional
 
 import numpy as np
@@ -123,6 +124,7 @@ class Context:
         _check(lib().cpz_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(self._h)))
         self.device = device
         self._ar_cb = None
+        self._models = weakref.WeakSet()  # models must be destroyed before their context
 
     def set_allreduce(self, fn, rank: int, world_size: int) -> None:
         """fn(dev_ptr:int, n_floats:int, stream:int) -> None must sum the device buffer over all ranks in place."""
@@ -154,6 +156,8 @@ class Context:
 
     def close(self) -> None:
         if self._h:
+            for m in list(self._models):
+                m.close()
             lib().cpz_ctx_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -173,6 +177,7 @@ class Model:
         self._c = desc.to_c()
         self._h = C.c_void_p()
         _check(lib().cpz_model_create(ctx._h, C.byref(self._c), C.byref(self._h)))
+        ctx._models.add(self)
         p = C.c_size_t(0)
         _check(lib().cpz_model_n_params(self._h, C.byref(p)))
         self.P = p.value
