@@ -1,0 +1,276 @@
+"""The oracle checked against everything the reference's own tests pin (scaler properties, loss-fraction identities),
+against analytic known answers, and against itself (literal dense-matrix restatement vs batched stencil form,
+autograd vs finite differences). CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from cpz_b200 import synthetic as syn
+from cpz_b200.desc import (FLAG_CA, FLAG_CA_LITERAL_U, FLAG_DIURNAL, FLAG_DIURNAL_UNSHIFTED, FLAG_MPP, FLAG_SMOOTH_NN,
+                           FLAG_SMOOTH_RI, FLAG_ZERO_WEIGHTS, RHS_INFER, RHS_TRAIN, ClosureDesc)
+from oracle import flux_nn, literal, nde, operators, scaling
+from util import oracle_loss_grad, oracle_rhs, oracle_solve, rel_inf, t64
+
+
+# ---- src/differentiation_operators.jl ------------------------------------------------------------------------------------
+def test_Df_linear_ramp_and_zero_boundary_rows():
+    N, delta = 32, 1 / 32
+    z = (np.arange(N) + 0.5) * delta
+    a, b = 3.7, -1.2
+    g = operators.D_f(N, delta) @ (a * z + b)
+    assert g.shape == (N + 1,)
+    np.testing.assert_allclose(g[1:-1], a, rtol=1e-12)
+    assert g[0] == 0 and g[-1] == 0
+
+
+def test_Dc_of_constant_is_zero_and_shapes():
+    N = 32
+    D = operators.D_c(N, 1 / N)
+    assert D.shape == (N, N + 1)
+    np.testing.assert_allclose(D @ np.full(N + 1, 4.2), 0, atol=1e-12)
+    f = np.arange(N + 1.0) ** 2
+    np.testing.assert_allclose(D @ f, N * (f[1:] - f[:-1]))
+
+
+def test_smoothing_filter_rows():
+    for n in (31, 32, 33):
+        F = operators.smoothing_filter(n, 3)
+        np.testing.assert_allclose(F.sum(axis=1), 1, rtol=1e-6)
+        assert np.count_nonzero(F[0]) == 2 and np.count_nonzero(F[-1]) == 2 and np.count_nonzero(F[5]) == 3
+
+
+# ---- test/test_feature_scaling.jl:1-30 (the one reference test touching the hot path) -----------------------------------
+@pytest.mark.parametrize("shape", [(10,), (5, 5), (3, 3, 3)])
+def test_zero_mean_unit_variance_scaling(shape):
+    data = np.random.default_rng(1).random(shape)
+    s = scaling.ZeroMeanUnitVarianceScaling(data)
+    assert s.mu == data.mean()
+    assert s.sigma == data.std(ddof=1)  # Julia's std is the corrected estimator
+    assert abs(s(data).mean()) < 1e-10
+    assert abs(s(data).std(ddof=1) - 1) < 1e-12
+    np.testing.assert_allclose(s.inv()(s(data)), data)
+
+
+@pytest.mark.parametrize("ab", [(0, 10), (-5, -1), (1, 2), (-1, 20)])
+def test_min_max_scaling(ab):
+    data = np.random.default_rng(2).random((5, 5))
+    s = scaling.MinMaxScaling(data, a=ab[0], b=ab[1])
+    assert s.data_min == data.min() and s.data_max == data.max()
+    assert abs(s(data).min() - ab[0]) < 1e-10 and abs(s(data).max() - ab[1]) < 1e-10
+    np.testing.assert_allclose(s.inv()(s(data)), data)
+
+
+# ---- wind_mixing/test/test_training_scaling.jl:17-19 ---------------------------------------------------------------------
+def test_loss_fraction_identities():
+    rng = np.random.default_rng(3)
+    losses = {k: rng.random() for k in ("u", "v", "T", "du", "dv", "dT")}
+    fr = {"T": rng.random(), "dT": rng.random(), "profile": rng.random()}
+    s = literal.calculate_loss_scalings(losses, fr, True)
+    L = literal.apply_loss_scalings(losses, s)
+    np.testing.assert_allclose(L["T"] / (L["u"] + L["v"]), fr["T"] / (1 - fr["T"]))
+    np.testing.assert_allclose(L["dT"] / (L["du"] + L["dv"]), fr["dT"] / (1 - fr["dT"]))
+    np.testing.assert_allclose((L["u"] + L["v"] + L["T"]) / (L["du"] + L["dv"] + L["dT"]), fr["profile"] / (1 - fr["profile"]))
+
+
+# ---- Flux semantics ----------------------------------------------------------------------------------------------------
+def test_destructure_order_is_column_major_W_then_b():
+    W = np.arange(6, dtype=np.float64).reshape(2, 3)  # out=2, in=3
+    b = np.array([10.0, 11.0])
+    th = flux_nn.destructure([(W, b)])
+    np.testing.assert_array_equal(th, [0, 3, 1, 4, 2, 5, 10, 11])
+    (W2, b2), = flux_nn.reconstruct(th, [3, 2])
+    np.testing.assert_array_equal(W2, W)
+    x = np.array([1.0, -2.0, 0.5])
+    np.testing.assert_allclose(flux_nn.chain_numpy(th, [3, 2], ["relu"], x), np.maximum(W @ x + b, 0))
+
+
+@pytest.mark.parametrize("act", ["relu", "mish", "swish", "leakyrelu", "tanh", "identity"])
+def test_activations_numpy_vs_torch(act):
+    x = np.linspace(-12, 12, 101)
+    np.testing.assert_allclose(flux_nn.act_torch(act, t64(x)).numpy(), flux_nn.act_numpy(act, x), rtol=1e-12, atol=1e-14)
+
+
+# ---- the two restatements agree -----------------------------------------------------------------------------------------
+UVT_CASES = [(RHS_TRAIN, FLAG_MPP | FLAG_ZERO_WEIGHTS), (RHS_TRAIN, FLAG_MPP), (RHS_TRAIN, FLAG_MPP | FLAG_ZERO_WEIGHTS | FLAG_SMOOTH_NN | FLAG_SMOOTH_RI),
+             (RHS_TRAIN, FLAG_CA), (RHS_TRAIN, 0), (RHS_TRAIN, FLAG_ZERO_WEIGHTS | FLAG_MPP | FLAG_DIURNAL), (RHS_INFER, FLAG_MPP | FLAG_ZERO_WEIGHTS),
+             (RHS_INFER, FLAG_MPP | FLAG_CA), (RHS_INFER, FLAG_MPP | FLAG_CA | FLAG_CA_LITERAL_U), (RHS_INFER, FLAG_DIURNAL),
+             (RHS_INFER, FLAG_DIURNAL | FLAG_DIURNAL_UNSHIFTED)]
+
+
+@pytest.mark.parametrize("variant,flags", UVT_CASES)
+def test_batched_rhs_equals_literal_rhs(variant, flags):
+    d = syn.wind_mixing_desc(variant=variant, flags=flags)
+    th = syn.theta_random(d, scale=1.0)
+    x0, bcs = syn.columns(d, 4)
+    Q = syn.diurnal_Q(4)
+    got = oracle_rhs(d, th, x0, bcs, 0.3, Q)
+    ref = np.stack([literal.rhs(d, th, x0[i], bcs[i], 0.3, Q[i]) for i in range(4)])
+    assert rel_inf(got, ref) < 1e-12
+
+
+@pytest.mark.parametrize("ca", [False, True])
+def test_batched_rhs_equals_literal_rhs_free_convection(ca):
+    d = syn.free_convection_desc(ca=ca)
+    th = syn.theta_random(d, scale=1.0)
+    x0, bcs = syn.columns(d, 4)
+    got = oracle_rhs(d, th, x0, bcs)
+    ref = np.stack([literal.rhs(d, th, x0[i], bcs[i]) for i in range(4)])
+    assert rel_inf(got, ref) < 1e-12
+
+
+def test_DE_is_train_rhs_without_nets():
+    d = syn.wind_mixing_desc(variant=RHS_TRAIN, net=None)
+    x0, bcs = syn.columns(d, 3)
+    got = oracle_rhs(d, np.zeros(0, np.float32), x0, bcs)
+    dz = syn.wind_mixing_desc(variant=RHS_TRAIN)
+    zero = np.zeros(dz.n_params, np.float32)
+    np.testing.assert_allclose(got, oracle_rhs(dz, zero, x0, bcs), rtol=1e-13)
+
+
+# ---- Tsit5 tableau ------------------------------------------------------------------------------------------------------
+def test_tsit5_order_conditions():
+    a, b, c = nde.TABLEAUS["tsit5"]
+    A = np.zeros((6, 6))
+    for i, row in enumerate(a):
+        A[i, :len(row)] = row
+    b, c = np.array(b), np.array(c)
+    np.testing.assert_allclose(A.sum(axis=1), c, atol=1e-15)
+    np.testing.assert_allclose(b.sum(), 1, atol=1e-15)
+    np.testing.assert_allclose(b @ c, 1 / 2, atol=1e-15)
+    np.testing.assert_allclose(b @ c ** 2, 1 / 3, atol=1e-15)
+    np.testing.assert_allclose(b @ (A @ c), 1 / 6, atol=1e-15)
+    np.testing.assert_allclose(b @ c ** 3, 1 / 4, atol=1e-15)
+    np.testing.assert_allclose(b @ (c * (A @ c)), 1 / 8, atol=1e-15)
+    np.testing.assert_allclose(b @ (A @ c ** 2), 1 / 12, atol=1e-15)
+    np.testing.assert_allclose(b @ (A @ (A @ c)), 1 / 24, atol=1e-15)
+    np.testing.assert_allclose(b @ c ** 4, 1 / 5, atol=1e-15)
+
+
+@pytest.mark.parametrize("name,order", [("euler", 1), ("rk4", 4), ("tsit5", 5)])
+def test_integrator_convergence_order(name, order):
+    """dy/dt = -y through the same stage recursion the oracle's rk_step uses."""
+    a, b, c = nde.TABLEAUS[name]
+
+    def step(y, h):
+        ks = []
+        for i in range(len(b)):
+            yi = y + h * sum(aij * ks[j] for j, aij in enumerate(a[i]))
+            ks.append(-yi)
+        return y + h * sum(bi * ki for bi, ki in zip(b, ks))
+
+    errs = []
+    for n in (8, 16):
+        y = 1.0
+        for _ in range(n):
+            y = step(y, 1.0 / n)
+        errs.append(abs(y - np.exp(-1)))
+    assert abs(np.log2(errs[0] / errs[1]) - order) < 0.5
+
+
+def _zero_flux_bcs(d, ncol):
+    """scaled boundary fluxes equal to s_q(0) in the oracle's own arithmetic (float32 constants promoted to float64)"""
+    z = [-float(np.float32(d.mu[3 + q])) / float(np.float32(d.sigma[3 + q])) for q in range(3)]
+    return np.array([[z[0], z[0], z[1], z[1], z[2], z[2]]] * ncol, dtype=np.float64)
+
+
+# ---- analytic known answers for the solve ----------------------------------------------------------------------------------
+def test_pure_diffusion_decays_cosine_mode_at_discrete_rate():
+    d = syn.wind_mixing_desc(variant=RHS_TRAIN, net=None, n_steps=40, save_stride=40, nu_m=0.0, f=0.0, nu0=1e-3, n_substeps=1)
+    N, mode = d.Nz, 3
+    k = np.arange(N) + 0.5
+    prof = np.cos(np.pi * mode * k / N)
+    x0 = np.zeros((1, 3 * N), np.float32)
+    x0[0, 2 * N:] = 1e-3 * prof  # small, so Ri stays far from the transition and nu = nu0 exactly (nu_m = 0 anyway)
+    x0[0, :N] = 1e-3 * prof
+    bcs = _zero_flux_bcs(d, 1)
+    traj = oracle_solve(d, np.zeros(0, np.float32), x0, bcs)
+    lam = -4 * N ** 2 * np.sin(np.pi * mode / (2 * N)) ** 2 * np.float32(d.nu0) * np.float32(d.tau) / np.float32(d.H) ** 2
+    T_end = d.n_steps * np.float32(d.dt)
+    np.testing.assert_allclose(traj[0, -1, 2 * N:], x0[0, 2 * N:].astype(np.float64) * np.exp(lam * T_end), rtol=2e-5, atol=1e-12)
+    # no Coriolis, so u diffuses the same way (mean-free mode; the mu_v constant term vanishes with f = 0)
+    np.testing.assert_allclose(traj[0, -1, :N], x0[0, :N].astype(np.float64) * np.exp(lam * T_end), rtol=2e-5, atol=1e-12)
+
+
+def test_inertial_oscillation_period():
+    """nu = 0, NN = 0, zero fluxes: physical (u, v) rotates with period 2 pi / f."""
+    d = syn.wind_mixing_desc(variant=RHS_TRAIN, net=None, nu0=0.0, nu_m=0.0, n_substeps=1)
+    period_hat = 2 * np.pi / (np.float32(d.f) * np.float32(d.tau))
+    d.n_steps = 64
+    d.dt = period_hat / 64
+    d.save_stride = 16
+    x0, _ = syn.columns(d, 2)
+    bcs = _zero_flux_bcs(d, 2)
+    tr = oracle_solve(d, np.zeros(0, np.float32), x0, bcs)
+    N = d.Nz
+    u = lambda fr: tr[:, fr, :N] * np.float32(d.sigma[0]) + np.float32(d.mu[0])
+    v = lambda fr: tr[:, fr, N:2 * N] * np.float32(d.sigma[1]) + np.float32(d.mu[1])
+    np.testing.assert_allclose(u(4), u(0), atol=1e-7)
+    np.testing.assert_allclose(v(4), v(0), atol=1e-7)
+    np.testing.assert_allclose(u(1), v(0), atol=1e-7)   # quarter period: (u, v) -> (v, -u)
+    np.testing.assert_allclose(v(1), -u(0), atol=1e-7)
+    np.testing.assert_allclose(tr[:, -1, 2 * N:], x0[:, 2 * N:], atol=1e-12)  # T untouched
+
+
+# ---- gradient = exact discrete adjoint -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["uvT", "T"])
+def test_autograd_gradient_matches_finite_differences(kind):
+    if kind == "uvT":
+        d = syn.wind_mixing_desc(variant=RHS_TRAIN, n_steps=4, save_stride=2)
+        w = np.array([0.7, 0.7, 1.0, 3e-3, 3e-3, 5e-3])
+    else:
+        d = syn.free_convection_desc(ca=False, n_steps=4, save_stride=2)
+        w = np.array([0, 0, 1.0, 0, 0, 0])
+    d.nets = [type(n)(n.sizes, ["tanh" if a != "identity" else a for a in n.acts]) for n in d.nets]  # smooth for FD
+    th = syn.theta_random(d, scale=0.3).astype(np.float64)
+    x0, bcs = syn.columns(d, 5)
+    tgt = oracle_solve(d, th * 1.2, x0, bcs)
+    tot, comps, g = oracle_loss_grad(d, th, x0, bcs, tgt, w)
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        v = rng.standard_normal(th.shape)
+        v /= np.linalg.norm(v)
+        h = 1e-5
+        lp = oracle_loss_grad(d, th + h * v, x0, bcs, tgt, w)[0]
+        lm = oracle_loss_grad(d, th - h * v, x0, bcs, tgt, w)[0]
+        fd = (lp - lm) / (2 * h)
+        assert abs(fd - g @ v) <= 1e-6 * max(abs(fd), np.linalg.norm(g) * 1e-2)
+
+
+def test_loss_components_match_literal_definition():
+    d = syn.wind_mixing_desc(variant=RHS_TRAIN, n_steps=4, save_stride=2)
+    th = syn.theta_random(d, scale=0.3)
+    x0, bcs = syn.columns(d, 3)
+    traj = oracle_solve(d, th, x0, bcs)
+    tgt = traj + 0.01 * np.random.default_rng(0).standard_normal(traj.shape)
+    comps = [float(c) for c in nde.loss_components(d, t64(traj), t64(tgt))]
+    N = d.Nz
+    D_face = operators.D_f(N, 1 / N)
+    for q in range(3):
+        per_sim = [literal.loss(traj[i, :, q * N:(q + 1) * N].T, tgt[i, :, q * N:(q + 1) * N].T) for i in range(3)]
+        np.testing.assert_allclose(comps[q], np.mean(per_sim), rtol=1e-12)
+        per_sim_g = [literal.loss(literal.d_dz(traj[i, :, q * N:(q + 1) * N].T, D_face), literal.d_dz(tgt[i, :, q * N:(q + 1) * N].T, D_face))
+                     for i in range(3)]
+        np.testing.assert_allclose(comps[3 + q], np.mean(per_sim_g), rtol=1e-12)
+
+
+def test_adam_first_step_is_lr_times_sign():
+    th = t64([1.0, -2.0, 3.0]); g = t64([0.5, -4.0, 1e-3])
+    th2, m, v, bp = nde.adam_step(th, g, torch.zeros(3, dtype=torch.float64), torch.zeros(3, dtype=torch.float64), (0.9, 0.999), 1e-3)
+    np.testing.assert_allclose((th - th2).numpy(), 1e-3 * np.sign(g.numpy()), rtol=1e-4)
+    assert bp == (0.9 * 0.9, 0.999 * 0.999)
+
+
+# ---- closure ---------------------------------------------------------------------------------------------------------------
+def test_closure_batched_equals_literal():
+    d = syn.free_convection_desc(ca=False)
+    th = syn.theta_random(d, scale=1.0)
+    T, y = syn.gyre_field(6, 3, 32)
+    T[:, :, ::2] = T[::-1, :, ::2]
+    cd = ClosureDesc(Nx=6, Ny=3, Nz=32)
+    forcing, T_out = nde.closure_step(d, t64(th), cd, t64(T), t64(y))
+    for (j, i) in [(0, 0), (1, 3), (2, 4)]:
+        T_adj = literal.convective_adjustment_implicit(T[:, j, i], cd.dt, cd.dz, cd.K)
+        np.testing.assert_allclose(T_out[:, j, i].numpy(), T_adj, rtol=1e-10)
+        np.testing.assert_allclose(forcing[:, j, i].numpy(), literal.gyre_closure_column(d, th, cd, T_adj, float(y[j])), rtol=1e-9, atol=1e-16)
+    # note: the reference's matrix (kappa located at centres, d_1 = 1 + r(kappa_1 + kappa_2)) is not conservative at the
+    # bottom cell when kappa_1 != 0; the oracle follows the code, so no column-mean invariant is asserted here.
