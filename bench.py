@@ -282,6 +282,67 @@ def main():
                              "peak_at_observed_clock": peak_tf_obs, "frac": ach_tf / peak_tf_obs, "flop_per_colstep": fl,
                              "stage_evals_per_s": value * d.rhs_evals_per_step},
     }
+    if not args.no_extras:
+        # ---- fwd + discrete adjoint + ADAM (BASELINE config 3: 9 forcing cases x 1024 columns, sharded over ranks) ----
+        try:
+            from cpz_b200 import parallel
+            if dist is not None:
+                parallel.attach_torch_allreduce(ctx)
+            NC3 = 9216
+            lo, hi = parallel.shard_columns(NC3, rank, world)
+            d3 = syn.wind_mixing_desc(variant=RHS_TRAIN, net="uvT_small", n_steps=NSTEPS, save_stride=9, ckpt_stride=9)
+            m3 = engine.Model(ctx, d3, syn.theta_init(d3, seed=42, scale=1e-5))
+            x3, b3 = syn.columns(d3, NC3, seed=1000)
+            x3_d, b3_d = torch.tensor(x3[lo:hi], device="cuda"), torch.tensor(b3[lo:hi], device="cuda")
+            # targets: a smooth drift of the initial profiles (any target gives the same cost)
+            tg = torch.tensor(x3[lo:hi], device="cuda")[:, None, :].repeat(1, d3.n_saved, 1).contiguous()
+            tg += 0.05 * torch.linspace(0, 1, d3.n_saved, device="cuda")[None, :, None]
+            w3 = np.array([1, 1, 1, 5e-3, 5e-3, 5e-3], dtype=np.float32)
+            m3.train_step_dev(x3_d, b3_d, tg, w3, 3e-4)  # warm-up (allocates scratch)
+            barrier()
+            l0 = ctx.launch_count
+            n3 = 2
+            a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(n3):
+                loss3 = m3.train_step_dev(x3_d, b3_d, tg, w3, 3e-4)
+            a1.record()
+            barrier()
+            t3 = torch.tensor([a0.elapsed_time(a1)], device="cuda")
+            if dist is not None:
+                dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+            ms3 = float(t3.item()) / n3
+            bytes3 = 129.0
+            line["adjoint"] = {
+                "metric": "column-steps/sec (forward + discrete adjoint + ADAM)", "value": NC3 * NSTEPS / (ms3 * 1e-3),
+                "unit": "column-steps/s", "ms_per_step": ms3, "scaling": "strong", "gpu_launches_per_step": int((ctx.launch_count - l0) / n3),
+                "config": {"workload": "BASELINE config 3: 9 forcing cases x 1024 columns, training RHS, 1152 steps, 129 saved frames, ckpt_stride 9, Tsit5 x2 sub-steps, ADAM(3e-4), one allreduce of P+8 floats",
+                           "columns_total": NC3, "columns_this_rank": hi - lo},
+                "loss": float(loss3[6]),
+                "roofline_hbm_frac": bytes3 * (hi - lo) * NSTEPS / (ms3 * 1e-3) / 1e9 / hbm_peak,
+            }
+            m3.close()
+        except Exception as e:  # noqa: BLE001
+            line["adjoint"] = {"error": repr(e)}
+        # ---- NN-free mPP-only forward (SURVEY 8d '2-base', the HBM-fair variant) ----
+        try:
+            d0 = syn.wind_mixing_desc(variant=RHS_INFER, net=None, n_steps=NSTEPS, save_stride=1)
+            m0 = engine.Model(ctx, d0, np.zeros(0, dtype=np.float32))
+            m0.solve_dev(x0_d, bcs_d, traj_d)
+            barrier()
+            b0 = torch.cuda.Event(enable_timing=True); b1 = torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for _ in range(3):
+                m0.solve_dev(x0_d, bcs_d, traj_d)
+            b1.record()
+            barrier()
+            ms0 = b0.elapsed_time(b1) / 3
+            gb0 = bytes_per_colstep * NCOL * NSTEPS / (ms0 * 1e-3) / 1e9
+            line["nn_free"] = {"metric": "column-steps/sec (forward, mPP only)", "value": NCOL * NSTEPS * world / (ms0 * 1e-3),
+                               "ms_per_step": ms0, "roofline": {"bound": "hbm", "achieved": gb0, "peak": hbm_peak, "unit": "GB/s", "frac": gb0 / hbm_peak}}
+            m0.close()
+        except Exception as e:  # noqa: BLE001
+            line["nn_free"] = {"error": repr(e)}
     if rank == 0 and not args.no_extras:
         try:
             line["cpu_baseline"] = cpu_baseline(syn, RHS_INFER)

@@ -30,7 +30,7 @@ struct AdjArgs {
 };
 
 struct AdjSmem {
-  int w, xs, xbar, xin, xb, arena, zarena, bcf, qs, red, total_floats;
+  int w, xs, xbar, xin, xb, arena, zarena, bcf, qs, red, model, total_floats;
 };
 __host__ __device__ inline AdjSmem adjoint_smem_layout(const ModelD& M, int CT) {
   AdjSmem L;
@@ -45,18 +45,19 @@ __host__ __device__ inline AdjSmem adjoint_smem_layout(const ModelD& M, int CT) 
   L.bcf = o; o += M.nbc * CT;
   L.qs = o; o += CT;
   L.red = o; o += 64;
+  L.model = o; o += (int)((sizeof(ModelD) + 15) / 16) * 4;
   L.total_floats = o + 4;
   return L;
 }
 inline size_t adjoint_other_smem(int S, int nbc, int CT) {
-  return ((size_t)3 * S * CT + (size_t)CT * (S + 4) + (size_t)nbc * CT + CT + 64 + 4) * sizeof(float);
+  return ((size_t)3 * S * CT + (size_t)CT * (S + 4) + (size_t)nbc * CT + CT + 64 + 4) * sizeof(float) + ((sizeof(ModelD) + 15) / 16) * 16;
 }
 
 // ---- VJP of the face fluxes ------------------------------------------------------------------------------------------
 // Reads kbar [S][CT] and the stage input X; writes the cotangent of the last-layer NN outputs into `nnbar` rows
 // (zarena at M.nn_off) and the cotangent of the face gradients Gbar_q[face][c] into `gbar` (arena flux rows).
 template <int CT, int NT>
-__device__ __forceinline__ void faces_vjp(const ModelD& M, const float* __restrict__ X, const float* __restrict__ kbar,
+__device__ __noinline__ void faces_vjp(const ModelD& M, const float* __restrict__ X, const float* __restrict__ kbar,
                                           float* __restrict__ zarena, float* __restrict__ gbar) {
   const int N = M.Nz, nfaces = N + 1;
   const bool has_nn = M.n_nets > 0;
@@ -129,7 +130,7 @@ __device__ __forceinline__ void faces_vjp(const ModelD& M, const float* __restri
 
 // Direct (non-MLP) part of Xbar_i = (df/dX)^T kbar_i, written IN PLACE over kbar (each thread owns (k,c) of all fields).
 template <int CT, int NT>
-__device__ __forceinline__ void centres_vjp(const ModelD& M, float* __restrict__ kbar_xb, const float* __restrict__ gbar) {
+__device__ __noinline__ void centres_vjp(const ModelD& M, float* __restrict__ kbar_xb, const float* __restrict__ gbar) {
   const int N = M.Nz, nfaces = N + 1;
   for (int it = threadIdx.x; it < N * CT; it += NT) {
     const int k = it / CT, c = it - k * CT;
@@ -233,7 +234,7 @@ __device__ __forceinline__ void bwd_weight_tile(const GemmD& g, const float* __r
 // Backward through layer index `l` of every net that has it: weight/bias gradients, then delta of the previous layer
 // (or the accumulation of W_0 delta_0 into Xbar for l == 0). One block barrier must follow.
 template <bool WS, int CT, int NT>
-__device__ __forceinline__ void mlp_backward_layer(const ModelD& M, int l, const float* __restrict__ Xin,
+__device__ __noinline__ void mlp_backward_layer(const ModelD& M, int l, const float* __restrict__ Xin,
                                                    const float* __restrict__ arena, float* __restrict__ zarena,
                                                    float* __restrict__ xb, const float* __restrict__ wsm,
                                                    const float* __restrict__ theta, float* __restrict__ gpart) {
@@ -332,7 +333,7 @@ __device__ __forceinline__ int last_layer_of(const ModelD& M) {
 // loss terms at one saved frame: accumulates the 6 squared-error sums and adds d(loss)/dx to xbar.
 // x: state tile, tg: target tile (same layout). Invalid columns (c >= nvalid) contribute nothing.
 template <int CT, int NT>
-__device__ __forceinline__ void loss_frame(const ModelD& M, const AdjArgs& a, const float* __restrict__ x,
+__device__ __noinline__ void loss_frame(const ModelD& M, const AdjArgs& a, const float* __restrict__ x,
                                            const float* __restrict__ tg, float* __restrict__ xbar, int nvalid,
                                            float (&lsum)[6]) {
   const int N = M.Nz;
@@ -362,7 +363,7 @@ __device__ __forceinline__ void loss_frame(const ModelD& M, const AdjArgs& a, co
 
 // x_in = xs + h * sum_{j<i} a_ij k_j  (k_j from the global slots)
 template <int CT, int NT>
-__device__ __forceinline__ void stage_input(const TableauD& tab, int i, float h, const float* __restrict__ xs,
+__device__ __noinline__ void stage_input(const TableauD& tab, int i, float h, const float* __restrict__ xs,
                                             const float* __restrict__ slots, int SC, float* __restrict__ xin) {
   for (int e4 = threadIdx.x; e4 < SC / 4; e4 += NT) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -380,10 +381,8 @@ __device__ __forceinline__ void stage_input(const TableauD& tab, int i, float h,
   }
 }
 
-template <int CT, int NT, bool WS>
-__global__ void __launch_bounds__(NT, 1) adjoint_kernel(const __grid_constant__ ModelD M, const __grid_constant__ TableauD tab,
-                                                        const TimeD tm, const __grid_constant__ AdjArgs a) {
-  extern __shared__ __align__(16) float smem[];
+template <int CT, int NT, bool WS, int NF>
+__device__ __forceinline__ void adjoint_body(const ModelD& M, const TableauD& tab, const TimeD& tm, const AdjArgs& a, float* smem) {
   const AdjSmem L = adjoint_smem_layout(M, CT);
   float* wsm = smem + L.w;
   float* xs = smem + L.xs;
@@ -463,11 +462,14 @@ __global__ void __launch_bounds__(NT, 1) adjoint_kernel(const __grid_constant__ 
         for (int i = 0; i < ns; ++i) {
           const float* in = xs;
           if (i > 0) { stage_input<CT, NT>(tab, i, h, xs, slots, SC, xin); __syncthreads(); in = xin; }
-          rhs_eval<CT, NT, WS>(M, in, arena, wsm, a.theta, bcf, qs, tb + tab.c[i] * h);
-          for (int it = threadIdx.x; it < N * CT; it += NT) {
-            const int k = it / CT, c = it - k * CT;
-            for (int q = 0; q < M.nf; ++q) __stcg(slots + (size_t)i * SC + (q * N + k) * CT + c, tendency(M, gflux, in, q, k, c, CT));
-          }
+          rhs_mlp<CT, NT, WS>(M, in, arena, wsm, a.theta, bcf, qs, tb + tab.c[i] * h);
+          float* slot_i = slots + (size_t)i * SC;
+          rhs_tendencies<CT, NT, NF>(M, in, arena, bcf, [=](int k0, int c, const float (&dx)[NF][4]) {
+#pragma unroll
+            for (int q = 0; q < NF; ++q)
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) __stcg(slot_i + (q * N + k0 + kk) * CT + c, dx[q][kk]);
+          });
           __syncthreads();
         }
         for (int e4 = threadIdx.x; e4 < SC / 4; e4 += NT) {  // x += h sum b_i k_i
@@ -493,11 +495,14 @@ __global__ void __launch_bounds__(NT, 1) adjoint_kernel(const __grid_constant__ 
         for (int i = 0; i + 1 < ns; ++i) {
           const float* in = xs;
           if (i > 0) { stage_input<CT, NT>(tab, i, h, xs, slots, SC, xin); __syncthreads(); in = xin; }
-          rhs_eval<CT, NT, WS>(M, in, arena, wsm, a.theta, bcf, qs, tb + tab.c[i] * h);
-          for (int it = threadIdx.x; it < N * CT; it += NT) {
-            const int k = it / CT, c = it - k * CT;
-            for (int q = 0; q < M.nf; ++q) __stcg(slots + (size_t)i * SC + (q * N + k) * CT + c, tendency(M, gflux, in, q, k, c, CT));
-          }
+          rhs_mlp<CT, NT, WS>(M, in, arena, wsm, a.theta, bcf, qs, tb + tab.c[i] * h);
+          float* slot_i = slots + (size_t)i * SC;
+          rhs_tendencies<CT, NT, NF>(M, in, arena, bcf, [=](int k0, int c, const float (&dx)[NF][4]) {
+#pragma unroll
+            for (int q = 0; q < NF; ++q)
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) __stcg(slot_i + (q * N + k0 + kk) * CT + c, dx[q][kk]);
+          });
           __syncthreads();
         }
         // (b) reverse stages
@@ -574,6 +579,16 @@ __global__ void __launch_bounds__(NT, 1) adjoint_kernel(const __grid_constant__ 
     }
     __syncthreads();
   }
+}
+
+template <int CT, int NT, bool WS>
+__global__ void __launch_bounds__(NT, 1) adjoint_kernel(const __grid_constant__ ModelD Mp, const __grid_constant__ TableauD tab,
+                                                        const TimeD tm, const __grid_constant__ AdjArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const AdjSmem L = adjoint_smem_layout(Mp, CT);
+  const ModelD& M = model_to_smem<NT>(Mp, smem + L.model);
+  if (Mp.nf == 3) adjoint_body<CT, NT, WS, 3>(M, tab, tm, a, smem);
+  else adjoint_body<CT, NT, WS, 1>(M, tab, tm, a, smem);
 }
 
 // ---- small reductions -----------------------------------------------------------------------------------------------

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -64,6 +65,24 @@ static int launch_solve_t(cpz_model* m, const SolveArgs& a) {
   auto kern = solve_kernel<CT, NT, WS>;
   CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_tiles = (a.ncol + CT - 1) / CT;
+  static const bool prof = getenv("CPZ_PROF") != nullptr;
+  if (prof && !a.rhs_only) {  // debug: per-phase cycle counters of CTA 0
+    SolveArgs ap = a;
+    unsigned long long* d = nullptr;
+    CPZ_CUDA(cudaMalloc(&d, 8 * sizeof(unsigned long long)));
+    CPZ_CUDA(cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), m->ctx->stream));
+    ap.prof = d;
+    kern<<<n_tiles, NT, smem, m->ctx->stream>>>(m->fwd.M, m->tab, m->tm, ap);
+    unsigned long long hcnt[8];
+    CPZ_CUDA(cudaMemcpyAsync(hcnt, d, sizeof(hcnt), cudaMemcpyDeviceToHost, m->ctx->stream));
+    CPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    cudaFree(d);
+    const double n_rhs = (double)m->tm.n_steps * m->tm.n_substeps * m->tab.n_stages;
+    fprintf(stderr, "[cpz prof] cycles per RHS: phase0 %.0f phase1 %.0f phase2 %.0f phase3+ %.0f stencil+update %.0f | per step: save %.0f | total/RHS %.0f\n",
+            hcnt[0] / n_rhs, hcnt[1] / n_rhs, hcnt[2] / n_rhs, hcnt[3] / n_rhs, hcnt[4] / n_rhs, hcnt[5] / (double)m->tm.n_steps, hcnt[7] / n_rhs);
+    m->ctx->launches++;
+    return CPZ_OK;
+  }
   kern<<<n_tiles, NT, smem, m->ctx->stream>>>(m->fwd.M, m->tab, m->tm, a);
   CPZ_CUDA(cudaGetLastError());
   m->ctx->launches++;
@@ -87,7 +106,7 @@ static int bind_device(const cpz_ctx* c) {
 
 static size_t solve_other_smem(const cpz_model_desc& d, int CT, int n_stages) {
   const int S = d.n_fields * d.Nz, nbc = d.n_fields == 3 ? 6 : 2;
-  return ((size_t)S * CT + (size_t)CT * (S + 4) + (size_t)n_stages * S * CT + (size_t)nbc * CT + CT + 4) * sizeof(float);
+  return ((size_t)3 * CT * (S + 4) + (size_t)n_stages * S * CT + (size_t)nbc * CT + CT + 4) * sizeof(float) + ((sizeof(ModelD) + 15) / 16) * 16;
 }
 
 static int rebuild_plans(cpz_model* m) {
@@ -254,7 +273,7 @@ int cpz_model_describe(const cpz_model* m, char* buf, size_t buf_len) {
              M.arena_floats, M.flux_off);
     s += line;
     for (int p = 0; p < M.n_phase; ++p) {
-      snprintf(line, sizeof(line), "  phase %d: tiles=%d:", p, M.phase[p].n_tiles);
+      snprintf(line, sizeof(line), "  phase %d: tiles=%d TO=%d ksplit=%d:", p, M.phase[p].n_tiles, M.phase[p].TO, M.phase[p].ksplit);
       s += line;
       for (int g = M.phase[p].g0; g < M.phase[p].g1; ++g) {
         const GemmD& G = M.gemm[g];

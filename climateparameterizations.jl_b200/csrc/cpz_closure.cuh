@@ -7,6 +7,7 @@
 // the [level][column] shared-memory layout of the MLP with fully coalesced 128-byte accesses and no transpose.
 #pragma once
 #include "cpz_device.cuh"
+#include "cpz_solve.cuh"
 
 namespace cpz {
 
@@ -29,7 +30,7 @@ struct ClosureArgs {
 };
 
 struct ClosureSmem {
-  int w, tt, xin, arena, cp, total_floats;
+  int w, tt, xin, arena, cp, model, total_floats;
 };
 __host__ __device__ inline ClosureSmem closure_smem_layout(const ModelD& M, int CT) {
   ClosureSmem L;
@@ -39,14 +40,16 @@ __host__ __device__ inline ClosureSmem closure_smem_layout(const ModelD& M, int 
   L.xin = o; o += M.Nz * CT;      // scaled NN input
   L.arena = o; o += M.arena_floats * CT;
   L.cp = o; o += M.Nz * CT;       // Thomas c' coefficients
+  L.model = o; o += (int)((sizeof(ModelD) + 15) / 16) * 4;
   L.total_floats = o + 4;
   return L;
 }
 
 template <int CT, int NT, bool WS>
-__global__ void __launch_bounds__(NT, 1) closure_kernel(const __grid_constant__ ModelD M, const ClosureD cd, const ClosureArgs a) {
+__global__ void __launch_bounds__(NT, 1) closure_kernel(const __grid_constant__ ModelD Mp, const ClosureD cd, const ClosureArgs a) {
   extern __shared__ __align__(16) float smem[];
-  const ClosureSmem L = closure_smem_layout(M, CT);
+  const ClosureSmem L = closure_smem_layout(Mp, CT);
+  const ModelD& M = model_to_smem<NT>(Mp, smem + L.model);
   float* wsm = smem + L.w;
   float* tt = smem + L.tt;
   float* xin = smem + L.xin;

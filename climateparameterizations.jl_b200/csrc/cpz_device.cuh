@@ -107,44 +107,62 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+__device__ __forceinline__ float4 act_fwd4(int act, float4 z) {
+  float4 r;
+  switch (act) {
+    case ACT_RELU: r = make_float4(fmaxf(z.x, 0.f), fmaxf(z.y, 0.f), fmaxf(z.z, 0.f), fmaxf(z.w, 0.f)); break;
+    case ACT_MISH: r = make_float4(act_fwd(ACT_MISH, z.x), act_fwd(ACT_MISH, z.y), act_fwd(ACT_MISH, z.z), act_fwd(ACT_MISH, z.w)); break;
+    case ACT_SWISH: r = make_float4(act_fwd(ACT_SWISH, z.x), act_fwd(ACT_SWISH, z.y), act_fwd(ACT_SWISH, z.z), act_fwd(ACT_SWISH, z.w)); break;
+    case ACT_LEAKY: r = make_float4(act_fwd(ACT_LEAKY, z.x), act_fwd(ACT_LEAKY, z.y), act_fwd(ACT_LEAKY, z.z), act_fwd(ACT_LEAKY, z.w)); break;
+    case ACT_TANH: r = make_float4(act_fwd(ACT_TANH, z.x), act_fwd(ACT_TANH, z.y), act_fwd(ACT_TANH, z.z), act_fwd(ACT_TANH, z.w)); break;
+    default: r = z; break;
+  }
+  return r;
+}
+
 // ---- dense layer: one 4-column x TO-output register tile (TO even) ---------------------------------------------
 // in:  [K][CT] shared, out: [N][CT] shared (post-activation), zout (optional): [N][CT] pre-activation.
 // WS: weights come from the shared arena (row stride Npad, zero padded) else straight from theta in global.
 // The accumulators are output PAIRS (float2) per column so the inner loop is FFMA2 (packed FP32, sm_100):
 //   acc[p][c] += (w[2p], w[2p+1]) * x[c]     -> FFMA2 R, R.F32x2, R.F32 (scalar broadcast), R.F32x2
 // per k: 1 LDS.128 (4 columns of the input row) + TO/2 LDS.64 (or TO/4 LDS.128) of the weight row, 2*TO FFMA2.
-template <int TO, bool WS, int CT, bool SAVE_Z>
-__device__ __forceinline__ void gemm_tile_fwd(const GemmD& g, const float* __restrict__ in, float* __restrict__ out,
-                                              float* __restrict__ zout, const float* __restrict__ W,
-                                              const float* __restrict__ bias, int cg, int og) {
-  static_assert(TO % 2 == 0, "TO must be even");
+template <int TO, bool WS, int CT>
+__device__ __forceinline__ void gemm_tile_accum(const GemmD& g, const float* __restrict__ in, const float* __restrict__ W,
+                                                int cg, int og, int k0, int k1, float2 (&acc)[TO / 2][4]) {
   constexpr int TP = TO / 2;
   const int j0 = og * TO;
-  const int K = g.K, N = g.N;
-  float2 acc[TP][4];
+  const int N = g.N;
   if constexpr (WS) {
-#pragma unroll
-    for (int p = 0; p < TP; ++p) {
-      const float2 bv = *reinterpret_cast<const float2*>(bias + j0 + 2 * p);
-      acc[p][0] = bv; acc[p][1] = bv; acc[p][2] = bv; acc[p][3] = bv;
-    }
-    const float* xp = in + 4 * cg;
-    const float* wp = W + j0;
     const int ldw = g.Npad;
-#pragma unroll 2
-    for (int k = 0; k < K; ++k) {
-      const float4 xv = *reinterpret_cast<const float4*>(xp);
-      float2 w[TP];
+    const float* xp = in + 4 * cg + k0 * CT;
+    const float* wp = W + j0 + k0 * ldw;
+    // software pipeline: the operands of iteration k+1 are loaded before the FFMA2s of iteration k issue
+    auto load_w = [&](const float* wq, float2 (&w)[TP]) {
       if constexpr (TO % 4 == 0) {
 #pragma unroll
         for (int p = 0; p < TP; p += 2) {
-          const float4 wv = *reinterpret_cast<const float4*>(wp + 2 * p);
+          const float4 wv = *reinterpret_cast<const float4*>(wq + 2 * p);
           w[p] = make_float2(wv.x, wv.y);
           w[p + 1] = make_float2(wv.z, wv.w);
         }
       } else {
 #pragma unroll
-        for (int p = 0; p < TP; ++p) w[p] = *reinterpret_cast<const float2*>(wp + 2 * p);
+        for (int p = 0; p < TP; ++p) w[p] = *reinterpret_cast<const float2*>(wq + 2 * p);
+      }
+    };
+    if (k0 >= k1) return;
+    float4 xv = *reinterpret_cast<const float4*>(xp);
+    float2 w[TP];
+    load_w(wp, w);
+#pragma unroll 2
+    for (int k = k0; k < k1; ++k) {
+      float4 xn = xv;
+      float2 wn[TP];
+#pragma unroll
+      for (int p = 0; p < TP; ++p) wn[p] = w[p];
+      if (k + 1 < k1) {
+        xn = *reinterpret_cast<const float4*>(xp + CT);
+        load_w(wp + ldw, wn);
       }
       const float2 x0 = make_float2(xv.x, xv.x), x1 = make_float2(xv.y, xv.y), x2 = make_float2(xv.z, xv.z),
                    x3 = make_float2(xv.w, xv.w);
@@ -155,6 +173,9 @@ __device__ __forceinline__ void gemm_tile_fwd(const GemmD& g, const float* __res
         acc[p][2] = __ffma2_rn(w[p], x2, acc[p][2]);
         acc[p][3] = __ffma2_rn(w[p], x3, acc[p][3]);
       }
+      xv = xn;
+#pragma unroll
+      for (int p = 0; p < TP; ++p) w[p] = wn[p];
       xp += CT;
       wp += ldw;
     }
@@ -162,15 +183,10 @@ __device__ __forceinline__ void gemm_tile_fwd(const GemmD& g, const float* __res
     int jo[TO];
 #pragma unroll
     for (int o = 0; o < TO; ++o) jo[o] = min(j0 + o, N - 1);
-#pragma unroll
-    for (int p = 0; p < TP; ++p) {
-      const float2 bv = make_float2(__ldg(bias + jo[2 * p]), __ldg(bias + jo[2 * p + 1]));
-      acc[p][0] = bv; acc[p][1] = bv; acc[p][2] = bv; acc[p][3] = bv;
-    }
-    const float* xp = in + 4 * cg;
-    const float* wp = W;
+    const float* xp = in + 4 * cg + k0 * CT;
+    const float* wp = W + (size_t)k0 * N;
 #pragma unroll 2
-    for (int k = 0; k < K; ++k) {
+    for (int k = k0; k < k1; ++k) {
       const float4 xv = *reinterpret_cast<const float4*>(xp);
       float2 w[TP];
 #pragma unroll
@@ -188,38 +204,103 @@ __device__ __forceinline__ void gemm_tile_fwd(const GemmD& g, const float* __res
       wp += N;
     }
   }
-  const int act = g.act;
+}
+
+template <int TO, bool WS>
+__device__ __forceinline__ void gemm_tile_init(const GemmD& g, const float* __restrict__ bias, int og, bool with_bias,
+                                               float2 (&acc)[TO / 2][4]) {
+  const int j0 = og * TO;
 #pragma unroll
-  for (int p = 0; p < TP; ++p) {
+  for (int p = 0; p < TO / 2; ++p) {
+    float2 bv = make_float2(0.f, 0.f);
+    if (with_bias) {
+      if constexpr (WS) bv = *reinterpret_cast<const float2*>(bias + j0 + 2 * p);
+      else bv = make_float2(__ldg(bias + min(j0 + 2 * p, g.N - 1)), __ldg(bias + min(j0 + 2 * p + 1, g.N - 1)));
+    }
+    acc[p][0] = bv; acc[p][1] = bv; acc[p][2] = bv; acc[p][3] = bv;
+  }
+}
+
+// finish output pair p of a tile: z = acc (+ partial already stored in out, when ADD_OUT), a = act(z)
+template <int CT, bool SAVE_Z, bool ADD_OUT>
+__device__ __forceinline__ void gemm_pair_finish(const GemmD& g, float* __restrict__ out, float* __restrict__ zout, int j,
+                                                 int cg, const float2 (&a4)[4]) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int j = j0 + 2 * p + h;
-      if (j < N) {
-        float4 z;
-        z.x = h ? acc[p][0].y : acc[p][0].x;
-        z.y = h ? acc[p][1].y : acc[p][1].x;
-        z.z = h ? acc[p][2].y : acc[p][2].x;
-        z.w = h ? acc[p][3].y : acc[p][3].x;
-        if constexpr (SAVE_Z) *reinterpret_cast<float4*>(zout + j * CT + 4 * cg) = z;
-        float4 r;
-        r.x = act_fwd(act, z.x);
-        r.y = act_fwd(act, z.y);
-        r.z = act_fwd(act, z.z);
-        r.w = act_fwd(act, z.w);
-        *reinterpret_cast<float4*>(out + j * CT + 4 * cg) = r;
+  for (int h = 0; h < 2; ++h) {
+    const int jj = j + h;
+    if (jj < g.N) {
+      float4 z;
+      z.x = h ? a4[0].y : a4[0].x;
+      z.y = h ? a4[1].y : a4[1].x;
+      z.z = h ? a4[2].y : a4[2].x;
+      z.w = h ? a4[3].y : a4[3].x;
+      float4* po = reinterpret_cast<float4*>(out + jj * CT + 4 * cg);
+      if constexpr (ADD_OUT) {
+        const float4 q = *po;
+        z.x += q.x; z.y += q.y; z.z += q.z; z.w += q.w;
       }
+      if constexpr (SAVE_Z) *reinterpret_cast<float4*>(zout + jj * CT + 4 * cg) = z;
+      *po = act_fwd4(g.act, z);
     }
   }
 }
 
-// One phase = the gemms [g0,g1) of the plan, run over a flattened (gemm, output group, column group) tile space.
-// X: state tile [S][CT]; arena: activations [rows][CT]; zarena: pre-activations (same row offsets) when SAVE_Z.
-template <bool WS, int CT, int NT, bool SAVE_Z>
-__device__ __forceinline__ void run_phase(const ModelD& M, int p, const float* __restrict__ X, float* __restrict__ arena,
-                                          float* __restrict__ zarena, const float* __restrict__ wsm,
-                                          const float* __restrict__ theta) {
+// raw partial sums of output pair p into the out rows (no activation)
+template <int CT>
+__device__ __forceinline__ void gemm_pair_stash(const GemmD& g, float* __restrict__ out, int j, int cg, const float2 (&a4)[4]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int jj = j + h;
+    if (jj < g.N)
+      *reinterpret_cast<float4*>(out + jj * CT + 4 * cg) =
+          make_float4(h ? a4[0].y : a4[0].x, h ? a4[1].y : a4[1].x, h ? a4[2].y : a4[2].x, h ? a4[3].y : a4[3].x);
+  }
+}
+
+// One phase with uniform tile shape TO. KS = 1: each thread owns whole tiles (strided over the flattened tile space).
+// KS = 2 (n_tiles <= NT/2): threads [0,NT/2) and [NT/2,NT) each take half of the k range of the same tile so that every
+// SM sub-partition has two warps to interleave (LDS issue stalls of one hide under the FFMA2 stream of the other);
+// the halves exchange partial sums through the output rows and each finishes half of the tile's outputs.
+template <int TO, bool WS, int CT, int NT, bool SAVE_Z>
+__device__ __noinline__ void run_phase_t(const ModelD& M, int p, const float* __restrict__ X, float* __restrict__ arena,
+                                            float* __restrict__ zarena, const float* __restrict__ wsm,
+                                            const float* __restrict__ theta) {
   constexpr int NCG = CT / 4;
+  constexpr int TP = TO / 2;
   const int g0 = M.phase[p].g0, g1 = M.phase[p].g1, n_tiles = M.phase[p].n_tiles;
+  if (M.phase[p].ksplit == 2) {
+    const int half = threadIdx.x / (NT / 2), tile = threadIdx.x - half * (NT / 2);
+    const bool active = tile < n_tiles;
+    int gi = g0;
+    if (active)
+      while (gi + 1 < g1 && tile >= M.gemm[gi + 1].tile_begin) ++gi;
+    const GemmD& g = M.gemm[gi];
+    const int local = active ? tile - g.tile_begin : 0;
+    const int cg = local % NCG, og = local / NCG;
+    const float* in = g.in_off < 0 ? X : arena + g.in_off * CT;
+    float* out = arena + g.out_off * CT;
+    float* zo = SAVE_Z ? zarena + g.out_off * CT : nullptr;
+    const float* W = WS ? wsm + g.sw_off : theta + g.w_off;
+    const float* B = WS ? wsm + g.sb_off : theta + g.b_off;
+    float2 acc[TP][4];
+    constexpr int P0 = (TP + 1) / 2;  // pairs finished by half 0; half 1 finishes the remaining TP-P0
+    if (active) {
+      const int kmid = g.K / 2;
+      gemm_tile_init<TO, WS>(g, B, og, half == 0, acc);
+      gemm_tile_accum<TO, WS, CT>(g, in, W, cg, og, half == 0 ? 0 : kmid, half == 0 ? kmid : g.K, acc);
+      // stash the partials of the pairs the OTHER half finishes
+#pragma unroll
+      for (int q = 0; q < TP; ++q)
+        if ((q < P0) == (half == 1)) gemm_pair_stash<CT>(g, out, og * TO + 2 * q, cg, acc[q]);
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int q = 0; q < TP; ++q)
+        if ((q < P0) == (half == 0)) gemm_pair_finish<CT, SAVE_Z, true>(g, out, zo, og * TO + 2 * q, cg, acc[q]);
+    }
+    return;
+  }
   for (int tile = threadIdx.x; tile < n_tiles; tile += NT) {
     int gi = g0;
     while (gi + 1 < g1 && tile >= M.gemm[gi + 1].tile_begin) ++gi;
@@ -231,20 +312,34 @@ __device__ __forceinline__ void run_phase(const ModelD& M, int p, const float* _
     float* zo = SAVE_Z ? zarena + g.out_off * CT : nullptr;
     const float* W = WS ? wsm + g.sw_off : theta + g.w_off;
     const float* B = WS ? wsm + g.sb_off : theta + g.b_off;
-    switch (g.TO) {
-      case 2: gemm_tile_fwd<2, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
-      case 4: gemm_tile_fwd<4, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
-      case 6: gemm_tile_fwd<6, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
-      case 8: gemm_tile_fwd<8, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
-      case 10: gemm_tile_fwd<10, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
-      default: gemm_tile_fwd<12, WS, CT, SAVE_Z>(g, in, out, zo, W, B, cg, og); break;
-    }
+    float2 acc[TP][4];
+    gemm_tile_init<TO, WS>(g, B, og, true, acc);
+    gemm_tile_accum<TO, WS, CT>(g, in, W, cg, og, 0, g.K, acc);
+#pragma unroll
+    for (int q = 0; q < TP; ++q) gemm_pair_finish<CT, SAVE_Z, false>(g, out, zo, og * TO + 2 * q, cg, acc[q]);
+  }
+}
+
+// One phase = the gemms [g0,g1) of the plan, run over a flattened (gemm, output group, column group) tile space.
+// X: state tile [S][CT]; arena: activations [rows][CT]; zarena: pre-activations (same row offsets) when SAVE_Z.
+// All gemms of a phase share one tile shape (planner), so the dispatch is block-uniform.
+template <bool WS, int CT, int NT, bool SAVE_Z>
+__device__ __forceinline__ void run_phase(const ModelD& M, int p, const float* __restrict__ X, float* __restrict__ arena,
+                                          float* __restrict__ zarena, const float* __restrict__ wsm,
+                                          const float* __restrict__ theta) {
+  switch (M.phase[p].TO) {
+    case 2: run_phase_t<2, WS, CT, NT, SAVE_Z>(M, p, X, arena, zarena, wsm, theta); break;
+    case 4: run_phase_t<4, WS, CT, NT, SAVE_Z>(M, p, X, arena, zarena, wsm, theta); break;
+    case 6: run_phase_t<6, WS, CT, NT, SAVE_Z>(M, p, X, arena, zarena, wsm, theta); break;
+    case 8: run_phase_t<8, WS, CT, NT, SAVE_Z>(M, p, X, arena, zarena, wsm, theta); break;
+    case 10: run_phase_t<10, WS, CT, NT, SAVE_Z>(M, p, X, arena, zarena, wsm, theta); break;
+    default: run_phase_t<12, WS, CT, NT, SAVE_Z>(M, p, X, arena, zarena, wsm, theta); break;
   }
 }
 
 // Copy theta into the shared weight arena in the plan's padded layout (rows of Npad floats, zero padded).
 template <int NT>
-__device__ __forceinline__ void load_weights_smem(const ModelD& M, float* __restrict__ wsm, const float* __restrict__ theta) {
+__device__ __noinline__ void load_weights_smem(const ModelD& M, float* __restrict__ wsm, const float* __restrict__ theta) {
   for (int i = threadIdx.x; i < M.smem_w_floats; i += NT) wsm[i] = 0.f;
   __syncthreads();
   for (int gi = 0; gi < M.n_gemm; ++gi) {
@@ -321,7 +416,7 @@ __device__ __forceinline__ float nu_of_ri(const ModelD& M, float Ri) {
 // E is the total (NN + diffusive [+ boundary]) flux whose cell-difference gives the tendency.
 // nn rows come from the activation arena (M.nn_off), or are zero when the model has no nets.
 template <int CT, int NT>
-__device__ __forceinline__ void faces_phase(const ModelD& M, const float* __restrict__ X, const float* __restrict__ arena,
+__device__ __noinline__ void faces_phase(const ModelD& M, const float* __restrict__ X, const float* __restrict__ arena,
                                             float* __restrict__ E, const float* __restrict__ bcf /*[nbc][CT]*/) {
   const int N = M.Nz;
   const int nfaces = N + 1;
@@ -412,11 +507,92 @@ __device__ __forceinline__ float tendency(const ModelD& M, const float* __restri
   return r;
 }
 
+// ---- fused, register-blocked stencil ------------------------------------------------------------------------------------
+// One work item = 4 consecutive levels of one column, all fields: the thread loads the 6 levels it needs per field,
+// evaluates the 5 bounding face fluxes in registers (mPP diffusivity, convective adjustment, NN fluxes, boundary
+// fluxes) and hands the 4 x NF tendencies to `sink(k0, c, dx)`. No flux scratch in shared memory, no barrier between
+// "faces" and "centres"; a warp is 32 consecutive columns of one level group (conflict-free LDS).
+// Not used for the smooth_NN / smooth_Ri variants (they need neighbouring faces' values; see faces_phase).
+template <int CT, int NT, int NF, class Sink>
+__device__ __noinline__ void stencil_fused(const ModelD& M, const float* __restrict__ X, const float* __restrict__ arena,
+                                           const float* __restrict__ bcf, Sink sink) {
+  const int N = M.Nz;
+  const bool has_nn = M.n_nets > 0;
+  const bool mpp = NF == 3 && ((M.flags & F_MPP) || M.variant == RHS_INFER);
+  const bool ca = (M.flags & F_CA) != 0;
+  const float eps = M.variant == RHS_TRAIN ? M.rc.eps : 0.f;
+  const float Nf = M.rc.Nf;
+  const int n_items = (N / 4) * CT;
+  for (int it = threadIdx.x; it < n_items; it += NT) {
+    const int kg = it / CT, c = it - kg * CT;
+    const int k0 = 4 * kg;
+    // levels k0-1 .. k0+4 (clamped; the clamped values only feed boundary faces, which use bcf instead)
+    float xl[NF][6];
+#pragma unroll
+    for (int q = 0; q < NF; ++q)
+#pragma unroll
+      for (int l = 0; l < 6; ++l) {
+        const int k = min(max(k0 - 1 + l, 0), N - 1);
+        xl[q][l] = X[(q * N + k) * CT + c];
+      }
+    float E[NF][5];
+#pragma unroll
+    for (int fi = 0; fi < 5; ++fi) {
+      const int f = k0 + fi;  // face between levels f-1 and f
+      if (f == 0 || f == N) {
+        const int tb = f == 0 ? 0 : 1;
+#pragma unroll
+        for (int q = 0; q < NF; ++q) E[q][fi] = bcf[(2 * q + tb) * CT + c];
+        continue;
+      }
+      float nn[NF];
+#pragma unroll
+      for (int q = 0; q < NF; ++q) nn[q] = has_nn ? arena[(M.nn_off[q] + f - 1) * CT + c] : 0.f;
+      float G[NF];
+#pragma unroll
+      for (int q = 0; q < NF; ++q) G[q] = Nf * (xl[q][fi + 1] - xl[q][fi]);
+      if constexpr (NF == 1) {
+        E[0][fi] = ca ? nn[0] - fminf(0.f, M.rc.K_ca * G[0]) : nn[0];
+      } else {
+        if (mpp) {
+          const float su = M.rc.sig_u * (G[0] + eps), sv = M.rc.sig_v * (G[1] + eps);
+          const float Ri = __fdividef(M.rc.BzC * (G[2] + eps), su * su + sv * sv);
+          const float nu = nu_of_ri(M, Ri);
+          float nuT = nu * M.rc.inv_Pr;
+          if (M.variant == RHS_INFER && ca) {
+            const float test = (M.flags & F_CA_LITERAL_U) ? G[0] : G[2];
+            nuT = test > 0.f ? nuT : M.rc.kappa;
+          }
+          E[0][fi] = nn[0] - M.rc.c[0] * nu * G[0];
+          E[1][fi] = nn[1] - M.rc.c[1] * nu * G[1];
+          E[2][fi] = nn[2] - M.rc.c[2] * nuT * G[2];
+        } else {
+          E[0][fi] = nn[0];
+          E[1][fi] = nn[1];
+          E[2][fi] = ca ? nn[2] - M.rc.c[2] * M.rc.kappa * fminf(0.f, G[2]) : nn[2];
+        }
+      }
+    }
+    float dx[NF][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      if constexpr (NF == 1) {
+        dx[0][kk] = -M.rc.A[2] * Nf * (E[0][kk + 1] - E[0][kk]);
+      } else {
+        dx[0][kk] = -M.rc.A[0] * Nf * (E[0][kk + 1] - E[0][kk]) + (M.rc.cor_u_s * xl[1][kk + 1] + M.rc.cor_u_m);
+        dx[1][kk] = -M.rc.A[1] * Nf * (E[1][kk + 1] - E[1][kk]) - (M.rc.cor_v_s * xl[0][kk + 1] + M.rc.cor_v_m);
+        dx[2][kk] = -M.rc.A[2] * Nf * (E[2][kk + 1] - E[2][kk]);
+      }
+    }
+    sink(k0, c, dx);
+  }
+}
+
 // ---- tile <-> global transposes --------------------------------------------------------------------------------------
 // Load columns [col0, col0+CT) of a [ncol][S] global array into dst[S][CT] through `stage` ([CT][S+4] floats),
 // using one bulk async copy per column. Columns past ncol replicate the last valid one (keeps the math finite).
 template <int CT, int NT>
-__device__ __forceinline__ void load_tile(float* __restrict__ dst, float* __restrict__ stage, uint64_t* bar, uint32_t& parity,
+__device__ __noinline__ void load_tile(float* __restrict__ dst, float* __restrict__ stage, uint64_t* bar, uint32_t& parity,
                                           const float* __restrict__ src, size_t row_stride, int S, int col0, int ncol) {
   const int SP = S + 4;
   if (threadIdx.x == 0) mbar_expect_tx(bar, (uint32_t)(CT * S * sizeof(float)));
@@ -442,7 +618,7 @@ __device__ __forceinline__ void load_tile(float* __restrict__ dst, float* __rest
 // The caller must __syncthreads() before (src complete) — this function syncs internally before issuing and the
 // issuing threads must call bulk_wait_read0() before `stage` is overwritten again.
 template <int CT, int NT>
-__device__ __forceinline__ void store_tile(const float* __restrict__ src, float* __restrict__ stage, float* __restrict__ dstg,
+__device__ __noinline__ void store_tile(const float* __restrict__ src, float* __restrict__ stage, float* __restrict__ dstg,
                                            size_t row_stride, int S, int col0, int ncol) {
   const int SP = S + 4;
   const int S4 = S / 4;

@@ -89,26 +89,57 @@ int lds_count(int TO, bool ws) {
   return TO / 2;
 }
 
-// Estimated issue cycles of one phase on the busiest SM sub-partition for a uniform TO.
-double phase_cost(const std::vector<std::pair<int, int>>& kn /*(K,N) per gemm*/, int TO, int NCG, int NT, bool ws) {
+double act_cost(int act) {
+  switch (act) {
+    case CPZ_ACT_MISH: return 10;
+    case CPZ_ACT_SWISH: return 6;
+    case CPZ_ACT_TANH: return 7;
+    default: return 1.5;
+  }
+}
+
+struct KN { int K, N, act; };
+
+// Estimated cycles of one phase on the busiest SM sub-partition for a uniform tile shape (TO, ksplit).
+// Measured on B200 (profiles/r01_forward_*.txt): an FFMA2 occupies the FMA pipe for 2 cycles, a shared load costs
+// ~3.7 issue cycles of its warp; with a single warp on a sub-partition the two do not overlap, with two or more
+// they do.
+double phase_cost(const std::vector<KN>& kn, int TO, int ksplit, int NCG, int NT, bool ws) {
   long tiles = 0;
-  double per_tile = 0;
+  double fma_tile = 0, ser_tile = 0, epi_tile = 0;
   for (auto& g : kn) {
-    const int n_og = (g.second + TO - 1) / TO;
+    const int n_og = (g.N + TO - 1) / TO;
     tiles += (long)n_og * NCG;
-    // per k: 2*TO FFMA2 occupy the FMA pipe for 4*TO cycles; issue slots = 2*TO + loads + 2
-    const double per_k = std::max(4.0 * TO, 2.0 * TO + 1 + lds_count(TO, ws) + 2) + 2.0;
-    per_tile = std::max(per_tile, (double)g.first * per_k + 14.0 * TO + 40.0);
+    const double kk = (double)g.K / ksplit;
+    const double L = 1 + lds_count(TO, ws);
+    fma_tile = std::max(fma_tile, kk * 4.0 * TO);
+    ser_tile = std::max(ser_tile, kk * (4.0 * TO + (ws ? 3.7 : 6.0) * L + 2));
+    epi_tile = std::max(epi_tile, (TO * (4 * act_cost(g.act) + 4.0)) / ksplit + 30.0 + (ksplit == 2 ? TO * 3.0 + 80.0 : 0.0));
   }
+  if (ksplit == 2 && tiles > NT / 2) return 1e300;
   const int warps = NT / 32;
-  double smsp[4] = {0, 0, 0, 0};
+  double fma[4] = {0, 0, 0, 0}, ser[4] = {0, 0, 0, 0};
+  int nw[4] = {0, 0, 0, 0};
   for (int w = 0; w < warps; ++w) {
-    const long first = (long)w * 32;
-    if (first >= tiles) break;
-    const long cnt = (tiles - first + NT - 1) / NT;  // tiles of the first lane of the warp = the warp's maximum
-    smsp[w % 4] += cnt * per_tile;
+    long cnt;
+    if (ksplit == 2) {
+      const long first = (long)(w % (warps / 2)) * 32;
+      cnt = first < tiles ? 1 : 0;
+    } else {
+      const long first = (long)w * 32;
+      cnt = first < tiles ? (tiles - first + NT - 1) / NT : 0;
+    }
+    if (cnt == 0) continue;
+    fma[w % 4] += cnt * fma_tile;
+    ser[w % 4] += cnt * (ser_tile + epi_tile);
+    nw[w % 4]++;
   }
-  return std::max(std::max(smsp[0], smsp[1]), std::max(smsp[2], smsp[3]));
+  double worst = 0;
+  for (int s = 0; s < 4; ++s) {
+    const double t = nw[s] <= 1 ? ser[s] : std::max(fma[s] * 1.08 + 0.5 * (ser[s] - fma[s]) / nw[s], 0.62 * ser[s]);
+    worst = std::max(worst, t);
+  }
+  return worst;
 }
 
 }  // namespace
@@ -171,7 +202,10 @@ bool build_plan(const cpz_model_desc& d, const PlanOptions& opt, Plan& out, std:
   }
   if (d.n_nets * maxL > CPZ_MAX_GEMM) { err = "too many layers"; return false; }
 
-  const int flux_rows = d.n_fields * (N + 1);
+  // face-flux scratch rows: the adjoint keeps face-gradient cotangents there; the forward kernel only needs them for the
+  // (slow, two-phase) smoothing variants — the default stencil is fused and register-blocked.
+  const bool smoothing = (d.flags & (CPZ_FLAG_SMOOTH_NN | CPZ_FLAG_SMOOTH_RI)) != 0;
+  const int flux_rows = (opt.keep_all || smoothing) ? d.n_fields * (N + 1) : 0;
 
   // ---- activation arena + phase schedule ----
   auto plan_schedule = [&](bool layer_major, std::vector<std::vector<int>>& phases /*gemm ids*/, std::vector<GemmD>& gemms,
@@ -272,6 +306,7 @@ bool build_plan(const cpz_model_desc& d, const PlanOptions& opt, Plan& out, std:
   };
 
   std::vector<std::vector<int>> phases;
+  std::vector<int> phase_to, phase_ks;
   std::vector<GemmD> gemms;
   int arena_rows = 0, nn_off[3], flux_off = 0;
   bool chosen = false;
@@ -280,18 +315,21 @@ bool build_plan(const cpz_model_desc& d, const PlanOptions& opt, Plan& out, std:
     if (attempt == 0 && !same_depth) continue;
     plan_schedule(layer_major, phases, gemms, arena_rows, nn_off, flux_off);
     // choose TO per phase
+    phase_to.clear(); phase_ks.clear();
     for (auto& ph : phases) {
-      std::vector<std::pair<int, int>> kn;
-      for (int gi : ph) kn.push_back({gemms[gi].K, gemms[gi].N});
-      int best = 4; double bc = 1e300;
+      std::vector<KN> kn;
+      for (int gi : ph) kn.push_back({gemms[gi].K, gemms[gi].N, gemms[gi].act});
+      int best = 4, best_ks = 1; double bc = 1e300;
       const int cand_f[] = {2, 4, 6, 8, 10, 12};
       const int cand_b[] = {4, 8, 12};
       const int* cand = opt.keep_all ? cand_b : cand_f;
       const int nc = opt.keep_all ? 3 : 6;
-      for (int ci = 0; ci < nc; ++ci) {
-        const double c1 = phase_cost(kn, cand[ci], NCG, opt.NT, true);
-        if (c1 < bc) { bc = c1; best = cand[ci]; }
-      }
+      for (int ci = 0; ci < nc; ++ci)
+        for (int ks = 1; ks <= 2; ++ks) {
+          const double c1 = phase_cost(kn, cand[ci], ks, NCG, opt.NT, true);
+          if (c1 < bc) { bc = c1; best = cand[ci]; best_ks = ks; }
+        }
+      phase_to.push_back(best); phase_ks.push_back(best_ks);
       int tb = 0;
       for (int gi : ph) {
         GemmD& g = gemms[gi];
@@ -339,6 +377,8 @@ bool build_plan(const cpz_model_desc& d, const PlanOptions& opt, Plan& out, std:
     int nt = 0;
     for (int gi : phases[p]) nt += gemms[gi].n_og * NCG;
     M.phase[p].n_tiles = nt;
+    M.phase[p].TO = phase_to[p];
+    M.phase[p].ksplit = phase_ks[p];
   }
   M.arena_floats = arena_rows;
   for (int n = 0; n < 3; ++n) M.nn_off[n] = nn_off[n];

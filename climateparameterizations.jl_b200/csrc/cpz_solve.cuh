@@ -18,31 +18,43 @@ struct SolveArgs {
   int n_ckpt;
   int rhs_only;
   float t_rhs;
+  unsigned long long* prof;  // optional [8] cycle counters (CTA 0, thread 0): set CPZ_PROF=1 in the environment
 };
+
+#define CPZ_PROF_BEGIN() const long long prof_t0__ = (a.prof && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0
+#define CPZ_PROF_END(slot)                                                                     \
+  do {                                                                                         \
+    if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[slot] += (unsigned long long)(clock64() - prof_t0__); \
+  } while (0)
 
 // shared-memory carve-up (floats) used by solve_kernel and by the host to size the launch
 struct SolveSmem {
-  int w, xs, xa, ks, arena, bcf, qs, total_floats;
+  int w, buf, bufsz, ks, arena, bcf, qs, model, total_floats;
 };
 __host__ __device__ inline SolveSmem solve_smem_layout(const ModelD& M, int CT, int n_stages) {
   SolveSmem L;
   int o = 0;
   L.w = o; o += M.w_in_smem ? M.smem_w_floats : 0;
-  L.xs = o; o += M.S * CT;
-  L.xa = o; o += CT * (M.S + 4);  // stage input for stages >= 1, doubles as the [CT][S+4] transpose staging buffer
+  // three rotating [S][CT] buffers (step state, two alternating stage inputs); each is large enough to double as the
+  // [CT][S+4] transpose staging buffer of the bulk copies
+  L.bufsz = CT * (M.S + 4);
+  L.buf = o; o += 3 * L.bufsz;
   L.ks = o; o += n_stages * M.S * CT;
   L.arena = o; o += M.arena_floats * CT;
   L.bcf = o; o += M.nbc * CT;
   L.qs = o; o += CT;
+  L.model = o; o += (int)((sizeof(ModelD) + 15) / 16) * 4;
   L.total_floats = o + 4;  // + mbarrier (8 B) and padding
   return L;
 }
 
-// One RHS evaluation for the tile: MLP phases, face fluxes; leaves E in the arena. `in` is the stage input [S][CT].
+struct StageCoef { float c[CPZ_MAX_STAGES]; };
+
+// MLP part of one RHS evaluation (each phase ends with a block barrier); also refreshes the diurnal top flux.
 template <int CT, int NT, bool WS>
-__device__ __forceinline__ void rhs_eval(const ModelD& M, const float* __restrict__ in, float* __restrict__ arena,
-                                         const float* __restrict__ wsm, const float* __restrict__ theta,
-                                         float* __restrict__ bcf, const float* __restrict__ qs, float t) {
+__device__ __forceinline__ void rhs_mlp(const ModelD& M, const float* __restrict__ in, float* __restrict__ arena,
+                                        const float* __restrict__ wsm, const float* __restrict__ theta,
+                                        float* __restrict__ bcf, const float* __restrict__ qs, float t) {
   if (M.flags & F_DIURNAL) {
     if (threadIdx.x < CT) bcf[(M.nbc - 1) * CT + threadIdx.x] = diurnal_top_eff(M, qs[threadIdx.x], t);
   }
@@ -50,19 +62,42 @@ __device__ __forceinline__ void rhs_eval(const ModelD& M, const float* __restric
     run_phase<WS, CT, NT, false>(M, p, in, arena, nullptr, wsm, theta);
     __syncthreads();
   }
-  if (M.n_phase == 0) __syncthreads();
-  faces_phase<CT, NT>(M, in, arena, arena + M.flux_off * CT, bcf);
-  __syncthreads();
+  if (M.n_phase == 0 && (M.flags & F_DIURNAL)) __syncthreads();
 }
 
-template <int CT, int NT, bool WS>
-__global__ void __launch_bounds__(NT, 1) solve_kernel(const __grid_constant__ ModelD M, const __grid_constant__ TableauD tab,
-                                                      const TimeD tm, const SolveArgs a) {
-  extern __shared__ __align__(16) float smem[];
+// Tendencies of one RHS evaluation handed to sink(k0, c, dx[NF][4]) (fused stencil), or — for the smoothing variants —
+// computed through the two-phase faces/centres path with the flux scratch in the arena.
+template <int CT, int NT, int NF, class Sink>
+__device__ __forceinline__ void rhs_tendencies(const ModelD& M, const float* __restrict__ in, float* __restrict__ arena,
+                                               const float* __restrict__ bcf, Sink sink) {
+  const bool smoothing = M.variant == RHS_TRAIN && (M.flags & (F_SMOOTH_NN | F_SMOOTH_RI));
+  if (!smoothing) {
+    stencil_fused<CT, NT, NF>(M, in, arena, bcf, sink);
+    return;
+  }
+  float* E = arena + M.flux_off * CT;
+  faces_phase<CT, NT>(M, in, arena, E, bcf);
+  __syncthreads();
+  const int N = M.Nz;
+  for (int it = threadIdx.x; it < (N / 4) * CT; it += NT) {
+    const int kg = it / CT, c = it - kg * CT;
+    float dx[NF][4];
+#pragma unroll
+    for (int q = 0; q < NF; ++q)
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) dx[q][kk] = tendency(M, E, in, q, 4 * kg + kk, c, CT);
+    sink(4 * kg, c, dx);
+  }
+}
+
+template <int CT, int NT, bool WS, int NF>
+__device__ __forceinline__ void solve_body(const ModelD& M, const TableauD& tab, const TimeD& tm, const SolveArgs& a,
+                                           float* smem) {
   const SolveSmem L = solve_smem_layout(M, CT, tab.n_stages);
   float* wsm = smem + L.w;
-  float* xs = smem + L.xs;
-  float* xa = smem + L.xa;
+  float* xs = smem + L.buf;                 // step state
+  float* xa = smem + L.buf + L.bufsz;       // stage input (alternates with xb)
+  float* xb = smem + L.buf + 2 * L.bufsz;
   float* ks = smem + L.ks;
   float* arena = smem + L.arena;
   float* bcf = smem + L.bcf;
@@ -83,9 +118,12 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(const __grid_constant__ Mo
   if (threadIdx.x < CT) {
     const int col = min(col0 + (int)threadIdx.x, a.ncol - 1);
     float raw[6], eff[6];
-    for (int j = 0; j < M.nbc; ++j) raw[j] = __ldg(a.bcs + (size_t)col * M.nbc + j);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) raw[j] = j < M.nbc ? __ldg(a.bcs + (size_t)col * M.nbc + j) : 0.f;
     bc_effective(M, raw, eff);
-    for (int j = 0; j < M.nbc; ++j) bcf[j * CT + threadIdx.x] = eff[j];
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+      if (j < M.nbc) bcf[j * CT + threadIdx.x] = eff[j];
     qs[threadIdx.x] = (a.Q != nullptr) ? __ldg(a.Q + col) : 0.f;
   }
   __syncthreads();
@@ -95,12 +133,13 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(const __grid_constant__ Mo
   const int ns = tab.n_stages;
 
   if (a.rhs_only) {
-    rhs_eval<CT, NT, WS>(M, xs, arena, wsm, a.theta, bcf, qs, a.t_rhs);
-    const float* E = arena + M.flux_off * CT;
-    for (int i = threadIdx.x; i < N * CT; i += NT) {
-      const int k = i / CT, c = i - k * CT;
-      for (int q = 0; q < M.nf; ++q) ks[(q * N + k) * CT + c] = tendency(M, E, xs, q, k, c, CT);
-    }
+    rhs_mlp<CT, NT, WS>(M, xs, arena, wsm, a.theta, bcf, qs, a.t_rhs);
+    rhs_tendencies<CT, NT, NF>(M, xs, arena, bcf, [=](int k0, int c, const float (&dx)[NF][4]) {
+#pragma unroll
+      for (int q = 0; q < NF; ++q)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) ks[(q * N + k0 + kk) * CT + c] = dx[q][kk];
+    });
     __syncthreads();
     store_tile<CT, NT>(ks, xa, a.dxdt, (size_t)S, S, col0, a.ncol);
     if (threadIdx.x < CT) bulk_wait0();
@@ -123,43 +162,63 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(const __grid_constant__ Mo
   }
   __syncthreads();
 
+  const long long prof_all0 = (a.prof && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0;
   for (int n = 0; n < tm.n_steps; ++n) {
     for (int sub = 0; sub < tm.n_substeps; ++sub) {
       const float tb = tm.t0 + (float)n * tm.dt + (float)sub * h;
+      const float* in = xs;
       for (int i = 0; i < ns; ++i) {
-        const float* in = (i == 0) ? xs : xa;
-        rhs_eval<CT, NT, WS>(M, in, arena, wsm, a.theta, bcf, qs, tb + tab.c[i] * h);
-        const float* E = arena + M.flux_off * CT;
-        const bool last = (i + 1 == ns);
-        for (int it = threadIdx.x; it < N * CT; it += NT) {
-          const int k = it / CT, c = it - k * CT;
-          float dx[3];
-          for (int q = 0; q < M.nf; ++q) dx[q] = tendency(M, E, in, q, k, c, CT);
-          for (int q = 0; q < M.nf; ++q) {
-            const int e = (q * N + k) * CT + c;
-            ks[i * SC + e] = dx[q];
-            if (!last) {
-              float acc = tab.a[i + 1][i] * dx[q];
-              for (int j = 0; j < i; ++j) acc = fmaf(tab.a[i + 1][j], ks[j * SC + e], acc);
-              xa[e] = fmaf(h, acc, xs[e]);
-            } else {
-              float acc = tab.b[i] * dx[q];
-              for (int j = 0; j < i; ++j) acc = fmaf(tab.b[j], ks[j * SC + e], acc);
-              xs[e] = fmaf(h, acc, xs[e]);
-            }
+        if (a.prof) {
+          for (int p = 0; p < M.n_phase; ++p) {
+            CPZ_PROF_BEGIN();
+            run_phase<WS, CT, NT, false>(M, p, in, arena, nullptr, wsm, a.theta);
+            __syncthreads();
+            CPZ_PROF_END(p < 3 ? p : 3);
           }
+        } else {
+          rhs_mlp<CT, NT, WS>(M, in, arena, wsm, a.theta, bcf, qs, tb + tab.c[i] * h);
         }
+        const bool last = (i + 1 == ns);
+        CPZ_PROF_BEGIN();
+        // the stencil of other threads still reads `in`, so the next stage input / new state goes to a different buffer
+        float* out = last ? ((in == xs) ? xa : xs) : ((in == xa) ? xb : xa);
+        StageCoef sc;
+#pragma unroll
+        for (int j = 0; j < CPZ_MAX_STAGES; ++j) sc.c[j] = last ? tab.b[j] : tab.a[(i + 1) % CPZ_MAX_STAGES][j];
+        const float coef_i = last ? tab.b[i] : tab.a[(i + 1) % CPZ_MAX_STAGES][i];
+        const float* xs_c = xs;
+        rhs_tendencies<CT, NT, NF>(M, in, arena, bcf, [=](int k0, int c, const float (&dx)[NF][4]) {
+#pragma unroll
+          for (int q = 0; q < NF; ++q)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const int e = (q * N + k0 + kk) * CT + c;
+              float acc = coef_i * dx[q][kk];
+#pragma unroll
+              for (int j = 0; j < CPZ_MAX_STAGES - 1; ++j)
+                if (j < i) acc = fmaf(sc.c[j], ks[j * SC + e], acc);
+              if (!last) ks[i * SC + e] = dx[q][kk];
+              out[e] = fmaf(h, acc, xs_c[e]);
+            }
+        });
         __syncthreads();
+        CPZ_PROF_END(4);
+        if (last && out != xs) {  // single-stage integrator: the new state was written next to the old one
+          float* t = xs; xs = out; xa = t;
+        }
+        in = out;
       }
     }
     const int step = n + 1;
     const bool do_save = a.traj != nullptr && ((tm.save_stride > 0 && step % tm.save_stride == 0) ||
                                                 (tm.save_stride <= 0 && step == tm.n_steps));
     if (do_save) {
+      CPZ_PROF_BEGIN();
       float* dst = a.traj + (size_t)frame * S;
-      store_tile<CT, NT>(xs, xa, dst, traj_stride, S, col0, a.ncol);
-      if (threadIdx.x < CT) bulk_wait_read0();  // xa is rewritten by the next stage
+      store_tile<CT, NT>(xs, xb, dst, traj_stride, S, col0, a.ncol);
+      if (threadIdx.x < CT) bulk_wait_read0();  // xb is rewritten by a later stage
       ++frame;
+      CPZ_PROF_END(5);
     }
     if (a.ckpt != nullptr && (step % tm.ckpt_stride == 0 || step == tm.n_steps)) {
       float4* dst = reinterpret_cast<float4*>(a.ckpt + ((size_t)tile * a.n_ckpt + ci) * SC);
@@ -167,7 +226,29 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(const __grid_constant__ Mo
       ++ci;
     }
   }
+  if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[7] += (unsigned long long)(clock64() - prof_all0);
   if (threadIdx.x < CT) bulk_wait0();
+}
+
+// The model description is copied from the kernel parameters into shared memory once: the (non-inlined) phase functions
+// take it by reference, and a reference into parameter space would turn every field access into a generic global load.
+template <int NT>
+__device__ __forceinline__ const ModelD& model_to_smem(const ModelD& Mp, float* dst) {
+  const int* src = reinterpret_cast<const int*>(&Mp);
+  int* d = reinterpret_cast<int*>(dst);
+  for (int i = threadIdx.x; i < (int)(sizeof(ModelD) / 4); i += NT) d[i] = src[i];
+  __syncthreads();
+  return *reinterpret_cast<const ModelD*>(dst);
+}
+
+template <int CT, int NT, bool WS>
+__global__ void __launch_bounds__(NT, 1) solve_kernel(const __grid_constant__ ModelD Mp, const __grid_constant__ TableauD tab,
+                                                      const TimeD tm, const SolveArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const SolveSmem L = solve_smem_layout(Mp, CT, tab.n_stages);
+  const ModelD& M = model_to_smem<NT>(Mp, smem + L.model);
+  if (Mp.nf == 3) solve_body<CT, NT, WS, 3>(M, tab, tm, a, smem);
+  else solve_body<CT, NT, WS, 1>(M, tab, tm, a, smem);
 }
 
 }  // namespace cpz
