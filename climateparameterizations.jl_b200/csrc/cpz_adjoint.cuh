@@ -382,7 +382,8 @@ __device__ __noinline__ void stage_input(const TableauD& tab, int i, float h, co
 }
 
 template <int CT, int NT, bool WS, int NF>
-__device__ __forceinline__ void adjoint_body(const ModelD& M, const TableauD& tab, const TimeD& tm, const AdjArgs& a, float* smem) {
+__device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, const TableauD& tab, const TimeD& tm,
+                                             const AdjArgs& a, float* smem) {
   const AdjSmem L = adjoint_smem_layout(M, CT);
   float* wsm = smem + L.w;
   float* xs = smem + L.xs;
@@ -404,6 +405,8 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const TableauD& ta
   uint32_t parity = 0;
   float lsum[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int Lmax = M.n_gemm > 0 ? last_layer_of<CT, NT>(M) : -1;
+  PhaseCache pc;
+  build_phase_cache<WS, CT, NT>(M, pc);
 
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
@@ -462,9 +465,9 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const TableauD& ta
         for (int i = 0; i < ns; ++i) {
           const float* in = xs;
           if (i > 0) { stage_input<CT, NT>(tab, i, h, xs, slots, SC, xin); __syncthreads(); in = xin; }
-          rhs_mlp<CT, NT, WS>(M, in, arena, wsm, a.theta, bcf, qs, tb + tab.c[i] * h);
+          rhs_mlp<CT, NT, WS>(M, pc, in, arena, wsm, a.theta, bcf, qs, tb + tab.c[i] * h);
           float* slot_i = slots + (size_t)i * SC;
-          rhs_tendencies<CT, NT, NF>(M, in, arena, bcf, [=](int k0, int c, const float (&dx)[NF][4]) {
+          rhs_tendencies<CT, NT, NF>(Mp, in, arena, bcf, [=](int k0, int c, const float (&dx)[NF][4]) {
 #pragma unroll
             for (int q = 0; q < NF; ++q)
 #pragma unroll
@@ -495,9 +498,9 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const TableauD& ta
         for (int i = 0; i + 1 < ns; ++i) {
           const float* in = xs;
           if (i > 0) { stage_input<CT, NT>(tab, i, h, xs, slots, SC, xin); __syncthreads(); in = xin; }
-          rhs_mlp<CT, NT, WS>(M, in, arena, wsm, a.theta, bcf, qs, tb + tab.c[i] * h);
+          rhs_mlp<CT, NT, WS>(M, pc, in, arena, wsm, a.theta, bcf, qs, tb + tab.c[i] * h);
           float* slot_i = slots + (size_t)i * SC;
-          rhs_tendencies<CT, NT, NF>(M, in, arena, bcf, [=](int k0, int c, const float (&dx)[NF][4]) {
+          rhs_tendencies<CT, NT, NF>(Mp, in, arena, bcf, [=](int k0, int c, const float (&dx)[NF][4]) {
 #pragma unroll
             for (int q = 0; q < NF; ++q)
 #pragma unroll
@@ -530,7 +533,7 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const TableauD& ta
           // MLP forward keeping z and a (the last layer's outputs are not needed: F is linear in them)
           for (int p = 0; p < M.n_phase; ++p) {
             if (M.gemm[M.phase[p].g0].layer == Lmax && M.gemm[M.phase[p].g1 - 1].layer == Lmax) continue;
-            run_phase<WS, CT, NT, true>(M, p, in, arena, zarena, wsm, a.theta);
+            run_phase_cached<CT, NT, WS, true>(M, p, pc, in, arena, zarena, wsm, a.theta);
             __syncthreads();
           }
           faces_vjp<CT, NT>(M, in, xb, zarena, gflux);
@@ -587,98 +590,10 @@ __global__ void __launch_bounds__(NT, 1) adjoint_kernel(const __grid_constant__ 
   extern __shared__ __align__(16) float smem[];
   const AdjSmem L = adjoint_smem_layout(Mp, CT);
   const ModelD& M = model_to_smem<NT>(Mp, smem + L.model);
-  if (Mp.nf == 3) adjoint_body<CT, NT, WS, 3>(M, tab, tm, a, smem);
-  else adjoint_body<CT, NT, WS, 1>(M, tab, tm, a, smem);
+  if (Mp.nf == 3) adjoint_body<CT, NT, WS, 3>(M, Mp, tab, tm, a, smem);
+  else adjoint_body<CT, NT, WS, 1>(M, Mp, tab, tm, a, smem);
 }
 
-// ---- small reductions -----------------------------------------------------------------------------------------------
-// out[p] = sum over slabs of part[slab][p]   (fixed order: deterministic)
-__global__ void reduce_slabs_kernel(const float* __restrict__ part, int n_slabs, int P, float* __restrict__ out) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  float s = 0.f;
-  for (int t = 0; t < n_slabs; ++t) s += part[(size_t)t * P + p];
-  out[p] = s;
-}
-
-// pack[0..P) = grad (unnormalised here: normalisation is folded into the loss cotangent), pack[P..P+6) = raw squared-error
-// sums, pack[P+6] = column count, pack[P+7] = 0.
-__global__ void pack_loss_kernel(const float* __restrict__ lpart, int n_slabs, float ncol, float* __restrict__ pack_tail) {
-  const int q = threadIdx.x;
-  if (q < 6) {
-    float s = 0.f;
-    for (int t = 0; t < n_slabs; ++t) s += lpart[(size_t)t * 8 + q];
-    pack_tail[q] = s;
-  } else if (q == 6) {
-    pack_tail[6] = ncol;
-  } else if (q == 7) {
-    pack_tail[7] = 0.f;
-  }
-}
-
-// loss_out[0..6) = w_q * sum_q * inv_norm_q ; loss_out[6] = total
 struct W6 { float w[6]; };
-__global__ void finalize_loss_kernel(const float* __restrict__ pack_tail, const W6 w6, float inv_prof,
-                                     float inv_grad, float* __restrict__ loss_out) {
-  if (threadIdx.x == 0) {
-    float tot = 0.f;
-    const float inv_ncol = 1.f / pack_tail[6];
-    for (int q = 0; q < 6; ++q) {
-      const float v = w6.w[q] * pack_tail[q] * (q < 3 ? inv_prof : inv_grad) * inv_ncol;
-      loss_out[q] = v;
-      tot += v;
-    }
-    loss_out[6] = tot;
-  }
-}
-
-// Loss-only path: six squared-error sums of a device trajectory against targets ([ncol][n_saved][S] both).
-// One block per column; partial sums to lpart[col][8].
-__global__ void loss_traj_kernel(const float* __restrict__ traj, const float* __restrict__ tgt, int n_saved, int S, int Nz,
-                                 int nf, float Nf, float* __restrict__ lpart) {
-  __shared__ float red[6][8];
-  const size_t base = (size_t)blockIdx.x * n_saved * S;
-  float ls[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int i = threadIdx.x; i < n_saved * S; i += blockDim.x) {
-    const int s = i % S, q = s / Nz, k = s - q * Nz;
-    const int wq = nf == 1 ? 2 : q;
-    const float d = traj[base + i] - tgt[base + i];
-    ls[wq] = fmaf(d, d, ls[wq]);
-    if (nf == 3 && k >= 1) {
-      const float g = Nf * (d - (traj[base + i - 1] - tgt[base + i - 1]));
-      ls[3 + q] = fmaf(g, g, ls[3 + q]);
-    }
-  }
-  for (int q = 0; q < 6; ++q) {
-    float v = ls[q];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < 6) {
-    float t = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[threadIdx.x][w];
-    lpart[(size_t)blockIdx.x * 8 + threadIdx.x] = t;
-  }
-}
-
-// grad[p] *= scale
-__global__ void scale_kernel(float* __restrict__ g, int P, const float* __restrict__ pack_tail) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < P) g[p] *= 1.f / pack_tail[6];
-}
-
-// Flux 0.11 ADAM: m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; theta -= lr * m/(1-bp1) / (sqrt(v/(1-bp2)) + eps)
-__global__ void adam_kernel(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
-                            int P, float lr, float b1, float b2, float eps, float bp1, float bp2) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  const float gp = g[p];
-  const float mp = b1 * m[p] + (1.f - b1) * gp;
-  const float vp = b2 * v[p] + (1.f - b2) * gp * gp;
-  m[p] = mp;
-  v[p] = vp;
-  theta[p] -= mp / (1.f - bp1) / (sqrtf(vp / (1.f - bp2)) + eps) * lr;
-}
 
 }  // namespace cpz

@@ -8,10 +8,7 @@
 #include <new>
 #include <vector>
 
-#include "cpz_adjoint.cuh"
-#include "cpz_closure.cuh"
-#include "cpz_internal.h"
-#include "cpz_solve.cuh"
+#include "cpz_launch.h"
 
 namespace cpz {
 
@@ -54,44 +51,6 @@ static int n_ckpt_of(const TimeD& tm) {
   int n = tm.n_steps / tm.ckpt_stride + 1;
   if (tm.n_steps % tm.ckpt_stride != 0) ++n;
   return n;
-}
-
-// ---- forward launch ---------------------------------------------------------------------------------------------
-template <int CT, int NT, bool WS>
-static int launch_solve_t(cpz_model* m, const SolveArgs& a) {
-  const SolveSmem L = solve_smem_layout(m->fwd.M, CT, m->tab.n_stages);
-  const size_t smem = (size_t)L.total_floats * sizeof(float);
-  if (smem > m->ctx->smem_optin) return fail(CPZ_ERR_INVALID, "forward kernel needs %zu B shared memory, device allows %zu", smem, m->ctx->smem_optin);
-  auto kern = solve_kernel<CT, NT, WS>;
-  CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int n_tiles = (a.ncol + CT - 1) / CT;
-  static const bool prof = getenv("CPZ_PROF") != nullptr;
-  if (prof && !a.rhs_only) {  // debug: per-phase cycle counters of CTA 0
-    SolveArgs ap = a;
-    unsigned long long* d = nullptr;
-    CPZ_CUDA(cudaMalloc(&d, 8 * sizeof(unsigned long long)));
-    CPZ_CUDA(cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), m->ctx->stream));
-    ap.prof = d;
-    kern<<<n_tiles, NT, smem, m->ctx->stream>>>(m->fwd.M, m->tab, m->tm, ap);
-    unsigned long long hcnt[8];
-    CPZ_CUDA(cudaMemcpyAsync(hcnt, d, sizeof(hcnt), cudaMemcpyDeviceToHost, m->ctx->stream));
-    CPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));
-    cudaFree(d);
-    const double n_rhs = (double)m->tm.n_steps * m->tm.n_substeps * m->tab.n_stages;
-    fprintf(stderr, "[cpz prof] cycles per RHS: phase0 %.0f phase1 %.0f phase2 %.0f phase3+ %.0f stencil+update %.0f | per step: save %.0f | total/RHS %.0f\n",
-            hcnt[0] / n_rhs, hcnt[1] / n_rhs, hcnt[2] / n_rhs, hcnt[3] / n_rhs, hcnt[4] / n_rhs, hcnt[5] / (double)m->tm.n_steps, hcnt[7] / n_rhs);
-    m->ctx->launches++;
-    return CPZ_OK;
-  }
-  kern<<<n_tiles, NT, smem, m->ctx->stream>>>(m->fwd.M, m->tab, m->tm, a);
-  CPZ_CUDA(cudaGetLastError());
-  m->ctx->launches++;
-  return CPZ_OK;
-}
-
-static int launch_solve(cpz_model* m, const SolveArgs& a) {
-  if (m->fwd.M.w_in_smem) return launch_solve_t<32, 256, true>(m, a);
-  return launch_solve_t<32, 256, false>(m, a);
 }
 
 static int check_model(const cpz_model* m) {
@@ -273,7 +232,7 @@ int cpz_model_describe(const cpz_model* m, char* buf, size_t buf_len) {
              M.arena_floats, M.flux_off);
     s += line;
     for (int p = 0; p < M.n_phase; ++p) {
-      snprintf(line, sizeof(line), "  phase %d: tiles=%d TO=%d ksplit=%d:", p, M.phase[p].n_tiles, M.phase[p].TO, M.phase[p].ksplit);
+      snprintf(line, sizeof(line), "  phase %d: tiles=%d tile=%dcols x %douts ksplit=%d:", p, M.phase[p].n_tiles, M.phase[p].TC, M.phase[p].TO, M.phase[p].ksplit);
       s += line;
       for (int g = M.phase[p].g0; g < M.phase[p].g1; ++g) {
         const GemmD& G = M.gemm[g];

@@ -58,6 +58,8 @@ __global__ void __launch_bounds__(NT, 1) closure_kernel(const __grid_constant__ 
   const int N = M.Nz;
   if (WS) load_weights_smem<NT>(M, wsm, a.theta);
   __syncthreads();
+  PhaseCache pc;
+  build_phase_cache<WS, CT, NT>(M, pc);
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int col0 = tile * CT;
     // coalesced load: row k of the tile = CT consecutive floats of level k
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(NT, 1) closure_kernel(const __grid_constant__ 
     }
     __syncthreads();
     for (int p = 0; p < M.n_phase; ++p) {
-      run_phase<WS, CT, NT, false>(M, p, xin, arena, nullptr, wsm, a.theta);
+      run_phase_cached<CT, NT, WS, false>(M, p, pc, xin, arena, nullptr, wsm, a.theta);
       __syncthreads();
     }
     // wT = [0; inv(wT_scaling)(NN); surface_flux]; forcing = d(wT)/dz at centres (double_gyre_nn.jl:159-166,140-147)

@@ -107,235 +107,9 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-__device__ __forceinline__ float4 act_fwd4(int act, float4 z) {
-  float4 r;
-  switch (act) {
-    case ACT_RELU: r = make_float4(fmaxf(z.x, 0.f), fmaxf(z.y, 0.f), fmaxf(z.z, 0.f), fmaxf(z.w, 0.f)); break;
-    case ACT_MISH: r = make_float4(act_fwd(ACT_MISH, z.x), act_fwd(ACT_MISH, z.y), act_fwd(ACT_MISH, z.z), act_fwd(ACT_MISH, z.w)); break;
-    case ACT_SWISH: r = make_float4(act_fwd(ACT_SWISH, z.x), act_fwd(ACT_SWISH, z.y), act_fwd(ACT_SWISH, z.z), act_fwd(ACT_SWISH, z.w)); break;
-    case ACT_LEAKY: r = make_float4(act_fwd(ACT_LEAKY, z.x), act_fwd(ACT_LEAKY, z.y), act_fwd(ACT_LEAKY, z.z), act_fwd(ACT_LEAKY, z.w)); break;
-    case ACT_TANH: r = make_float4(act_fwd(ACT_TANH, z.x), act_fwd(ACT_TANH, z.y), act_fwd(ACT_TANH, z.z), act_fwd(ACT_TANH, z.w)); break;
-    default: r = z; break;
-  }
-  return r;
-}
-
-// ---- dense layer: one 4-column x TO-output register tile (TO even) ---------------------------------------------
-// in:  [K][CT] shared, out: [N][CT] shared (post-activation), zout (optional): [N][CT] pre-activation.
-// WS: weights come from the shared arena (row stride Npad, zero padded) else straight from theta in global.
-// The accumulators are output PAIRS (float2) per column so the inner loop is FFMA2 (packed FP32, sm_100):
-//   acc[p][c] += (w[2p], w[2p+1]) * x[c]     -> FFMA2 R, R.F32x2, R.F32 (scalar broadcast), R.F32x2
-// per k: 1 LDS.128 (4 columns of the input row) + TO/2 LDS.64 (or TO/4 LDS.128) of the weight row, 2*TO FFMA2.
-template <int TO, bool WS, int CT>
-__device__ __forceinline__ void gemm_tile_accum(const GemmD& g, const float* __restrict__ in, const float* __restrict__ W,
-                                                int cg, int og, int k0, int k1, float2 (&acc)[TO / 2][4]) {
-  constexpr int TP = TO / 2;
-  const int j0 = og * TO;
-  const int N = g.N;
-  if constexpr (WS) {
-    const int ldw = g.Npad;
-    const float* xp = in + 4 * cg + k0 * CT;
-    const float* wp = W + j0 + k0 * ldw;
-    // software pipeline: the operands of iteration k+1 are loaded before the FFMA2s of iteration k issue
-    auto load_w = [&](const float* wq, float2 (&w)[TP]) {
-      if constexpr (TO % 4 == 0) {
-#pragma unroll
-        for (int p = 0; p < TP; p += 2) {
-          const float4 wv = *reinterpret_cast<const float4*>(wq + 2 * p);
-          w[p] = make_float2(wv.x, wv.y);
-          w[p + 1] = make_float2(wv.z, wv.w);
-        }
-      } else {
-#pragma unroll
-        for (int p = 0; p < TP; ++p) w[p] = *reinterpret_cast<const float2*>(wq + 2 * p);
-      }
-    };
-    if (k0 >= k1) return;
-    float4 xv = *reinterpret_cast<const float4*>(xp);
-    float2 w[TP];
-    load_w(wp, w);
-#pragma unroll 2
-    for (int k = k0; k < k1; ++k) {
-      float4 xn = xv;
-      float2 wn[TP];
-#pragma unroll
-      for (int p = 0; p < TP; ++p) wn[p] = w[p];
-      if (k + 1 < k1) {
-        xn = *reinterpret_cast<const float4*>(xp + CT);
-        load_w(wp + ldw, wn);
-      }
-      const float2 x0 = make_float2(xv.x, xv.x), x1 = make_float2(xv.y, xv.y), x2 = make_float2(xv.z, xv.z),
-                   x3 = make_float2(xv.w, xv.w);
-#pragma unroll
-      for (int p = 0; p < TP; ++p) {
-        acc[p][0] = __ffma2_rn(w[p], x0, acc[p][0]);
-        acc[p][1] = __ffma2_rn(w[p], x1, acc[p][1]);
-        acc[p][2] = __ffma2_rn(w[p], x2, acc[p][2]);
-        acc[p][3] = __ffma2_rn(w[p], x3, acc[p][3]);
-      }
-      xv = xn;
-#pragma unroll
-      for (int p = 0; p < TP; ++p) w[p] = wn[p];
-      xp += CT;
-      wp += ldw;
-    }
-  } else {
-    int jo[TO];
-#pragma unroll
-    for (int o = 0; o < TO; ++o) jo[o] = min(j0 + o, N - 1);
-    const float* xp = in + 4 * cg + k0 * CT;
-    const float* wp = W + (size_t)k0 * N;
-#pragma unroll 2
-    for (int k = k0; k < k1; ++k) {
-      const float4 xv = *reinterpret_cast<const float4*>(xp);
-      float2 w[TP];
-#pragma unroll
-      for (int p = 0; p < TP; ++p) w[p] = make_float2(__ldg(wp + jo[2 * p]), __ldg(wp + jo[2 * p + 1]));
-      const float2 x0 = make_float2(xv.x, xv.x), x1 = make_float2(xv.y, xv.y), x2 = make_float2(xv.z, xv.z),
-                   x3 = make_float2(xv.w, xv.w);
-#pragma unroll
-      for (int p = 0; p < TP; ++p) {
-        acc[p][0] = __ffma2_rn(w[p], x0, acc[p][0]);
-        acc[p][1] = __ffma2_rn(w[p], x1, acc[p][1]);
-        acc[p][2] = __ffma2_rn(w[p], x2, acc[p][2]);
-        acc[p][3] = __ffma2_rn(w[p], x3, acc[p][3]);
-      }
-      xp += CT;
-      wp += N;
-    }
-  }
-}
-
-template <int TO, bool WS>
-__device__ __forceinline__ void gemm_tile_init(const GemmD& g, const float* __restrict__ bias, int og, bool with_bias,
-                                               float2 (&acc)[TO / 2][4]) {
-  const int j0 = og * TO;
-#pragma unroll
-  for (int p = 0; p < TO / 2; ++p) {
-    float2 bv = make_float2(0.f, 0.f);
-    if (with_bias) {
-      if constexpr (WS) bv = *reinterpret_cast<const float2*>(bias + j0 + 2 * p);
-      else bv = make_float2(__ldg(bias + min(j0 + 2 * p, g.N - 1)), __ldg(bias + min(j0 + 2 * p + 1, g.N - 1)));
-    }
-    acc[p][0] = bv; acc[p][1] = bv; acc[p][2] = bv; acc[p][3] = bv;
-  }
-}
-
-// finish output pair p of a tile: z = acc (+ partial already stored in out, when ADD_OUT), a = act(z)
-template <int CT, bool SAVE_Z, bool ADD_OUT>
-__device__ __forceinline__ void gemm_pair_finish(const GemmD& g, float* __restrict__ out, float* __restrict__ zout, int j,
-                                                 int cg, const float2 (&a4)[4]) {
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int jj = j + h;
-    if (jj < g.N) {
-      float4 z;
-      z.x = h ? a4[0].y : a4[0].x;
-      z.y = h ? a4[1].y : a4[1].x;
-      z.z = h ? a4[2].y : a4[2].x;
-      z.w = h ? a4[3].y : a4[3].x;
-      float4* po = reinterpret_cast<float4*>(out + jj * CT + 4 * cg);
-      if constexpr (ADD_OUT) {
-        const float4 q = *po;
-        z.x += q.x; z.y += q.y; z.z += q.z; z.w += q.w;
-      }
-      if constexpr (SAVE_Z) *reinterpret_cast<float4*>(zout + jj * CT + 4 * cg) = z;
-      *po = act_fwd4(g.act, z);
-    }
-  }
-}
-
-// raw partial sums of output pair p into the out rows (no activation)
-template <int CT>
-__device__ __forceinline__ void gemm_pair_stash(const GemmD& g, float* __restrict__ out, int j, int cg, const float2 (&a4)[4]) {
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int jj = j + h;
-    if (jj < g.N)
-      *reinterpret_cast<float4*>(out + jj * CT + 4 * cg) =
-          make_float4(h ? a4[0].y : a4[0].x, h ? a4[1].y : a4[1].x, h ? a4[2].y : a4[2].x, h ? a4[3].y : a4[3].x);
-  }
-}
-
-// One phase with uniform tile shape TO. KS = 1: each thread owns whole tiles (strided over the flattened tile space).
-// KS = 2 (n_tiles <= NT/2): threads [0,NT/2) and [NT/2,NT) each take half of the k range of the same tile so that every
-// SM sub-partition has two warps to interleave (LDS issue stalls of one hide under the FFMA2 stream of the other);
-// the halves exchange partial sums through the output rows and each finishes half of the tile's outputs.
-template <int TO, bool WS, int CT, int NT, bool SAVE_Z>
-__device__ __noinline__ void run_phase_t(const ModelD& M, int p, const float* __restrict__ X, float* __restrict__ arena,
-                                            float* __restrict__ zarena, const float* __restrict__ wsm,
-                                            const float* __restrict__ theta) {
-  constexpr int NCG = CT / 4;
-  constexpr int TP = TO / 2;
-  const int g0 = M.phase[p].g0, g1 = M.phase[p].g1, n_tiles = M.phase[p].n_tiles;
-  if (M.phase[p].ksplit == 2) {
-    const int half = threadIdx.x / (NT / 2), tile = threadIdx.x - half * (NT / 2);
-    const bool active = tile < n_tiles;
-    int gi = g0;
-    if (active)
-      while (gi + 1 < g1 && tile >= M.gemm[gi + 1].tile_begin) ++gi;
-    const GemmD& g = M.gemm[gi];
-    const int local = active ? tile - g.tile_begin : 0;
-    const int cg = local % NCG, og = local / NCG;
-    const float* in = g.in_off < 0 ? X : arena + g.in_off * CT;
-    float* out = arena + g.out_off * CT;
-    float* zo = SAVE_Z ? zarena + g.out_off * CT : nullptr;
-    const float* W = WS ? wsm + g.sw_off : theta + g.w_off;
-    const float* B = WS ? wsm + g.sb_off : theta + g.b_off;
-    float2 acc[TP][4];
-    constexpr int P0 = (TP + 1) / 2;  // pairs finished by half 0; half 1 finishes the remaining TP-P0
-    if (active) {
-      const int kmid = g.K / 2;
-      gemm_tile_init<TO, WS>(g, B, og, half == 0, acc);
-      gemm_tile_accum<TO, WS, CT>(g, in, W, cg, og, half == 0 ? 0 : kmid, half == 0 ? kmid : g.K, acc);
-      // stash the partials of the pairs the OTHER half finishes
-#pragma unroll
-      for (int q = 0; q < TP; ++q)
-        if ((q < P0) == (half == 1)) gemm_pair_stash<CT>(g, out, og * TO + 2 * q, cg, acc[q]);
-    }
-    __syncthreads();
-    if (active) {
-#pragma unroll
-      for (int q = 0; q < TP; ++q)
-        if ((q < P0) == (half == 0)) gemm_pair_finish<CT, SAVE_Z, true>(g, out, zo, og * TO + 2 * q, cg, acc[q]);
-    }
-    return;
-  }
-  for (int tile = threadIdx.x; tile < n_tiles; tile += NT) {
-    int gi = g0;
-    while (gi + 1 < g1 && tile >= M.gemm[gi + 1].tile_begin) ++gi;
-    const GemmD& g = M.gemm[gi];
-    const int local = tile - g.tile_begin;
-    const int cg = local % NCG, og = local / NCG;
-    const float* in = g.in_off < 0 ? X : arena + g.in_off * CT;
-    float* out = arena + g.out_off * CT;
-    float* zo = SAVE_Z ? zarena + g.out_off * CT : nullptr;
-    const float* W = WS ? wsm + g.sw_off : theta + g.w_off;
-    const float* B = WS ? wsm + g.sb_off : theta + g.b_off;
-    float2 acc[TP][4];
-    gemm_tile_init<TO, WS>(g, B, og, true, acc);
-    gemm_tile_accum<TO, WS, CT>(g, in, W, cg, og, 0, g.K, acc);
-#pragma unroll
-    for (int q = 0; q < TP; ++q) gemm_pair_finish<CT, SAVE_Z, false>(g, out, zo, og * TO + 2 * q, cg, acc[q]);
-  }
-}
-
-// One phase = the gemms [g0,g1) of the plan, run over a flattened (gemm, output group, column group) tile space.
-// X: state tile [S][CT]; arena: activations [rows][CT]; zarena: pre-activations (same row offsets) when SAVE_Z.
-// All gemms of a phase share one tile shape (planner), so the dispatch is block-uniform.
-template <bool WS, int CT, int NT, bool SAVE_Z>
-__device__ __forceinline__ void run_phase(const ModelD& M, int p, const float* __restrict__ X, float* __restrict__ arena,
-                                          float* __restrict__ zarena, const float* __restrict__ wsm,
-                                          const float* __restrict__ theta) {
-  switch (M.phase[p].TO) {
-    case 2: run_phase_t<2, WS, CT, NT, SAVE_Z>(M, p, X, arena, zarena, wsm, theta); break;
-    case 4: run_phase_t<4, WS, CT, NT, SAVE_Z>(M, p, X, arena, zarena, wsm, theta); break;
-    case 6: run_phase_t<6, WS, CT, NT, SAVE_Z>(M, p, X, arena, zarena, wsm, theta); break;
-    case 8: run_phase_t<8, WS, CT, NT, SAVE_Z>(M, p, X, arena, zarena, wsm, theta); break;
-    case 10: run_phase_t<10, WS, CT, NT, SAVE_Z>(M, p, X, arena, zarena, wsm, theta); break;
-    default: run_phase_t<12, WS, CT, NT, SAVE_Z>(M, p, X, arena, zarena, wsm, theta); break;
-  }
-}
+}  // namespace cpz
+#include "cpz_gemm.cuh"
+namespace cpz {
 
 // Copy theta into the shared weight arena in the plan's padded layout (rows of Npad floats, zero padded).
 template <int NT>
@@ -514,7 +288,7 @@ __device__ __forceinline__ float tendency(const ModelD& M, const float* __restri
 // "faces" and "centres"; a warp is 32 consecutive columns of one level group (conflict-free LDS).
 // Not used for the smooth_NN / smooth_Ri variants (they need neighbouring faces' values; see faces_phase).
 template <int CT, int NT, int NF, class Sink>
-__device__ __noinline__ void stencil_fused(const ModelD& M, const float* __restrict__ X, const float* __restrict__ arena,
+__device__ __forceinline__ void stencil_fused(const ModelD& M, const float* __restrict__ X, const float* __restrict__ arena,
                                            const float* __restrict__ bcf, Sink sink) {
   const int N = M.Nz;
   const bool has_nn = M.n_nets > 0;

@@ -1,0 +1,18 @@
+// Launchers implemented in the per-kernel translation units (compiled in parallel).
+#pragma once
+#include "cpz_internal.h"
+#include "cpz_solve.cuh"
+#include "cpz_adjoint.cuh"
+#include "cpz_closure.cuh"
+
+namespace cpz {
+int launch_solve(cpz_model* m, const SolveArgs& a);
+int launch_adjoint(cpz_model* m, const AdjArgs& a, int grid);
+int launch_closure(cpz_model* m, const ClosureD& cd, const ClosureArgs& a);
+int launch_reduce_slabs(cpz_model* m, const float* part, int n_slabs, int P, float* out);
+int launch_pack_loss(cpz_model* m, const float* lpart, int n_slabs, float ncol, float* pack_tail);
+int launch_finalize_loss(cpz_model* m, const float* pack_tail, const float* w6, float inv_prof, float inv_grad, float* loss_out);
+int launch_loss_traj(cpz_model* m, const float* traj, const float* tgt, int ncol, int n_saved, int S, int Nz, int nf, float* lpart);
+int launch_scale(cpz_model* m, float* g, int P, const float* pack_tail);
+int launch_adam(cpz_model* m, const float* g, float lr, float b1, float b2, float eps);
+}  // namespace cpz

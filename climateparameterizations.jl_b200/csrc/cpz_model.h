@@ -26,8 +26,8 @@ struct GemmD {
 struct PhaseD {
   int g0, g1;
   int n_tiles;
-  int TO;      // outputs per thread tile, uniform over the phase's gemms
-  int ksplit;  // 1, or 2: two half-k partial tiles per output tile (needs n_tiles <= NT/2)
+  int TC, TO;  // thread tile: TC columns x TO outputs, uniform over the phase's gemms
+  int ksplit;  // KQ: lanes of one warp that split the k range of a tile (1, 2 or 4)
 };
 
 // Pre-folded RHS constants (computed in double on the host, rounded once to float).

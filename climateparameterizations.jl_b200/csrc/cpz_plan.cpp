@@ -3,6 +3,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -38,7 +40,7 @@ bool validate_desc(const cpz_model_desc& d, std::string& err) {
     if (nd.sizes[0] != S) { err = "net input size must be n_fields*Nz"; return false; }
     if (nd.sizes[nd.n_layers] != d.Nz - 1) { err = "net output size must be Nz-1 (interior faces)"; return false; }
     for (int l = 0; l <= nd.n_layers; ++l)
-      if (nd.sizes[l] < 1 || nd.sizes[l] > 4096) { err = "layer width out of range [1,4096]"; return false; }
+      if (nd.sizes[l] < 1 || nd.sizes[l] > 2048) { err = "layer width out of range [1,2048]"; return false; }
     for (int l = 0; l < nd.n_layers; ++l)
       if (nd.act[l] < 0 || nd.act[l] > CPZ_ACT_TANH) { err = "unknown activation"; return false; }
   }
@@ -100,46 +102,45 @@ double act_cost(int act) {
 
 struct KN { int K, N, act; };
 
-// Estimated cycles of one phase on the busiest SM sub-partition for a uniform tile shape (TO, ksplit).
-// Measured on B200 (profiles/r01_forward_*.txt): an FFMA2 occupies the FMA pipe for 2 cycles, a shared load costs
-// ~3.7 issue cycles of its warp; with a single warp on a sub-partition the two do not overlap, with two or more
-// they do.
-double phase_cost(const std::vector<KN>& kn, int TO, int ksplit, int NCG, int NT, bool ws) {
+struct Shape { int TC, TO, KQ; };
+// keep in sync with the CPZ_SHAPE list in cpz_gemm.cuh
+const Shape kShapes[] = {{8, 10, 4}, {8, 10, 2}, {8, 10, 1}, {8, 8, 4}, {8, 8, 2}, {8, 8, 1}, {8, 4, 4}, {8, 4, 2},
+                         {4, 4, 4},  {4, 4, 2},  {4, 4, 1},  {4, 2, 2}};
+
+// Estimated cycles of one phase for a tile shape. Constants measured on B200 (tools/micro/ffma2_bench.cu): a scalar FFMA
+// issues every ~1.1 cycles per SM sub-partition; a thread tile costs (TC+TO) shared-memory wavefronts per k and the SM
+// serves one wavefront per cycle; a shuffle ~3 issue cycles.
+double phase_cost(const std::vector<KN>& kn, const Shape& sh, int CT, int NT, bool ws) {
+  if (CT % sh.TC != 0) return 1e300;
+  const int NCG = CT / sh.TC, TPW = 32 / sh.KQ, nwarps = NT / 32;
+  const int RP = ((sh.TO + sh.KQ - 1) / sh.KQ) * sh.KQ, RS = RP / sh.KQ;
   long tiles = 0;
-  double fma_tile = 0, ser_tile = 0, epi_tile = 0;
+  double fma = 0, wf = 0, epi = 0;
   for (auto& g : kn) {
-    const int n_og = (g.N + TO - 1) / TO;
-    tiles += (long)n_og * NCG;
-    const double kk = (double)g.K / ksplit;
-    const double L = 1 + lds_count(TO, ws);
-    fma_tile = std::max(fma_tile, kk * 4.0 * TO);
-    ser_tile = std::max(ser_tile, kk * (4.0 * TO + (ws ? 3.7 : 6.0) * L + 2));
-    epi_tile = std::max(epi_tile, (TO * (4 * act_cost(g.act) + 4.0)) / ksplit + 30.0 + (ksplit == 2 ? TO * 3.0 + 80.0 : 0.0));
+    tiles += (long)((g.N + sh.TO - 1) / sh.TO) * NCG;
+    const double kk = std::ceil((double)g.K / sh.KQ);
+    fma = std::max(fma, kk * sh.TC * sh.TO * 1.1 + kk * 4.0);
+    wf = std::max(wf, kk * (sh.TC + sh.TO) * (ws ? 1.0 : 2.5));
+    const double shf = sh.KQ == 4 ? (RP / 2 + RP / 4) * sh.TC : (sh.KQ == 2 ? (RP / 2) * sh.TC : 0);
+    epi = std::max(epi, shf * 3.0 + RS * sh.TC * (act_cost(g.act) + 1.5) + 150.0);
   }
-  if (ksplit == 2 && tiles > NT / 2) return 1e300;
-  const int warps = NT / 32;
-  double fma[4] = {0, 0, 0, 0}, ser[4] = {0, 0, 0, 0};
+  double smsp[4] = {0, 0, 0, 0}, smem = 0;
   int nw[4] = {0, 0, 0, 0};
-  for (int w = 0; w < warps; ++w) {
-    long cnt;
-    if (ksplit == 2) {
-      const long first = (long)(w % (warps / 2)) * 32;
-      cnt = first < tiles ? 1 : 0;
-    } else {
-      const long first = (long)w * 32;
-      cnt = first < tiles ? (tiles - first + NT - 1) / NT : 0;
-    }
+  for (int w = 0; w < nwarps; ++w) {
+    long cnt = 0;
+    for (long base = (long)w * TPW; base < tiles; base += (long)nwarps * TPW) ++cnt;
     if (cnt == 0) continue;
-    fma[w % 4] += cnt * fma_tile;
-    ser[w % 4] += cnt * (ser_tile + epi_tile);
+    smsp[w % 4] += cnt * (fma + epi);
     nw[w % 4]++;
+    smem += cnt * wf;
   }
   double worst = 0;
-  for (int s = 0; s < 4; ++s) {
-    const double t = nw[s] <= 1 ? ser[s] : std::max(fma[s] * 1.08 + 0.5 * (ser[s] - fma[s]) / nw[s], 0.62 * ser[s]);
-    worst = std::max(worst, t);
+  for (int q = 0; q < 4; ++q) {
+    // a lone warp on a sub-partition cannot hide shared-load / FMA latency (measured 4.8 vs 3.2 cycles per FFMA pair)
+    const double lat = nw[q] <= 1 ? 1.5 : (nw[q] == 2 ? 1.0 : 0.93);
+    worst = std::max(worst, smsp[q] * lat);
   }
-  return worst;
+  return std::max(worst, smem) + 100.0;
 }
 
 }  // namespace
@@ -306,7 +307,7 @@ bool build_plan(const cpz_model_desc& d, const PlanOptions& opt, Plan& out, std:
   };
 
   std::vector<std::vector<int>> phases;
-  std::vector<int> phase_to, phase_ks;
+  std::vector<int> phase_to, phase_ks, phase_tc;
   std::vector<GemmD> gemms;
   int arena_rows = 0, nn_off[3], flux_off = 0;
   bool chosen = false;
@@ -315,21 +316,29 @@ bool build_plan(const cpz_model_desc& d, const PlanOptions& opt, Plan& out, std:
     if (attempt == 0 && !same_depth) continue;
     plan_schedule(layer_major, phases, gemms, arena_rows, nn_off, flux_off);
     // choose TO per phase
-    phase_to.clear(); phase_ks.clear();
+    phase_to.clear(); phase_ks.clear(); phase_tc.clear();
     for (auto& ph : phases) {
       std::vector<KN> kn;
       for (int gi : ph) kn.push_back({gemms[gi].K, gemms[gi].N, gemms[gi].act});
-      int best = 4, best_ks = 1; double bc = 1e300;
-      const int cand_f[] = {2, 4, 6, 8, 10, 12};
-      const int cand_b[] = {4, 8, 12};
-      const int* cand = opt.keep_all ? cand_b : cand_f;
-      const int nc = opt.keep_all ? 3 : 6;
-      for (int ci = 0; ci < nc; ++ci)
-        for (int ks = 1; ks <= 2; ++ks) {
-          const double c1 = phase_cost(kn, cand[ci], ks, NCG, opt.NT, true);
-          if (c1 < bc) { bc = c1; best = cand[ci]; best_ks = ks; }
-        }
-      phase_to.push_back(best); phase_ks.push_back(best_ks);
+      Shape bs = {4, 4, 1};
+      double bc = 1e300;
+      // debug/tuning override: CPZ_SHAPES="tc,to,kq;tc,to,kq;..." (one triple per phase, forward plan only)
+      if (const char* ov = opt.keep_all ? nullptr : getenv("CPZ_SHAPES")) {
+        int idx = (int)phase_to.size(), cur = 0;
+        const char* q = ov;
+        while (cur < idx && *q) { if (*q == ';') ++cur; ++q; }
+        int a1, a2, a3;
+        if (cur == idx && sscanf(q, "%d,%d,%d", &a1, &a2, &a3) == 3) { bs = {a1, a2, a3}; bc = -1; }
+      }
+      if (bc > 0)
+      for (const Shape& sh : kShapes) {
+        if (opt.keep_all && sh.TO % 4 != 0) continue;  // the adjoint reads weight rows as float4
+        const double c1 = phase_cost(kn, sh, opt.CT, opt.NT, true);
+        if (c1 < bc) { bc = c1; bs = sh; }
+      }
+      const int best = bs.TO;
+      const int NCGp = opt.CT / bs.TC;
+      phase_to.push_back(bs.TO); phase_ks.push_back(bs.KQ); phase_tc.push_back(bs.TC);
       int tb = 0;
       for (int gi : ph) {
         GemmD& g = gemms[gi];
@@ -337,7 +346,7 @@ bool build_plan(const cpz_model_desc& d, const PlanOptions& opt, Plan& out, std:
         g.n_og = (g.N + best - 1) / best;
         g.Npad = g.n_og * best;
         g.tile_begin = tb;
-        tb += g.n_og * NCG;
+        tb += g.n_og * NCGp;
       }
     }
     // the adjoint also keeps a pre-activation/delta row for every layer output row (flux_off rows)
@@ -375,8 +384,9 @@ bool build_plan(const cpz_model_desc& d, const PlanOptions& opt, Plan& out, std:
     M.phase[p].g0 = phases[p].front();
     M.phase[p].g1 = phases[p].back() + 1;
     int nt = 0;
-    for (int gi : phases[p]) nt += gemms[gi].n_og * NCG;
+    for (int gi : phases[p]) nt += gemms[gi].n_og * (opt.CT / phase_tc[p]);
     M.phase[p].n_tiles = nt;
+    M.phase[p].TC = phase_tc[p];
     M.phase[p].TO = phase_to[p];
     M.phase[p].ksplit = phase_ks[p];
   }

@@ -51,15 +51,29 @@ __host__ __device__ inline SolveSmem solve_smem_layout(const ModelD& M, int CT, 
 struct StageCoef { float c[CPZ_MAX_STAGES]; };
 
 // MLP part of one RHS evaluation (each phase ends with a block barrier); also refreshes the diurnal top flux.
+template <int CT, int NT, bool WS, bool SAVE_Z>
+__device__ __forceinline__ void run_phase_cached(const ModelD& M, int p, const PhaseCache& pc, const float* __restrict__ in,
+                                                 float* __restrict__ arena, float* __restrict__ zarena,
+                                                 const float* __restrict__ wsm, const float* __restrict__ theta) {
+  switch (p) {  // static indices keep the cache in registers
+    case 0: run_phase<WS, CT, NT, SAVE_Z>(M, 0, pc.tp[0], pc.shape[0], pc.rounds[0], in, arena, zarena, wsm, theta); break;
+    case 1: run_phase<WS, CT, NT, SAVE_Z>(M, 1, pc.tp[1], pc.shape[1], pc.rounds[1], in, arena, zarena, wsm, theta); break;
+    case 2: run_phase<WS, CT, NT, SAVE_Z>(M, 2, pc.tp[2], pc.shape[2], pc.rounds[2], in, arena, zarena, wsm, theta); break;
+    case 3: run_phase<WS, CT, NT, SAVE_Z>(M, 3, pc.tp[3], pc.shape[3], pc.rounds[3], in, arena, zarena, wsm, theta); break;
+    default: run_phase<WS, CT, NT, SAVE_Z>(M, p, pc.tp[0], 0, -1, in, arena, zarena, wsm, theta); break;
+  }
+}
+
 template <int CT, int NT, bool WS>
-__device__ __forceinline__ void rhs_mlp(const ModelD& M, const float* __restrict__ in, float* __restrict__ arena,
-                                        const float* __restrict__ wsm, const float* __restrict__ theta,
-                                        float* __restrict__ bcf, const float* __restrict__ qs, float t) {
+__device__ __forceinline__ void rhs_mlp(const ModelD& M, const PhaseCache& pc, const float* __restrict__ in,
+                                        float* __restrict__ arena, const float* __restrict__ wsm,
+                                        const float* __restrict__ theta, float* __restrict__ bcf,
+                                        const float* __restrict__ qs, float t) {
   if (M.flags & F_DIURNAL) {
     if (threadIdx.x < CT) bcf[(M.nbc - 1) * CT + threadIdx.x] = diurnal_top_eff(M, qs[threadIdx.x], t);
   }
   for (int p = 0; p < M.n_phase; ++p) {
-    run_phase<WS, CT, NT, false>(M, p, in, arena, nullptr, wsm, theta);
+    run_phase_cached<CT, NT, WS, false>(M, p, pc, in, arena, nullptr, wsm, theta);
     __syncthreads();
   }
   if (M.n_phase == 0 && (M.flags & F_DIURNAL)) __syncthreads();
@@ -90,9 +104,11 @@ __device__ __forceinline__ void rhs_tendencies(const ModelD& M, const float* __r
   }
 }
 
+// M: shared-memory copy of the model (for the non-inlined phase functions); Mp: the kernel parameter itself, whose
+// fields the inlined stencil reads as constant-bank operands.
 template <int CT, int NT, bool WS, int NF>
-__device__ __forceinline__ void solve_body(const ModelD& M, const TableauD& tab, const TimeD& tm, const SolveArgs& a,
-                                           float* smem) {
+__device__ __forceinline__ void solve_body(const ModelD& M, const ModelD& Mp, const TableauD& tab, const TimeD& tm,
+                                           const SolveArgs& a, float* smem) {
   const SolveSmem L = solve_smem_layout(M, CT, tab.n_stages);
   float* wsm = smem + L.w;
   float* xs = smem + L.buf;                 // step state
@@ -131,10 +147,12 @@ __device__ __forceinline__ void solve_body(const ModelD& M, const TableauD& tab,
   __syncthreads();
 
   const int ns = tab.n_stages;
+  PhaseCache pc;
+  build_phase_cache<WS, CT, NT>(M, pc);
 
   if (a.rhs_only) {
-    rhs_mlp<CT, NT, WS>(M, xs, arena, wsm, a.theta, bcf, qs, a.t_rhs);
-    rhs_tendencies<CT, NT, NF>(M, xs, arena, bcf, [=](int k0, int c, const float (&dx)[NF][4]) {
+    rhs_mlp<CT, NT, WS>(M, pc, xs, arena, wsm, a.theta, bcf, qs, a.t_rhs);
+    rhs_tendencies<CT, NT, NF>(Mp, xs, arena, bcf, [=](int k0, int c, const float (&dx)[NF][4]) {
 #pragma unroll
       for (int q = 0; q < NF; ++q)
 #pragma unroll
@@ -171,12 +189,12 @@ __device__ __forceinline__ void solve_body(const ModelD& M, const TableauD& tab,
         if (a.prof) {
           for (int p = 0; p < M.n_phase; ++p) {
             CPZ_PROF_BEGIN();
-            run_phase<WS, CT, NT, false>(M, p, in, arena, nullptr, wsm, a.theta);
+            run_phase_cached<CT, NT, WS, false>(M, p, pc, in, arena, nullptr, wsm, a.theta);
             __syncthreads();
             CPZ_PROF_END(p < 3 ? p : 3);
           }
         } else {
-          rhs_mlp<CT, NT, WS>(M, in, arena, wsm, a.theta, bcf, qs, tb + tab.c[i] * h);
+          rhs_mlp<CT, NT, WS>(M, pc, in, arena, wsm, a.theta, bcf, qs, tb + tab.c[i] * h);
         }
         const bool last = (i + 1 == ns);
         CPZ_PROF_BEGIN();
@@ -187,7 +205,7 @@ __device__ __forceinline__ void solve_body(const ModelD& M, const TableauD& tab,
         for (int j = 0; j < CPZ_MAX_STAGES; ++j) sc.c[j] = last ? tab.b[j] : tab.a[(i + 1) % CPZ_MAX_STAGES][j];
         const float coef_i = last ? tab.b[i] : tab.a[(i + 1) % CPZ_MAX_STAGES][i];
         const float* xs_c = xs;
-        rhs_tendencies<CT, NT, NF>(M, in, arena, bcf, [=](int k0, int c, const float (&dx)[NF][4]) {
+        rhs_tendencies<CT, NT, NF>(Mp, in, arena, bcf, [=](int k0, int c, const float (&dx)[NF][4]) {
 #pragma unroll
           for (int q = 0; q < NF; ++q)
 #pragma unroll
@@ -247,8 +265,8 @@ __global__ void __launch_bounds__(NT, 1) solve_kernel(const __grid_constant__ Mo
   extern __shared__ __align__(16) float smem[];
   const SolveSmem L = solve_smem_layout(Mp, CT, tab.n_stages);
   const ModelD& M = model_to_smem<NT>(Mp, smem + L.model);
-  if (Mp.nf == 3) solve_body<CT, NT, WS, 3>(M, tab, tm, a, smem);
-  else solve_body<CT, NT, WS, 1>(M, tab, tm, a, smem);
+  if (Mp.nf == 3) solve_body<CT, NT, WS, 3>(M, Mp, tab, tm, a, smem);
+  else solve_body<CT, NT, WS, 1>(M, Mp, tab, tm, a, smem);
 }
 
 }  // namespace cpz
