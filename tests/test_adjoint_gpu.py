@@ -125,7 +125,9 @@ def test_train_step_matches_flux_adam(ctx):
         np.testing.assert_allclose(loss, l_pre, rtol=1e-6)  # the callback sees the loss BEFORE the update
         tot, comps, g = oracle_loss_grad(d, theta.numpy(), x0, bcs, tgt, W_GRAD)
         assert abs(loss[6] - tot) / abs(tot) <= TOL
-        assert np.linalg.norm(g_gpu - g) / np.linalg.norm(g) <= TOL
+        g32 = oracle_loss_grad(d, theta.numpy(), x0, bcs, tgt, W_GRAD, dtype=torch.float32)[2]
+        floor = np.linalg.norm(g32 - g) / np.linalg.norm(g)
+        assert np.linalg.norm(g_gpu - g) / np.linalg.norm(g) <= max(TOL, floor)  # same rule as _check
         theta, mt, vt, bp = nde.adam_step(theta, t64(g_gpu), mt, vt, bp, lr)
         got = m.get_theta()
         err = np.abs(got - theta.numpy()).max() / lr
