@@ -22,12 +22,15 @@ struct AdjArgs {
   const float* ckpt;     // [n_tiles][n_ckpt][S][CT]
   float* kslots;         // [grid][n_stages][S][CT]
   float* segx;           // [grid][seg_len][S][CT]
-  float* gpart;          // [grid][P]   (zeroed by the host)
+  float* gpart;          // [grid][M.slab] gradient slabs in tile layout (zeroed by the host)
   float* lpart;          // [grid][8]   (zeroed by the host)
   int ncol, n_saved, n_ckpt, n_tiles, seg_len;
   float w[6];
   float inv_prof, inv_grad;  // 1/(Nz*n_saved*ncol_global), 1/((Nz+1)*n_saved*ncol_global)
+  unsigned long long* prof;  // optional [8] cycle counters of CTA 0 (CPZ_PROF=1)
 };
+#define CPZ_APROF_T() ((a.prof && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0)
+#define CPZ_APROF_ADD(slot, t0) do { if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[slot] += (unsigned long long)(clock64() - (t0)); } while (0)
 
 struct AdjSmem {
   int w, xs, xbar, xin, xb, arena, zarena, bcf, qs, red, model, total_floats;
@@ -160,7 +163,7 @@ __device__ __noinline__ void centres_vjp(const ModelD& M, float* __restrict__ kb
 // Returns the tile in acc (pairs over columns); the caller applies act' or accumulates into Xbar.
 template <bool WS, int CT>
 __device__ __forceinline__ void bwd_data_tile(const GemmD& g, const float* __restrict__ W, const float* __restrict__ delta,
-                                              int k0, int cg, float2 (&acc)[4][2]) {
+                                              int k0, int cg, float (&acc)[4][4]) {
   const int K = g.K, N = g.N;
   const int ldw = WS ? g.Npad : N;
   int kr[4];
@@ -168,6 +171,7 @@ __device__ __forceinline__ void bwd_data_tile(const GemmD& g, const float* __res
   for (int kk = 0; kk < 4; ++kk) kr[kk] = min(k0 + kk, K - 1) * ldw;
   const float* dp = delta + 4 * cg;
   const int N4 = WS ? (N & ~3) : 0;
+#pragma unroll 2
   for (int j = 0; j < N4; j += 4) {
     float4 d[4];
 #pragma unroll
@@ -178,8 +182,10 @@ __device__ __forceinline__ void bwd_data_tile(const GemmD& g, const float* __res
       const float wj[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
-        acc[kk][0] = __ffma2_rn(make_float2(d[jj].x, d[jj].y), make_float2(wj[jj], wj[jj]), acc[kk][0]);
-        acc[kk][1] = __ffma2_rn(make_float2(d[jj].z, d[jj].w), make_float2(wj[jj], wj[jj]), acc[kk][1]);
+        acc[kk][0] = fmaf(wj[jj], d[jj].x, acc[kk][0]);
+        acc[kk][1] = fmaf(wj[jj], d[jj].y, acc[kk][1]);
+        acc[kk][2] = fmaf(wj[jj], d[jj].z, acc[kk][2]);
+        acc[kk][3] = fmaf(wj[jj], d[jj].w, acc[kk][3]);
       }
     }
   }
@@ -188,28 +194,40 @@ __device__ __forceinline__ void bwd_data_tile(const GemmD& g, const float* __res
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       const float wv = WS ? W[kr[kk] + j] : __ldg(W + kr[kk] + j);
-      acc[kk][0] = __ffma2_rn(make_float2(d.x, d.y), make_float2(wv, wv), acc[kk][0]);
-      acc[kk][1] = __ffma2_rn(make_float2(d.z, d.w), make_float2(wv, wv), acc[kk][1]);
+      acc[kk][0] = fmaf(wv, d.x, acc[kk][0]);
+      acc[kk][1] = fmaf(wv, d.y, acc[kk][1]);
+      acc[kk][2] = fmaf(wv, d.z, acc[kk][2]);
+      acc[kk][3] = fmaf(wv, d.w, acc[kk][3]);
     }
   }
 }
 
-// Weight gradient of one gemm on a 4(k) x 4(j) tile: dW[k][j] += sum_c a[k][c] delta[j][c]; RED into gpart (destructure
-// order, W is [K][N] row-major there).
+// Weight gradient of one gemm on a 4(k) x 4(j) tile: dW[k][j] += sum_c a[k][c] delta[j][c], accumulated into the
+// tile's 16 contiguous floats of the CTA's gradient slab with a plain vectorised read-modify-write (every tile has
+// exactly one owner thread per CTA, stages are separated by block barriers, so no atomics are needed; the 16 floats of
+// consecutive lanes are contiguous, i.e. fully coalesced).
 template <int CT>
 __device__ __forceinline__ void bwd_weight_tile(const GemmD& g, const float* __restrict__ a, const float* __restrict__ delta,
-                                                int k0, int j0, float* __restrict__ gW) {
+                                                int k0, int j0, float* __restrict__ gtile) {
   const int K = g.K, N = g.N;
-  float2 acc[4][4];
+  float4 old[4];
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) old[kk] = __ldcg(reinterpret_cast<const float4*>(gtile) + kk);  // issued early, used last
+  float acc[4][4];
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) acc[kk][jj] = make_float2(0.f, 0.f);
+    for (int jj = 0; jj < 4; ++jj) acc[kk][jj] = 0.f;
   int kr[4], jr[4];
 #pragma unroll
   for (int t = 0; t < 4; ++t) { kr[t] = min(k0 + t, K - 1) * CT; jr[t] = min(j0 + t, N - 1) * CT; }
+  // The reduction runs over the tile's columns in chunks of 4. Lanes of a quarter-warp own tiles whose delta rows are
+  // 4 rows (= 512 B, the same banks) apart, so every lane starts at a different chunk: at each step the 8 lanes read 8
+  // different 16-byte bank groups (conflict-free) instead of colliding 8-way on one.
+  const int rot = (threadIdx.x & 7) * 4;
 #pragma unroll 2
-  for (int c = 0; c < CT; c += 4) {
+  for (int c0 = 0; c0 < CT; c0 += 4) {
+    const int c = (c0 + rot) & (CT - 1);
     float4 av[4], dv[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
@@ -220,15 +238,23 @@ __device__ __forceinline__ void bwd_weight_tile(const GemmD& g, const float* __r
     for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
-        acc[kk][jj] = __ffma2_rn(make_float2(av[kk].x, av[kk].y), make_float2(dv[jj].x, dv[jj].y), acc[kk][jj]);
-        acc[kk][jj] = __ffma2_rn(make_float2(av[kk].z, av[kk].w), make_float2(dv[jj].z, dv[jj].w), acc[kk][jj]);
+        acc[kk][jj] = fmaf(av[kk].x, dv[jj].x, acc[kk][jj]);
+        acc[kk][jj] = fmaf(av[kk].y, dv[jj].y, acc[kk][jj]);
+        acc[kk][jj] = fmaf(av[kk].z, dv[jj].z, acc[kk][jj]);
+        acc[kk][jj] = fmaf(av[kk].w, dv[jj].w, acc[kk][jj]);
       }
   }
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj)
-      if (k0 + kk < K && j0 + jj < N) atomicAdd(gW + (size_t)(k0 + kk) * N + j0 + jj, acc[kk][jj].x + acc[kk][jj].y);
+  for (int kk = 0; kk < 4; ++kk) {
+    // rows/columns past the layer edge hold duplicates of the clamped row: zero them so the slab stays clean
+    const bool kv = k0 + kk < K;
+    float4 o = old[kk];
+    o.x += (kv && j0 + 0 < N) ? acc[kk][0] : 0.f;
+    o.y += (kv && j0 + 1 < N) ? acc[kk][1] : 0.f;
+    o.z += (kv && j0 + 2 < N) ? acc[kk][2] : 0.f;
+    o.w += (kv && j0 + 3 < N) ? acc[kk][3] : 0.f;
+    __stcg(reinterpret_cast<float4*>(gtile) + kk, o);
+  }
 }
 
 // Backward through layer index `l` of every net that has it: weight/bias gradients, then delta of the previous layer
@@ -245,9 +271,11 @@ __device__ __noinline__ void mlp_backward_layer(const ModelD& M, int l, const fl
     const int nkg = (S + 3) / 4;
     for (int tile = threadIdx.x; tile < nkg * NCG; tile += NT) {
       const int cg = tile % NCG, k0 = (tile / NCG) * 4;
-      float2 acc[4][2];
+      float acc[4][4];
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) { acc[kk][0] = make_float2(0.f, 0.f); acc[kk][1] = make_float2(0.f, 0.f); }
+      for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) acc[kk][cc] = 0.f;
       for (int gi = 0; gi < M.n_gemm; ++gi) {
         const GemmD& g = M.gemm[gi];
         if (g.layer != 0) continue;
@@ -259,7 +287,7 @@ __device__ __noinline__ void mlp_backward_layer(const ModelD& M, int l, const fl
         if (k0 + kk < S) {
           float4* p = reinterpret_cast<float4*>(xb + (k0 + kk) * CT + 4 * cg);
           float4 v = *p;
-          v.x += acc[kk][0].x; v.y += acc[kk][0].y; v.z += acc[kk][1].x; v.w += acc[kk][1].y;
+          v.x += acc[kk][0]; v.y += acc[kk][1]; v.z += acc[kk][2]; v.w += acc[kk][3];
           *p = v;
         }
       }
@@ -278,9 +306,11 @@ __device__ __noinline__ void mlp_backward_layer(const ModelD& M, int l, const fl
       float* zprev = zarena + g.in_off * CT;
       for (int tile = threadIdx.x; tile < nkg * NCG; tile += NT) {
         const int cg = tile % NCG, k0 = (tile / NCG) * 4;
-        float2 acc[4][2];
+        float acc[4][4];
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) { acc[kk][0] = make_float2(0.f, 0.f); acc[kk][1] = make_float2(0.f, 0.f); }
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) acc[kk][cc] = 0.f;
         bwd_data_tile<WS, CT>(g, W, zarena + g.out_off * CT, k0, cg, acc);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
@@ -288,10 +318,10 @@ __device__ __noinline__ void mlp_backward_layer(const ModelD& M, int l, const fl
             float4* p = reinterpret_cast<float4*>(zprev + (k0 + kk) * CT + 4 * cg);
             const float4 z = *p;
             float4 d;
-            d.x = acc[kk][0].x * act_grad(actp, z.x);
-            d.y = acc[kk][0].y * act_grad(actp, z.y);
-            d.z = acc[kk][1].x * act_grad(actp, z.z);
-            d.w = acc[kk][1].y * act_grad(actp, z.w);
+            d.x = acc[kk][0] * act_grad(actp, z.x);
+            d.y = acc[kk][1] * act_grad(actp, z.y);
+            d.z = acc[kk][2] * act_grad(actp, z.z);
+            d.w = acc[kk][3] * act_grad(actp, z.w);
             *p = d;
           }
         }
@@ -307,7 +337,7 @@ __device__ __noinline__ void mlp_backward_layer(const ModelD& M, int l, const fl
     const int nkg = (g.K + 3) / 4, njg = (g.N + 3) / 4;
     for (int tile = threadIdx.x; tile < nkg * njg; tile += NT) {
       const int jg = tile % njg, kg = tile / njg;
-      bwd_weight_tile<CT>(g, a, delta, kg * 4, jg * 4, gpart + g.w_off);
+      bwd_weight_tile<CT>(g, a, delta, kg * 4, jg * 4, gpart + g.gw_off + (size_t)tile * 16);
     }
     for (int j = threadIdx.x; j < g.N; j += NT) {
       float s = 0.f;
@@ -315,7 +345,7 @@ __device__ __noinline__ void mlp_backward_layer(const ModelD& M, int l, const fl
         const float4 d = *reinterpret_cast<const float4*>(delta + j * CT + c);
         s += (d.x + d.y) + (d.z + d.w);
       }
-      atomicAdd(gpart + g.b_off + j, s);
+      gpart[g.gb_off + j] += s;  // thread j owns this entry
     }
   }
 }
@@ -400,7 +430,7 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, 
   const float h = tm.dt / (float)tm.n_substeps;
   float* slots = a.kslots + (size_t)blockIdx.x * ns * SC;
   float* segx = a.segx + (size_t)blockIdx.x * a.seg_len * SC;
-  float* gpart = a.gpart + (size_t)blockIdx.x * M.P;
+  float* gpart = a.gpart + (size_t)blockIdx.x * M.slab;
   float* gflux = arena + M.flux_off * CT;
   uint32_t parity = 0;
   float lsum[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -495,6 +525,7 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, 
         const int nstep = n0 + r / tm.n_substeps, sub = r % tm.n_substeps;
         const float tb = tm.t0 + (float)nstep * tm.dt + (float)sub * h;
         // (a) forward stages 0..ns-2 -> k_i into the slots
+        const long long pa0 = CPZ_APROF_T();
         for (int i = 0; i + 1 < ns; ++i) {
           const float* in = xs;
           if (i > 0) { stage_input<CT, NT>(tab, i, h, xs, slots, SC, xin); __syncthreads(); in = xin; }
@@ -508,8 +539,10 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, 
           });
           __syncthreads();
         }
+        CPZ_APROF_ADD(0, pa0);
         // (b) reverse stages
         for (int i = ns - 1; i >= 0; --i) {
+          const long long pb0 = CPZ_APROF_T();
           const float* in = xs;
           if (i > 0) { stage_input<CT, NT>(tab, i, h, xs, slots, SC, xin); in = xin; }
           // kbar_i = h (b_i xbar + sum_{j>i} a_ji Xbar_j)   (slots j>i hold Xbar_j)
@@ -530,22 +563,31 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, 
             if (threadIdx.x < CT) bcf[(M.nbc - 1) * CT + threadIdx.x] = diurnal_top_eff(M, qs[threadIdx.x], tb + tab.c[i] * h);
           }
           __syncthreads();
+          CPZ_APROF_ADD(1, pb0);
+          const long long pb1 = CPZ_APROF_T();
           // MLP forward keeping z and a (the last layer's outputs are not needed: F is linear in them)
           for (int p = 0; p < M.n_phase; ++p) {
             if (M.gemm[M.phase[p].g0].layer == Lmax && M.gemm[M.phase[p].g1 - 1].layer == Lmax) continue;
             run_phase_cached<CT, NT, WS, true>(M, p, pc, in, arena, zarena, wsm, a.theta);
             __syncthreads();
           }
+          CPZ_APROF_ADD(2, pb1);
+          const long long pb2 = CPZ_APROF_T();
           faces_vjp<CT, NT>(M, in, xb, zarena, gflux);
           __syncthreads();
           centres_vjp<CT, NT>(M, xb, gflux);
           __syncthreads();
+          CPZ_APROF_ADD(3, pb2);
           for (int l = Lmax; l >= 0; --l) {
+            const long long pb3 = CPZ_APROF_T();
             mlp_backward_layer<WS, CT, NT>(M, l, in, arena, zarena, xb, wsm, a.theta, gpart);
             __syncthreads();
+            CPZ_APROF_ADD(4 + (l < 2 ? l : 2), pb3);
           }
+          const long long pb4 = CPZ_APROF_T();
           store_state(slots + (size_t)i * SC, xb);  // slot i now holds Xbar_i
           __syncthreads();
+          CPZ_APROF_ADD(1, pb4);
         }
         // xbar_n = xbar_{n+1} + sum_i Xbar_i
         for (int e4 = threadIdx.x; e4 < SC / 4; e4 += NT) {

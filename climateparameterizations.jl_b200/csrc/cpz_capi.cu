@@ -83,6 +83,21 @@ static int rebuild_plans(cpz_model* m) {
   bo.smem_budget = m->ctx->smem_optin;
   bo.other_smem_bytes = adjoint_other_smem(m->desc.n_fields * m->desc.Nz, m->desc.n_fields == 3 ? 6 : 2, m->CT);
   m->has_bwd = build_plan(m->desc, bo, m->bwd, m->bwd_err);
+  if (m->has_bwd && m->P > 0) {
+    std::vector<int> map(m->P, 0);
+    const ModelD& B = m->bwd.M;
+    for (int gi = 0; gi < B.n_gemm; ++gi) {
+      const GemmD& g = B.gemm[gi];
+      const int njg = (g.N + 3) / 4;
+      for (int k = 0; k < g.K; ++k)
+        for (int j = 0; j < g.N; ++j)
+          map[g.w_off + k * g.N + j] = g.gw_off + ((k / 4) * njg + j / 4) * 16 + (k % 4) * 4 + (j % 4);
+      for (int j = 0; j < g.N; ++j) map[g.b_off + j] = g.gb_off + j;
+    }
+    if (!m->d_gmap) CPZ_CUDA(cudaMalloc(&m->d_gmap, m->P * sizeof(int)));
+    CPZ_CUDA(cudaMemcpyAsync(m->d_gmap, map.data(), m->P * sizeof(int), cudaMemcpyHostToDevice, m->ctx->stream));
+    CPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  }
   return CPZ_OK;
 }
 
@@ -203,6 +218,7 @@ int cpz_model_destroy(cpz_model* m) {
   if (m->d_theta) cudaFree(m->d_theta);
   if (m->d_m) cudaFree(m->d_m);
   if (m->d_v) cudaFree(m->d_v);
+  if (m->d_gmap) cudaFree(m->d_gmap);
   DevBuf* bufs[] = {&m->b_x0, &m->b_bcs, &m->b_q, &m->b_traj, &m->b_tgt, &m->b_ckpt, &m->b_scr, &m->b_part, &m->b_red, &m->b_out, &m->b_w};
   for (DevBuf* b : bufs) release(*b);
   delete m;

@@ -1,15 +1,21 @@
 // Adjoint kernel instantiations, small reduction / optimiser kernels and their launchers.
+#include <cstdio>
+#include <cstdlib>
+
 #include "cpz_launch.h"
 
 namespace cpz {
 
 // ---- small reductions -----------------------------------------------------------------------------------------------
-// out[p] = sum over slabs of part[slab][p]   (fixed order: deterministic)
-__global__ void reduce_slabs_kernel(const float* __restrict__ part, int n_slabs, int P, float* __restrict__ out) {
+// out[p] = sum over CTA slabs of part[slab][map[p]]  (fixed order: deterministic); map translates destructure order into
+// the adjoint's 4x4-tile slab layout.
+__global__ void reduce_slabs_kernel(const float* __restrict__ part, int n_slabs, int slab, const int* __restrict__ map, int P,
+                                    float* __restrict__ out) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
+  const int o = map[p];
   float s = 0.f;
-  for (int t = 0; t < n_slabs; ++t) s += part[(size_t)t * P + p];
+  for (int t = 0; t < n_slabs; ++t) s += part[(size_t)t * slab + o];
   out[p] = s;
 }
 
@@ -100,6 +106,25 @@ static int launch_adjoint_t(cpz_model* m, const AdjArgs& a, int grid) {
   if (smem > m->ctx->smem_optin) return fail(CPZ_ERR_INVALID, "adjoint kernel needs %zu B shared memory, device allows %zu", smem, m->ctx->smem_optin);
   auto kern = adjoint_kernel<CT, NT, WS>;
   CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static const bool prof = getenv("CPZ_PROF") != nullptr;
+  if (prof) {
+    AdjArgs ap = a;
+    unsigned long long* d = nullptr;
+    CPZ_CUDA(cudaMalloc(&d, 8 * sizeof(unsigned long long)));
+    CPZ_CUDA(cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), m->ctx->stream));
+    ap.prof = d;
+    kern<<<grid, NT, smem, m->ctx->stream>>>(m->bwd.M, m->tab, m->tm, ap);
+    unsigned long long hc[8];
+    CPZ_CUDA(cudaMemcpyAsync(hc, d, sizeof(hc), cudaMemcpyDeviceToHost, m->ctx->stream));
+    CPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    cudaFree(d);
+    const int tiles0 = (a.n_tiles + grid - 1) / grid;  // tiles processed by CTA 0
+    const double nrk = (double)m->tm.n_steps * m->tm.n_substeps * tiles0, nst = nrk * m->tab.n_stages;
+    fprintf(stderr, "[cpz prof adjoint] cycles per RK step: fwd-recompute(5 stages) %.0f | per reverse stage: combine+store %.0f mlp-fwd %.0f stencil-vjp %.0f bwd-L0 %.0f bwd-L1 %.0f bwd-L2+ %.0f\n",
+            hc[0] / nrk, hc[1] / nst, hc[2] / nst, hc[3] / nst, hc[4] / nst, hc[5] / nst, hc[6] / nst);
+    m->ctx->launches++;
+    return CPZ_OK;
+  }
   kern<<<grid, NT, smem, m->ctx->stream>>>(m->bwd.M, m->tab, m->tm, a);
   CPZ_CUDA(cudaGetLastError());
   m->ctx->launches++;
@@ -117,7 +142,7 @@ int launch_adjoint(cpz_model* m, const AdjArgs& a, int grid) {
   return CPZ_OK
 
 int launch_reduce_slabs(cpz_model* m, const float* part, int n_slabs, int P, float* out) {
-  reduce_slabs_kernel<<<(P + 255) / 256, 256, 0, m->ctx->stream>>>(part, n_slabs, P, out);
+  reduce_slabs_kernel<<<(P + 255) / 256, 256, 0, m->ctx->stream>>>(part, n_slabs, m->bwd.M.slab, m->d_gmap, P, out);
   CPZ_LAUNCHED(m);
 }
 int launch_pack_loss(cpz_model* m, const float* lpart, int n_slabs, float ncol, float* pack_tail) {

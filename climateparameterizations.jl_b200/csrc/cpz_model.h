@@ -20,6 +20,7 @@ struct GemmD {
   int n_og;          // output groups = ceil(N/TO)
   int TO;            // outputs per thread tile
   int net, layer;
+  int gw_off, gb_off;// adjoint: offsets of this gemm's weight-gradient tiles / bias gradients in a CTA's gradient slab
 };
 
 // Gemms [g0,g1) run concurrently between two block barriers over a flattened tile space.
@@ -52,6 +53,7 @@ struct ModelD {
   int n_nets, n_gemm, n_phase;
   int nbc;             // 6 or 2
   int P;               // total parameters
+  int slab;            // adjoint: floats per CTA gradient slab (4x4 weight-gradient tiles, 16 contiguous floats each, then biases)
   int w_in_smem;       // 1: all weights resident in shared memory
   int smem_w_floats;   // size of the shared weight arena
   int arena_floats;    // per-column floats of the activation arena (rows; multiply by CT)

@@ -376,6 +376,14 @@ bool build_plan(const cpz_model_desc& d, const PlanOptions& opt, Plan& out, std:
     }
     M.smem_w_floats = M.w_in_smem ? (int)((f + 3) & ~(size_t)3) : 0;
   }
+  // gradient slab layout of the adjoint: per gemm ceil(K/4)*ceil(N/4) tiles of 16 floats (thread-contiguous, so the
+  // read-modify-write of a warp is one coalesced 2 KB span), then the bias gradients
+  {
+    int off2 = 0;
+    for (auto& g : gemms) { g.gw_off = off2; off2 += ((g.K + 3) / 4) * ((g.N + 3) / 4) * 16; }
+    for (auto& g : gemms) { g.gb_off = off2; off2 += (g.N + 3) & ~3; }
+    M.slab = off2;
+  }
   M.n_gemm = (int)gemms.size();
   M.n_phase = (int)phases.size();
   if (M.n_gemm > CPZ_MAX_GEMM || M.n_phase > CPZ_MAX_PHASE) { err = "too many layers"; return false; }
