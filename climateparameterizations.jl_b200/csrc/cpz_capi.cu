@@ -219,7 +219,7 @@ int cpz_model_destroy(cpz_model* m) {
   if (m->d_m) cudaFree(m->d_m);
   if (m->d_v) cudaFree(m->d_v);
   if (m->d_gmap) cudaFree(m->d_gmap);
-  DevBuf* bufs[] = {&m->b_x0, &m->b_bcs, &m->b_q, &m->b_traj, &m->b_tgt, &m->b_ckpt, &m->b_scr, &m->b_part, &m->b_red, &m->b_out, &m->b_w};
+  DevBuf* bufs[] = {&m->b_x0, &m->b_bcs, &m->b_q, &m->b_traj, &m->b_tgt, &m->b_ckpt, &m->b_scr, &m->b_part, &m->b_red, &m->b_out, &m->b_w, &m->b_wimg};
   for (DevBuf* b : bufs) release(*b);
   delete m;
   return CPZ_OK;
@@ -258,6 +258,7 @@ int cpz_model_describe(const cpz_model* m, char* buf, size_t buf_len) {
       s += "\n";
     }
   };
+  s += tc_describe(m);
   dump("forward", m->fwd, solve_other_smem(m->desc, m->CT, m->tab.n_stages));
   if (m->has_bwd) dump("adjoint", m->bwd, adjoint_other_smem(m->desc.n_fields * m->desc.Nz, m->desc.n_fields == 3 ? 6 : 2, m->CT));
   else s += "adjoint plan: unavailable (" + m->bwd_err + ")\n";

@@ -7,6 +7,9 @@
 
 namespace cpz {
 int launch_solve(cpz_model* m, const SolveArgs& a);
+int launch_solve_tc(cpz_model* m, const SolveArgs& a);
+// one line for cpz_model_describe: which forward kernel this model runs on and why
+std::string tc_describe(const cpz_model* m);  // 1 = not eligible, use the SIMT kernel
 int launch_adjoint(cpz_model* m, const AdjArgs& a, int grid);
 int launch_closure(cpz_model* m, const ClosureD& cd, const ClosureArgs& a);
 int launch_reduce_slabs(cpz_model* m, const float* part, int n_slabs, int P, float* out);
