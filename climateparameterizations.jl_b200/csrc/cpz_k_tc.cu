@@ -1,4 +1,6 @@
 // Tensor-core (tcgen05) forward solve: eligibility, weight image, launcher.
+#include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "cpz_launch.h"
@@ -28,20 +30,20 @@ bool tc_plan(const cpz_model* m, TcD& T, std::string& why) {
   T.act1 = n0.act[0]; T.act2 = n0.act[1]; T.act3 = n0.act[2];
   if (3 * T.h1 > 160 || T.h2 > 32 || T.h1 < 1 || T.h2 < 1) { why = "hidden widths outside 3*h1 <= 160, h2 <= 32"; return false; }
   T.n1b = 3 * T.h1 > 128 ? 3 * T.h1 - 128 : 0;
-  auto windows = [](int width, int* start, int& steps, int& rows) {
-    steps = 0; rows = 0;
-    for (int q = 0; q < 3; ++q) {
-      start[q] = (width * q) & ~3;
-      const int s = (width * q + width - start[q] + 7) / 8;
-      if (s > steps) steps = s;
-    }
-    for (int q = 0; q < 3; ++q) if (start[q] + 8 * steps > rows) rows = start[q] + 8 * steps;
-    rows = (rows + 3) & ~3;
-  };
-  windows(T.h1, T.k2_start, T.k2_steps, T.h1_rows);
-  windows(T.h2, T.k3_start, T.k3_steps, T.h2_rows);
-  if (T.h1_rows < 128 + 32) T.h1_rows = 160;  // the layer-1 epilogue writes rows 0..127 (+ block 1) unconditionally
-  const int K2 = 8 * T.k2_steps, K3 = 8 * T.k3_steps;
+  // K windows: net q's inputs are operand rows width*q.. ; a window starts on a 4-row chunk and spans 8*steps rows
+  int need2 = 0, need3 = 0;
+  for (int q = 0; q < 3; ++q) {
+    T.k2_start[q] = (T.h1 * q) & ~3; T.k3_start[q] = (T.h2 * q) & ~3;
+    need2 = std::max(need2, T.h1 * q + T.h1 - T.k2_start[q]);
+    need3 = std::max(need3, T.h2 * q + T.h2 - T.k3_start[q]);
+  }
+  if (need2 > 8 * TC_K2S) { why = "layer-2 window"; return false; }
+  T.k3_steps = need3 <= 24 ? 3 : 4;
+  if (need3 > 32) { why = "layer-3 window needs more than 4 K steps"; return false; }
+  // operand rows: the layer-1 epilogue writes rows 0..127 unconditionally and rows 128..128+n1b of the quadrant-3 block
+  T.h1_rows = (std::max(T.k2_start[2] + 8 * TC_K2S, 160) + 7) & ~7;
+  T.h2_rows = (T.k3_start[2] + 8 * T.k3_steps + 7) & ~7;
+  const int K2 = 8 * TC_K2S, K3 = 8 * T.k3_steps;
   if (2 * K2 + 2 * K3 > 192) { why = "layer-2/3 stacks exceed the 192 free TMEM columns"; return false; }
   T.c_a2hi = 192; T.c_a2lo = 192 + K2; T.c_a3hi = 192 + 2 * K2; T.c_a3lo = 192 + 2 * K2 + K3;
   const ModelD& M = m->fwd.M;
@@ -53,6 +55,24 @@ bool tc_plan(const cpz_model* m, TcD& T, std::string& why) {
     ++found;
   }
   if (found != 9) { why = "plan"; return false; }
+  {  // face-diffusivity mode and folded constants (see side_column)
+    const RhsC& rc = M.rc;
+    const bool mpp = (M.flags & F_MPP) || M.variant == RHS_INFER;
+    const bool ca = (M.flags & F_CA) != 0;
+    T.side_mode = SIDE_NONE;
+    if (mpp) T.side_mode = (M.variant == RHS_INFER && ca) ? ((M.flags & F_CA_LITERAL_U) ? SIDE_MPP_CA_U : SIDE_MPP_CA_T) : SIDE_MPP;
+    else if (ca) T.side_mode = SIDE_CA_ONLY;
+    const double Nf = rc.Nf, L2E = 1.4426950408889634;
+    SideC& C = T.sc;
+    C.e = M.variant == RHS_TRAIN ? (float)(rc.eps / Nf) : 0.f;
+    C.su2 = (float)((double)rc.sig_u * rc.sig_u); C.sv2 = (float)((double)rc.sig_v * rc.sig_v);
+    C.k1 = (float)(2.0 * rc.inv_dRi * (rc.BzC / Nf) * L2E);
+    C.k2 = (float)(2.0 * rc.inv_dRi * rc.Ric * L2E);
+    C.a0 = (float)(Nf * rc.c[0] * rc.nu0); C.a1 = (float)(Nf * rc.c[0] * rc.nu_m);
+    C.b0 = (float)(Nf * rc.c[1] * rc.nu0); C.b1 = (float)(Nf * rc.c[1] * rc.nu_m);
+    C.t0 = (float)(Nf * rc.c[2] * rc.inv_Pr * rc.nu0); C.t1 = (float)(Nf * rc.c[2] * rc.inv_Pr * rc.nu_m);
+    C.kap = (float)(Nf * rc.c[2] * rc.kappa);
+  }
   const TcSmem L = tc_smem_layout(T, m->tab.n_stages);
   if ((size_t)L.total > m->ctx->smem_optin) { why = "shared memory"; return false; }
   return true;
@@ -67,18 +87,45 @@ std::string tc_describe(const cpz_model* m) {
   const TcSmem L = tc_smem_layout(T, m->tab.n_stages);
   snprintf(line, sizeof(line),
            "forward kernel: tcgen05 3xTF32 (weights in TMEM; %d column groups x %d columns, %d threads; layer-1 rows %d+%d, "
-           "layer-2 K windows %d/%d/%d x%d steps, layer-3 K windows %d/%d/%d x%d steps; MMAs per RHS and group %d; smem %d B)\n",
-           TC_NG, TC_GN, TC_NT, 3 * T.h1 - T.n1b, T.n1b, T.k2_start[0], T.k2_start[1], T.k2_start[2], T.k2_steps, T.k3_start[0],
-           T.k3_start[1], T.k3_start[2], T.k3_steps, 36 * (T.n1b > 0 ? 2 : 1) + 9 * T.k2_steps + 9 * T.k3_steps, L.total);
+           "layer-2 %d K steps, layer-3 %d K steps; MMAs per RHS and group %d; smem %d B)\n",
+           TC_NG, TC_GN, TC_NT, 3 * T.h1 - T.n1b, T.n1b, TC_K2S, T.k3_steps,
+           36 * (T.n1b > 0 ? 2 : 1) + 9 * TC_K2S + 9 * T.k3_steps, L.total);
   return line;
 }
 
-template <int ACT>
+template <int ACT, int K3S>
 static int launch_tc_t(cpz_model* m, const TcD& T, const SolveArgs& a, const TcArgs& ta) {
   const TcSmem L = tc_smem_layout(T, m->tab.n_stages);
-  auto kern = solve_tc_kernel<ACT>;
+  auto kern = solve_tc_kernel<ACT, K3S>;
   CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
   const int n_tiles = (a.ncol + TC_CT - 1) / TC_CT;
+  if (getenv("CPZ_TC_PROF") != nullptr && !a.rhs_only) {  // debug: per-phase cycle counters of CTA 0
+    auto pk = solve_tc_kernel<ACT, K3S, true>;
+    CPZ_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    SolveArgs ap = a;
+    unsigned long long* dcnt = nullptr;
+    CPZ_CUDA(cudaMalloc(&dcnt, 224 * sizeof(unsigned long long)));
+    CPZ_CUDA(cudaMemsetAsync(dcnt, 0, 224 * sizeof(unsigned long long), m->ctx->stream));
+    ap.prof = dcnt;
+    pk<<<n_tiles, TC_NT, L.total, m->ctx->stream>>>(m->fwd.M, T, m->tab, m->tm, ap, ta);
+    unsigned long long hc[32 + 192];
+    CPZ_CUDA(cudaMemcpyAsync(hc, dcnt, sizeof(hc), cudaMemcpyDeviceToHost, m->ctx->stream));
+    CPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    cudaFree(dcnt);
+    const double nr = (double)m->tm.n_steps * m->tm.n_substeps * m->tab.n_stages;
+    double tot = 0;
+    for (int i = 0; i < 8; ++i) tot += hc[i] / nr;
+    fprintf(stderr, "[cpz tc prof] warp 0 E1 detail: tmem ld %.0f | act+stores %.0f | fences %.0f | bar2 wait %.0f\n", hc[12] / nr, hc[13] / nr, hc[14] / nr, hc[2] / nr);
+    fprintf(stderr, "[cpz tc prof] cycles per RHS (warp 0): bar1 %.0f | wait L1 %.0f | E1+bar %.0f | wait L2 %.0f | E2+bar %.0f | wait L3 %.0f | "
+            "E3+stencil %.0f | RK+writeX %.0f | total %.0f || quadrant-3 warp: issue L1 %.0f faces %.0f wait L1 %.0f E1 x2 %.0f\n",
+            hc[0] / nr, hc[1] / nr, hc[2] / nr, hc[3] / nr, hc[4] / nr, hc[5] / nr, hc[6] / nr, hc[7] / nr, tot, hc[8] / nr, hc[9] / nr,
+            hc[10] / nr, hc[11] / nr);
+    fprintf(stderr, "[cpz tc prof] RHS start clocks, group0 (delta to previous) / group1 - group0:");
+    for (int i = 1; i < 96; i += 5) fprintf(stderr, " %lld/%lld", (long long)(hc[32 + 2 * i] - hc[32 + 2 * i - 2]), (long long)(hc[33 + 2 * i] - hc[32 + 2 * i]));
+    fprintf(stderr, "\n");
+    m->ctx->launches++;
+    return CPZ_OK;
+  }
   kern<<<n_tiles, TC_NT, L.total, m->ctx->stream>>>(m->fwd.M, T, m->tab, m->tm, a, ta);
   CPZ_CUDA(cudaGetLastError());
   m->ctx->launches++;
@@ -101,10 +148,12 @@ int launch_solve_tc(cpz_model* m, const SolveArgs& a) {
   tc_image_kernel<<<(int)((need + 255) / 256), 256, 0, m->ctx->stream>>>(T, a.theta, m->b_wimg.p);
   CPZ_CUDA(cudaGetLastError());
   m->ctx->launches++;
-  TcArgs ta{m->b_wimg.p};
-  if (T.act1 == T.act2 && T.act1 == ACT_MISH) return launch_tc_t<ACT_MISH>(m, T, a, ta);
-  if (T.act1 == T.act2 && T.act1 == ACT_RELU) return launch_tc_t<ACT_RELU>(m, T, a, ta);
-  return launch_tc_t<-1>(m, T, a, ta);
+  const char* stg = getenv("CPZ_TC_STAGGER");
+  TcArgs ta{m->b_wimg.p, stg ? atoi(stg) : 1600};
+  const bool k3 = T.k3_steps == 3;
+  if (T.act1 == T.act2 && T.act1 == ACT_MISH) return k3 ? launch_tc_t<ACT_MISH, 3>(m, T, a, ta) : launch_tc_t<ACT_MISH, 4>(m, T, a, ta);
+  if (T.act1 == T.act2 && T.act1 == ACT_RELU) return k3 ? launch_tc_t<ACT_RELU, 3>(m, T, a, ta) : launch_tc_t<ACT_RELU, 4>(m, T, a, ta);
+  return k3 ? launch_tc_t<-1, 3>(m, T, a, ta) : launch_tc_t<-1, 4>(m, T, a, ta);
 }
 
 }  // namespace cpz

@@ -26,6 +26,8 @@
 //     (Nz = 32) resp. output row, 8 columns per thread in registers. Quadrant 3 owns the 22 extra layer-1 rows and
 //     computes the Richardson-number diffusivities and Coriolis terms while layer 1 is in the tensor pipe.
 #pragma once
+#include <type_traits>
+
 #include "cpz_solve.cuh"
 
 namespace cpz {
@@ -34,22 +36,41 @@ constexpr int TC_NG = 2;     // column groups per CTA
 constexpr int TC_GN = 16;    // columns per group = MMA N
 constexpr int TC_CT = TC_NG * TC_GN;
 constexpr int TC_NT = 512;   // 2 groups x 8 warps
-constexpr uint32_t TC_SBO = 128;
-constexpr uint32_t TC_LBO = (TC_GN / 8) * 128 + 16;  // 272
-constexpr int TC_WCOLS = 384;                         // TMEM columns holding weights
-constexpr int TC_SIDE_ARRAYS = 8;                     // Du, Dv, DT, cor_u, cor_v, Xu, Xv, XT
+constexpr uint32_t TC_SBO = 128;                      // bytes between column octets of a B operand
+constexpr uint32_t TC_LBO = (TC_GN / 8) * 128 + 16;  // 272: bytes between 4-row K chunks (16 B pad: conflict-free row stores)
+constexpr int TC_K2S = 7;            // K steps of a layer-2 chain (covers h1 <= 53 plus window alignment)
+constexpr int TC_WCOLS = 384;        // TMEM columns holding weights
+constexpr int TC_SIDE_ARRAYS = 6;    // Du, Dv, DT (x Nz, face lane+1), Xu, Xv, XT (full-precision stage input)
+
+// constants of the face-diffusivity computation, folded on the host
+struct SideC {
+  float e;          // eps / Nz (train variant) or 0
+  float su2, sv2;   // sigma_u^2, sigma_v^2
+  float k1, k2;     // exp2 argument: k1 * (dT+e)/den - k2, with the factors 2/dRi, BzC/Nz and log2(e) folded in
+  float a0, a1;     // Nz*c_u*nu0, Nz*c_u*nu_m
+  float b0, b1;     // v
+  float t0, t1;     // T (includes 1/Pr)
+  float kap;        // Nz*c_T*kappa
+};
 
 struct TcD {
   int h1, h2, nout;      // per-net layer widths (identical for the three nets)
   int act1, act2, act3;
   int n1b;               // layer-1 rows in block 1 (= 3*h1 - 128, <= 32)
-  int k2_start[3], k2_steps;  // K windows (rows of H1) of the three layer-2 MMAs
-  int k3_start[3], k3_steps;  // K windows (rows of H2) of the three layer-3 MMAs
-  int h1_rows, h2_rows;       // allocated rows (multiples of 4; rows past the real ones stay zero)
+  int k2_start[3], k3_start[3];  // first operand row (multiple of 4) of net q's K window in H1 / H2
+  int k3_steps;                  // K steps (of 8 rows) of a layer-3 chain (3 or 4); layer 2 always runs TC_K2S
+  int h1_rows, h2_rows;       // allocated operand rows (rows past the real ones stay zero)
   int c_a2hi, c_a2lo, c_a3hi, c_a3lo;  // TMEM columns of the layer-2/3 stacks
   int w_off[3][3], b_off[3][3];        // theta offsets [net][layer]
+  int side_mode;
+  SideC sc;
 };
 
+// B operand planes (activations) in shared memory: canonical K-major layout without swizzle (verified by the address
+// probe in tools/micro/umma_test.cu):  byte(n, k) = (n/8)*SBO + (n%8)*16 + (k/4)*LBO + (k%4)*4.
+// A thread owns one row k and 8 columns: 8 scalar stores 16 B apart; the 32 rows of a warp hit 32 distinct banks.
+// (An MN-major operand would allow 16-byte stores, but kind::tf32 with an un-swizzled MN-major B returned zeros in the
+// probe, so it is not used.)
 struct TcSmem {  // byte offsets
   int xh, xl, h1h, h1l, h2h, h2l, side, bc, grp_bytes;  // per group (relative to the group's base)
   int ks, misc, total;
@@ -75,7 +96,7 @@ __host__ __device__ inline TcSmem tc_smem_layout(const TcD& T, int n_stages) {
 __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {  // K-major, no swizzle, LBO/SBO of the B layout
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(TC_LBO >> 4) << 16) | ((uint64_t)(TC_SBO >> 4) << 32) | (1ull << 46);
 }
-__host__ __device__ constexpr uint32_t tc_idesc(int M, int N) {  // kind::tf32, FP32 accumulate, A and B K-major
+__host__ __device__ constexpr uint32_t tc_idesc(int M, int N) {  // kind::tf32, FP32 accumulate, A (TMEM) and B K-major
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void tc_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -109,11 +130,8 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
                : "memory");
 }
 __device__ __forceinline__ void bar_sync_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ float tf32_hi(float x) {
-  uint32_t h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  return __uint_as_float(h);
-}
+// round to nearest tf32 (ties away from zero, as cvt.rna.tf32.f32, without its Inf/NaN guard: 2 ALU instructions, not 4)
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -124,20 +142,42 @@ __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
   return v;
 }
 
-// split 8 values and store them as one row (k) of a B operand: columns 8h..8h+7 of the group
-__device__ __forceinline__ void store_row_hilo(uint32_t hi_base, uint32_t lo_base, const float* v) {
+// fast activations on raw MUFU.EX2 / MUFU.RCP (ex2.approx.ftz, rcp.approx.ftz: no range fix-ups; arguments are clamped)
+__device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+template <int ACT>
+__device__ __forceinline__ float tc_act(int act_rt, float x) {
+  constexpr float L2E = 1.4426950408889634f;
+  if constexpr (ACT == ACT_MISH) {  // x*tanh(softplus(x)) = x*n/(n+2), n = e^x(e^x+2)      (NNlib 0.7.20 mish)
+    const float e = ex2_fast(fminf(x, 20.f) * L2E);
+    const float n = e * (e + 2.f);
+    return x * n * rcp_fast(n + 2.f);
+  } else if constexpr (ACT == ACT_RELU) {
+    return fmaxf(x, 0.f);
+  } else {
+    return act_fwd(act_rt, x);
+  }
+}
+
+// split 8 values (columns 8h..8h+7 of one operand row) into tf32 hi + residual lo and store them (16 B apart)
+__device__ __forceinline__ void store_row_hilo(uint32_t hi_addr, uint32_t lo_addr, const float* v) {
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const float hi = tf32_hi(v[r]);
-    sts_f32(hi_base + 16 * r, hi);
-    sts_f32(lo_base + 16 * r, v[r] - hi);
+    sts_f32(hi_addr + 16 * r, hi);
+    sts_f32(lo_addr + 16 * r, v[r] - hi);
   }
 }
 // byte offset of (row k, column octet h) inside a B operand plane
 __device__ __forceinline__ uint32_t tc_row_off(int k, int h) { return (uint32_t)(k >> 2) * TC_LBO + (uint32_t)(k & 3) * 4 + (uint32_t)h * TC_SBO; }
+__device__ __forceinline__ void lds8(uint32_t a0, uint32_t a1, float* v) {
+  const float4 p = lds_v4(a0), q = lds_v4(a1);
+  v[0] = p.x; v[1] = p.y; v[2] = p.z; v[3] = p.w; v[4] = q.x; v[5] = q.y; v[6] = q.z; v[7] = q.w;
+}
 
 struct TcArgs {
   const float* wimg;  // [TC_WCOLS][128] TMEM image of the weights (hi/lo split), built by tc_image_kernel
+  int stagger_ns;     // start delay of the second column group
 };
 
 // ---- weight image ---------------------------------------------------------------------------------------------
@@ -159,31 +199,48 @@ __global__ void tc_image_kernel(const __grid_constant__ TcD T, const float* __re
     const int k = lo ? c - 288 : c - 192;
     const int f = 128 + (l - 96);
     if (f < 3 * T.h1) { const int q = f / T.h1, o = f - q * T.h1; w = theta[T.w_off[q][0] + k * T.h1 + o]; }
-  } else {  // layer 2 / 3 stacks
+  } else {  // layer 2 / 3 stacks: lane 32q+o = output o of net q, column = input index inside the net's K window
     const int q = l >> 5, o = l & 31;
-    const int K2 = 8 * T.k2_steps, K3 = 8 * T.k3_steps;
-    if (c >= T.c_a2hi && c < T.c_a2hi + K2) {
-      const int f = T.k2_start[q] + (c - T.c_a2hi) - T.h1 * q;
-      if (o < T.h2 && f >= 0 && f < T.h1) w = theta[T.w_off[q][1] + f * T.h2 + o];
-    } else if (c >= T.c_a2lo && c < T.c_a2lo + K2) {
-      lo = true;
-      const int f = T.k2_start[q] + (c - T.c_a2lo) - T.h1 * q;
-      if (o < T.h2 && f >= 0 && f < T.h1) w = theta[T.w_off[q][1] + f * T.h2 + o];
-    } else if (c >= T.c_a3hi && c < T.c_a3hi + K3) {
-      const int f = T.k3_start[q] + (c - T.c_a3hi) - T.h2 * q;
-      if (o < T.nout && f >= 0 && f < T.h2) w = theta[T.w_off[q][2] + f * T.nout + o];
-    } else if (c >= T.c_a3lo && c < T.c_a3lo + K3) {
-      lo = true;
-      const int f = T.k3_start[q] + (c - T.c_a3lo) - T.h2 * q;
-      if (o < T.nout && f >= 0 && f < T.h2) w = theta[T.w_off[q][2] + f * T.nout + o];
-    }
+    const int K2 = 8 * TC_K2S, K3 = 8 * T.k3_steps;
+    int f = -1, layer = 0;
+    if (c >= T.c_a2hi && c < T.c_a2hi + K2) { f = c - T.c_a2hi; layer = 1; }
+    else if (c >= T.c_a2lo && c < T.c_a2lo + K2) { f = c - T.c_a2lo; layer = 1; lo = true; }
+    else if (c >= T.c_a3hi && c < T.c_a3hi + K3) { f = c - T.c_a3hi; layer = 2; }
+    else if (c >= T.c_a3lo && c < T.c_a3lo + K3) { f = c - T.c_a3lo; layer = 2; lo = true; }
+    if (layer == 1) f += T.k2_start[q] - T.h1 * q;  // operand row -> input index of net q
+    if (layer == 2) f += T.k3_start[q] - T.h2 * q;
+    if (layer == 1 && o < T.h2 && f >= 0 && f < T.h1) w = theta[T.w_off[q][1] + f * T.h2 + o];
+    if (layer == 2 && o < T.nout && f >= 0 && f < T.h2) w = theta[T.w_off[q][2] + f * T.nout + o];
   }
   const float hi = tf32_hi(w);
   wimg[idx] = lo ? (w - hi) : hi;
 }
 
+// diffusivity modes of the face computation (hoisted out of the column loop)
+enum { SIDE_NONE = 0, SIDE_MPP = 1, SIDE_MPP_CA_T = 2, SIDE_MPP_CA_U = 3, SIDE_CA_ONLY = 4 };
+
+// Nz * c_q * nu_q at face lane+1 from the level differences du, dv, dT (lane+1 minus lane) of one column.
+// Ri = H g alpha sigma_T dT/dz / ((sigma_u du/dz)^2 + (sigma_v dv/dz)^2)      (NDE_training.jl:46-52,115-119)
+// nu = nu0 + nu_m (1 - tanh((Ri - Ric)/dRi))/2 = nu0 + nu_m / (1 + exp(2 (Ri - Ric)/dRi))   (NDE_training.jl:54,125)
+template <int MODE>
+__device__ __forceinline__ void side_column(const SideC& C, float du, float dv, float dT, float& Du, float& Dv, float& DT) {
+  if constexpr (MODE == SIDE_NONE) {
+    Du = 0.f; Dv = 0.f; DT = 0.f;
+  } else if constexpr (MODE == SIDE_CA_ONLY) {  // c_T*kappa*min(0, dT/dz): NDE_training.jl:140-143
+    Du = 0.f; Dv = 0.f; DT = dT < 0.f ? C.kap : 0.f;
+  } else {
+    const float a = du + C.e, b = dv + C.e, c = dT + C.e;
+    const float den = fmaf(C.sv2 * b, b, C.su2 * a * a);
+    const float y = fmaf(C.k1 * c, rcp_fast(den), -C.k2);
+    const float w = rcp_fast(1.f + ex2_fast(fminf(y, 126.f)));
+    Du = fmaf(C.a1, w, C.a0); Dv = fmaf(C.b1, w, C.b0); DT = fmaf(C.t1, w, C.t0);
+    if constexpr (MODE == SIDE_MPP_CA_T) DT = dT > 0.f ? DT : C.kap;   // training_postprocessing.jl:118-124
+    if constexpr (MODE == SIDE_MPP_CA_U) DT = du > 0.f ? DT : C.kap;
+  }
+}
+
 // ---- the solve kernel ---------------------------------------------------------------------------------------------
-template <int ACT>  // hidden activation when both hidden layers share it, -1 = read T.act1/T.act2 at run time
+template <int ACT, int K3S, bool PROF = false>  // ACT: shared hidden activation (-1: T.act1/T.act2 at run time); K3S: layer-3 K steps
 __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constant__ ModelD M, const __grid_constant__ TcD T,
                                                             const __grid_constant__ TableauD tab, const TimeD tm,
                                                             const SolveArgs a, const TcArgs ta) {
@@ -195,7 +252,6 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
   const uint32_t gbase = sbase + g * L.grp_bytes;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_tc + L.misc) + g;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_tc + L.misc + 64);
-  const int N = 32;
   const int tile = blockIdx.x, col0 = tile * TC_CT;
   const int cg0 = TC_GN * g + 8 * h;  // first of this thread's 8 columns inside the tile
 
@@ -237,240 +293,238 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
     if (qd < 3 && lane < T.h2) b2 = __ldg(a.theta + T.b_off[qd][1] + lane);
     if (qd < 3 && lane < T.nout) b3 = __ldg(a.theta + T.b_off[qd][2] + lane);
   }
-  // boundary fluxes -> bc[q*2+tb][16] and diurnal amplitudes -> bc[6][16] of the group
-  float* bcs_g = reinterpret_cast<float*>(smem_tc + g * L.grp_bytes + L.bc);
-  if (wg == 0 && lane < TC_GN) {
-    const int col = min(col0 + TC_GN * g + lane, a.ncol - 1);
-    float raw[6], eff[6];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) raw[j] = __ldg(a.bcs + (size_t)col * 6 + j);
-    bc_effective(M, raw, eff);
-#pragma unroll
-    for (int j = 0; j < 6; ++j) bcs_g[j * TC_GN + lane] = eff[j];
-    bcs_g[6 * TC_GN + lane] = a.Q != nullptr ? __ldg(a.Q + col) : 0.f;
-  }
-  // state: x[r] = field qd, level lane, column cg0 + r
-  float x[8], X[8];
+  // state x[r] = field qd, level lane, column cg0 + r; bnd[r] = effective boundary flux of field qd: bottom (lane 0) /
+  // top (lane 31) of column r; Qd[r] = diurnal amplitude (only read by lane 31 of the T warps)
+  float x[8], X[8], bnd[8];
+  const bool diurnal = (M.flags & F_DIURNAL) != 0;
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const int col = min(col0 + cg0 + r, a.ncol - 1);
     x[r] = qd < 3 ? __ldg(a.x0 + (size_t)col * 96 + 32 * qd + lane) : 0.f;
     X[r] = x[r];
+    float raw[6], eff[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) raw[j] = __ldg(a.bcs + (size_t)col * 6 + j);
+    bc_effective(M, raw, eff);
+    bnd[r] = 0.f;
+    if (qd < 3) bnd[r] = lane == 0 ? eff[2 * qd] : eff[2 * qd + 1];
+    if (diurnal && qd == 2 && lane == 31) reinterpret_cast<float*>(smem_tc + g * L.grp_bytes + L.bc)[8 * h + r] = a.Q != nullptr ? __ldg(a.Q + col) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
 
-  // shared-memory addresses of this thread
-  const uint32_t x_off = tc_row_off(32 * qd + lane, h);             // X row (qd < 3) / H1 row of block 0
-  const uint32_t h1b_off = tc_row_off(128 + lane, h);               // H1 row of block 1 (qd == 3)
-  const uint32_t h2_off = tc_row_off(T.h2 * qd + lane, h);          // H2 row (qd < 3, lane < h2)
-  const uint32_t side = gbase + L.side;                             // [array][chunk 0..3][lane] float4
-  auto side_addr = [&](int arr, int chunk) { return side + (uint32_t)(((arr * 4 + chunk) * 32 + lane) * 16); };
+  // shared-memory addresses of this thread (operand planes: [column block][row][4])
+  const uint32_t xb = tc_row_off(32 * qd + lane, h);            // X row (qd < 3) and H1 row of block 0
+  const uint32_t h1a = xb;
+  const uint32_t h1b = tc_row_off(128 + lane, h);               // H1 row of block 1 (qd == 3)
+  const uint32_t h2a = tc_row_off(T.h2 * qd + lane, h);         // H2 row (qd < 3, lane < h2)
+  const uint32_t side = gbase + L.side;                                                         // [array][column block][lane] float4
+  auto side_addr = [&](int arr, int blk) { return side + (uint32_t)(((arr * 4 + blk) * 32 + lane) * 16); };
   const int tq = ((g * 2 + h) * 3 + qd) * 32 + lane;                // index among the stencil threads (qd < 3)
   const uint32_t ks_base = sbase + L.ks + (uint32_t)tq * 32;
   const uint32_t ks_stride = (uint32_t)(TC_NG * 2 * 3 * 32) * 32;
   const uint32_t dg = tb + 384 + 64 * g;                            // accumulator columns of this group
   const uint32_t id16 = tc_idesc(128, TC_GN);
-  const bool issuer = (wg == 7);
   uint32_t parity = 0;
   const int bar_id = 1 + g;
-  const bool mpp = (M.flags & F_MPP) || M.variant == RHS_INFER;
-  const bool ca = (M.flags & F_CA) != 0;
-  const float eps = M.variant == RHS_TRAIN ? M.rc.eps : 0.f;
-  const float Nf = M.rc.Nf;
-  const int act1 = ACT >= 0 ? ACT : T.act1, act2 = ACT >= 0 ? ACT : T.act2;
+  const int act1 = T.act1, act2 = T.act2;
+  // per-thread stencil constants: dx = cs * X_other + cm - Aq * (F_up - F_down)
+  const float Aq = qd < 3 ? M.rc.A[qd] * M.rc.Nf : 0.f;
+  const float cs = qd == 0 ? M.rc.cor_u_s : (qd == 1 ? -M.rc.cor_v_s : 0.f);
+  const float cm = qd == 0 ? M.rc.cor_u_m : (qd == 1 ? -M.rc.cor_v_m : 0.f);
+  const int side_mode = T.side_mode;
 
-  auto write_X = [&]() {  // stage input -> B operand (hi/lo) + full-precision copy for quadrant 3
+  auto write_X = [&]() {  // stage input -> B operand (hi/lo) + full-precision copy
     if (qd < 3) {
-      store_row_hilo(gbase + L.xh + x_off, gbase + L.xl + x_off, X);
-      sts_v4(side_addr(5 + qd, 2 * h), X[0], X[1], X[2], X[3]);
-      sts_v4(side_addr(5 + qd, 2 * h + 1), X[4], X[5], X[6], X[7]);
+      store_row_hilo(gbase + L.xh + xb, gbase + L.xl + xb, X);
+      sts_v4(side_addr(3 + qd, 2 * h), X[0], X[1], X[2], X[3]);
+      sts_v4(side_addr(3 + qd, 2 * h + 1), X[4], X[5], X[6], X[7]);
     }
+  };
+
+  // PROF: cycle counters of CTA 0 — slots 0..7 warp 0 (a stencil warp): bar1, wait1, E1+bar2, wait2, E2+bar3, wait3, E3+stencil, RK+write;
+  // slots 8..11 warp 7 (quadrant 3 of group 0): issue L1, face diffusivities, wait L1, E1 (two blocks)
+  long long pt = 0;
+  int trace_n = 0;
+  auto tick = [&](int slot) {
+    if constexpr (PROF) {
+      if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 7)) {
+        const long long now = clock64();
+        if (slot >= 0 && ((warp == 0) == (slot < 8 || slot >= 12))) atomicAdd(a.prof + slot, (unsigned long long)(now - pt));
+        pt = now;
+      }
+    }
+  };
+
+  // MMA chains: D (+)= Whi*Xlo + Wlo*Xhi + Whi*Xhi over `steps` K steps of 8 rows; a?? = TMEM columns, b? = descriptors
+  auto chain = [&](uint32_t d, uint32_t ahi, uint32_t alo, uint64_t bh, uint64_t bl, auto STEPS) {
+    constexpr int NS = decltype(STEPS)::value;
+    constexpr uint64_t kstep = (2 * TC_LBO) >> 4;  // one K step = two 4-row chunks
+#pragma unroll
+    for (int s = 0; s < NS; ++s) tc_mma_ts(d, ahi + 8 * s, bl + s * kstep, id16, s > 0);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) tc_mma_ts(d, alo + 8 * s, bh + s * kstep, id16, 1);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) tc_mma_ts(d, ahi + 8 * s, bh + s * kstep, id16, 1);
   };
 
   // one RHS evaluation at stage input X (registers + shared memory); returns the tendencies in dx (qd < 3)
   auto rhs_eval = [&](float t_stage, float* dx) {
     // (1) operands visible to the async proxy, previous accumulator reads done
+    tick(-1);
     fence_proxy_async();
     tc_fence_before();
     bar_sync_named(bar_id, 256);
-    if (issuer) {
+    tick(0);
+    if constexpr (PROF) {  // trace: clock at the start of the first 96 RHS evaluations of both groups (CTA 0)
+      if (blockIdx.x == 0 && wg == 0 && lane == 0 && trace_n < 96) { a.prof[32 + 2 * trace_n + g] = (unsigned long long)clock64(); ++trace_n; }
+    }
+    if (wg == 7) {  // layer 1: rows 0..127 then the quadrant-3 block
       tc_fence_after();
       if (elect_one()) {
         const uint64_t bh = tc_desc(gbase + L.xh), bl = tc_desc(gbase + L.xl);
-        const uint64_t kstep = (2 * TC_LBO) >> 4;
-#pragma unroll 1
-        for (int blk = 0; blk < 2; ++blk) {
-          if (blk == 1 && T.n1b == 0) break;
-          const uint32_t ahi = tb + 192 * blk, alo = ahi + 96, d = dg + 16 * blk;
+        chain(dg, tb, tb + 96, bh, bl, std::integral_constant<int, 12>{});
+        if (T.n1b > 0) chain(dg + 16, tb + 192, tb + 288, bh, bl, std::integral_constant<int, 12>{});
+        tc_commit(mbar);
+      }
+      __syncwarp();
+      tick(8);
+    }
+    {
+      // face diffusivities (x Nz) at face lane+1, two columns per thread (columns 8h + 2qd, +1), while layer 1 runs
+      const uint32_t off = (uint32_t)(8 * (qd & 1));
+      const int blk = 2 * h + (qd >> 1);
+      float2 u, v, Tt, Du, Dv, DT;
+      asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(u.x), "=f"(u.y) : "r"(side_addr(3, blk) + off) : "memory");
+      asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(side_addr(4, blk) + off) : "memory");
+      asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(Tt.x), "=f"(Tt.y) : "r"(side_addr(5, blk) + off) : "memory");
+      u.x = __shfl_down_sync(0xffffffffu, u.x, 1) - u.x; u.y = __shfl_down_sync(0xffffffffu, u.y, 1) - u.y;
+      v.x = __shfl_down_sync(0xffffffffu, v.x, 1) - v.x; v.y = __shfl_down_sync(0xffffffffu, v.y, 1) - v.y;
+      Tt.x = __shfl_down_sync(0xffffffffu, Tt.x, 1) - Tt.x; Tt.y = __shfl_down_sync(0xffffffffu, Tt.y, 1) - Tt.y;
+      switch (side_mode) {
+#define CPZ_SIDE_CASE(MODE)                                             \
+  case MODE:                                                            \
+    side_column<MODE>(T.sc, u.x, v.x, Tt.x, Du.x, Dv.x, DT.x);           \
+    side_column<MODE>(T.sc, u.y, v.y, Tt.y, Du.y, Dv.y, DT.y);           \
+    break;
+        CPZ_SIDE_CASE(SIDE_MPP)
+        CPZ_SIDE_CASE(SIDE_MPP_CA_T)
+        CPZ_SIDE_CASE(SIDE_MPP_CA_U)
+        CPZ_SIDE_CASE(SIDE_CA_ONLY)
+        default:
+          CPZ_SIDE_CASE(SIDE_NONE)
+#undef CPZ_SIDE_CASE
+      }
+      asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(side_addr(0, blk) + off), "f"(Du.x), "f"(Du.y) : "memory");
+      asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(side_addr(1, blk) + off), "f"(Dv.x), "f"(Dv.y) : "memory");
+      asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(side_addr(2, blk) + off), "f"(DT.x), "f"(DT.y) : "memory");
+      if (wg == 7) tick(9);
+    }
+    float Xo[8];  // the other horizontal velocity at this level (Coriolis), read while layer 1 runs
 #pragma unroll
-          for (int s = 0; s < 12; ++s) tc_mma_ts(d, ahi + 8 * s, bl + s * kstep, id16, s > 0);  // Whi * Xlo
+    for (int r = 0; r < 8; ++r) Xo[r] = 0.f;
+    if (qd < 2) lds8(side_addr(3 + (1 - qd), 2 * h), side_addr(3 + (1 - qd), 2 * h + 1), Xo);
+    if (diurnal && qd == 2 && lane == 31) {
+      const float* Qs = reinterpret_cast<const float*>(smem_tc + g * L.grp_bytes + L.bc) + 8 * h;
 #pragma unroll
-          for (int s = 0; s < 12; ++s) tc_mma_ts(d, alo + 8 * s, bh + s * kstep, id16, 1);      // Wlo * Xhi
+      for (int r = 0; r < 8; ++r) bnd[r] = diurnal_top_eff(M, Qs[r], t_stage);
+    }
+    // ---- layer 1 epilogue ----
+    mbar_wait(mbar, parity); parity ^= 1u;
+    tc_fence_after();
+    tick(1);
+    if (wg == 7) tick(10);
+    {
+      float v[8];
+      tmem_ld8(dg + ((uint32_t)(32 * qd) << 16) + 8 * h, v);
+      tick(12);
 #pragma unroll
-          for (int s = 0; s < 12; ++s) tc_mma_ts(d, ahi + 8 * s, bh + s * kstep, id16, 1);      // Whi * Xhi
+      for (int r = 0; r < 8; ++r) v[r] = tc_act<ACT>(act1, v[r] + b1a);
+      store_row_hilo(gbase + L.h1h + h1a, gbase + L.h1l + h1a, v);
+      tick(13);
+      if (qd == 3 && T.n1b > 0) {
+        tmem_ld8(dg + ((uint32_t)96 << 16) + 16 + 8 * h, v);
+        if (lane < T.n1b) {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) v[r] = tc_act<ACT>(act1, v[r] + b1b);
+          store_row_hilo(gbase + L.h1h + h1b, gbase + L.h1l + h1b, v);
+        }
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    tick(14);
+    if (wg == 7) tick(11);
+    bar_sync_named(bar_id, 256);
+    tick(2);
+    // ---- layer 2: net q reads rows h1*q.. of H1, result in lanes 32q.. of accumulator block q ----
+    if (wg == 3) {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const uint64_t bh = tc_desc(gbase + L.h1h + (uint32_t)(T.k2_start[q] >> 2) * TC_LBO);
+          const uint64_t bl = tc_desc(gbase + L.h1l + (uint32_t)(T.k2_start[q] >> 2) * TC_LBO);
+          chain(dg + 16 * q, tb + T.c_a2hi, tb + T.c_a2lo, bh, bl, std::integral_constant<int, TC_K2S>{});
         }
         tc_commit(mbar);
       }
       __syncwarp();
     }
     if (qd == 3) {
-      // diffusivities at face lane+1 and Coriolis terms at level lane, for this thread's 8 columns
-      float u[8], v[8], Tt[8];
-      {
-        float4 p;
-        p = lds_v4(side_addr(5, 2 * h)); u[0] = p.x; u[1] = p.y; u[2] = p.z; u[3] = p.w;
-        p = lds_v4(side_addr(5, 2 * h + 1)); u[4] = p.x; u[5] = p.y; u[6] = p.z; u[7] = p.w;
-        p = lds_v4(side_addr(6, 2 * h)); v[0] = p.x; v[1] = p.y; v[2] = p.z; v[3] = p.w;
-        p = lds_v4(side_addr(6, 2 * h + 1)); v[4] = p.x; v[5] = p.y; v[6] = p.z; v[7] = p.w;
-        p = lds_v4(side_addr(7, 2 * h)); Tt[0] = p.x; Tt[1] = p.y; Tt[2] = p.z; Tt[3] = p.w;
-        p = lds_v4(side_addr(7, 2 * h + 1)); Tt[4] = p.x; Tt[5] = p.y; Tt[6] = p.z; Tt[7] = p.w;
-      }
-      float Du[8], Dv[8], DT[8], cu[8], cv[8];
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const float Gu = Nf * (__shfl_down_sync(0xffffffffu, u[r], 1) - u[r]);
-        const float Gv = Nf * (__shfl_down_sync(0xffffffffu, v[r], 1) - v[r]);
-        const float GT = Nf * (__shfl_down_sync(0xffffffffu, Tt[r], 1) - Tt[r]);
-        float nu = 0.f, nuT = 0.f;
-        if (mpp) {
-          const float su = M.rc.sig_u * (Gu + eps), sv = M.rc.sig_v * (Gv + eps);
-          const float Ri = __fdividef(M.rc.BzC * (GT + eps), su * su + sv * sv);
-          nu = nu_of_ri(M, Ri);
-          nuT = nu * M.rc.inv_Pr;
-          if (M.variant == RHS_INFER && ca) {
-            const float test = (M.flags & F_CA_LITERAL_U) ? Gu : GT;
-            nuT = test > 0.f ? nuT : M.rc.kappa;
-          }
-        } else if (ca) {
-          nuT = GT < 0.f ? M.rc.kappa : 0.f;  // c2*kappa*min(0, G_T) (NDE_training.jl:140-143 with the inference kappa)
-        }
-        Du[r] = M.rc.c[0] * nu; Dv[r] = M.rc.c[1] * nu; DT[r] = M.rc.c[2] * nuT;
-        cu[r] = M.rc.cor_u_s * v[r] + M.rc.cor_u_m;
-        cv[r] = -(M.rc.cor_v_s * u[r] + M.rc.cor_v_m);
-      }
-      sts_v4(side_addr(0, 2 * h), Du[0], Du[1], Du[2], Du[3]); sts_v4(side_addr(0, 2 * h + 1), Du[4], Du[5], Du[6], Du[7]);
-      sts_v4(side_addr(1, 2 * h), Dv[0], Dv[1], Dv[2], Dv[3]); sts_v4(side_addr(1, 2 * h + 1), Dv[4], Dv[5], Dv[6], Dv[7]);
-      sts_v4(side_addr(2, 2 * h), DT[0], DT[1], DT[2], DT[3]); sts_v4(side_addr(2, 2 * h + 1), DT[4], DT[5], DT[6], DT[7]);
-      sts_v4(side_addr(3, 2 * h), cu[0], cu[1], cu[2], cu[3]); sts_v4(side_addr(3, 2 * h + 1), cu[4], cu[5], cu[6], cu[7]);
-      sts_v4(side_addr(4, 2 * h), cv[0], cv[1], cv[2], cv[3]); sts_v4(side_addr(4, 2 * h + 1), cv[4], cv[5], cv[6], cv[7]);
-      if ((M.flags & F_DIURNAL) && h == 0 && lane < TC_GN) bcs_g[5 * TC_GN + lane] = diurnal_top_eff(M, bcs_g[6 * TC_GN + lane], t_stage);
-    }
-    // ---- layer 1 epilogue ----
-    mbar_wait(mbar, parity); parity ^= 1u;
-    tc_fence_after();
-    {
-      float v[8];
-      tmem_ld8(dg + ((uint32_t)(32 * qd) << 16) + 8 * h, v);
-#pragma unroll
-      for (int r = 0; r < 8; ++r) v[r] = act_fwd(act1, v[r] + b1a);
-      store_row_hilo(gbase + L.h1h + x_off, gbase + L.h1l + x_off, v);
-      if (qd == 3 && T.n1b > 0) {
-        tmem_ld8(dg + ((uint32_t)96 << 16) + 16 + 8 * h, v);
-        if (lane < T.n1b) {
-#pragma unroll
-          for (int r = 0; r < 8; ++r) v[r] = act_fwd(act1, v[r] + b1b);
-          store_row_hilo(gbase + L.h1h + h1b_off, gbase + L.h1l + h1b_off, v);
-        }
-      }
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    bar_sync_named(bar_id, 256);
-    // ---- layer 2 ----
-    if (issuer) {
+      parity ^= 1u;  // quadrant 3 has no layer-2 / layer-3 epilogue: it skips those two waits
+    } else {
+      mbar_wait(mbar, parity); parity ^= 1u;
       tc_fence_after();
-      if (elect_one()) {
-        const uint64_t kstep = (2 * TC_LBO) >> 4;
-#pragma unroll 1
-        for (int q = 0; q < 3; ++q) {
-          const uint64_t bh = tc_desc(gbase + L.h1h + (T.k2_start[q] >> 2) * TC_LBO);
-          const uint64_t bl = tc_desc(gbase + L.h1l + (T.k2_start[q] >> 2) * TC_LBO);
-          const uint32_t d = dg + 16 * q;
-          const uint32_t ahi = tb + T.c_a2hi, alo = tb + T.c_a2lo;
-#pragma unroll 1
-          for (int s = 0; s < T.k2_steps; ++s) tc_mma_ts(d, ahi + 8 * s, bl + s * kstep, id16, s > 0);
-#pragma unroll 1
-          for (int s = 0; s < T.k2_steps; ++s) tc_mma_ts(d, alo + 8 * s, bh + s * kstep, id16, 1);
-#pragma unroll 1
-          for (int s = 0; s < T.k2_steps; ++s) tc_mma_ts(d, ahi + 8 * s, bh + s * kstep, id16, 1);
-        }
-        tc_commit(mbar);
-      }
-      __syncwarp();
-    }
-    mbar_wait(mbar, parity); parity ^= 1u;
-    tc_fence_after();
-    if (qd < 3) {
+      tick(3);
       float v[8];
       tmem_ld8(dg + ((uint32_t)(32 * qd) << 16) + 16 * qd + 8 * h, v);
       if (lane < T.h2) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) v[r] = act_fwd(act2, v[r] + b2);
-        store_row_hilo(gbase + L.h2h + h2_off, gbase + L.h2l + h2_off, v);
+        for (int r = 0; r < 8; ++r) v[r] = tc_act<ACT>(act2, v[r] + b2);
+        store_row_hilo(gbase + L.h2h + h2a, gbase + L.h2l + h2a, v);
       }
     }
     fence_proxy_async();
     tc_fence_before();
     bar_sync_named(bar_id, 256);
+    tick(4);
     // ---- layer 3 ----
-    if (issuer) {
+    if (wg == 3) {
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t kstep = (2 * TC_LBO) >> 4;
-#pragma unroll 1
+#pragma unroll
         for (int q = 0; q < 3; ++q) {
-          const uint64_t bh = tc_desc(gbase + L.h2h + (T.k3_start[q] >> 2) * TC_LBO);
-          const uint64_t bl = tc_desc(gbase + L.h2l + (T.k3_start[q] >> 2) * TC_LBO);
-          const uint32_t d = dg + 16 * q;
-          const uint32_t ahi = tb + T.c_a3hi, alo = tb + T.c_a3lo;
-#pragma unroll 1
-          for (int s = 0; s < T.k3_steps; ++s) tc_mma_ts(d, ahi + 8 * s, bl + s * kstep, id16, s > 0);
-#pragma unroll 1
-          for (int s = 0; s < T.k3_steps; ++s) tc_mma_ts(d, alo + 8 * s, bh + s * kstep, id16, 1);
-#pragma unroll 1
-          for (int s = 0; s < T.k3_steps; ++s) tc_mma_ts(d, ahi + 8 * s, bh + s * kstep, id16, 1);
+          const uint64_t bh = tc_desc(gbase + L.h2h + (uint32_t)(T.k3_start[q] >> 2) * TC_LBO);
+          const uint64_t bl = tc_desc(gbase + L.h2l + (uint32_t)(T.k3_start[q] >> 2) * TC_LBO);
+          chain(dg + 16 * q, tb + T.c_a3hi, tb + T.c_a3lo, bh, bl, std::integral_constant<int, K3S>{});
         }
         tc_commit(mbar);
       }
       __syncwarp();
     }
-    mbar_wait(mbar, parity); parity ^= 1u;
-    tc_fence_after();
-    // ---- layer 3 epilogue + stencil (Appendix A of SURVEY.md) ----
-    if (qd < 3) {
-      float nn[8];
+    if (qd == 3) {
+      parity ^= 1u;
+    } else {
+      mbar_wait(mbar, parity); parity ^= 1u;
+      tc_fence_after();
+      tick(5);
+      // ---- layer 3 epilogue + stencil: flux at face lane+1, divergence at level lane ----
+      float nn[8], D[8];
       tmem_ld8(dg + ((uint32_t)(32 * qd) << 16) + 16 * qd + 8 * h, nn);
-      float D[8], cor[8], bt[8], bb[8];
-      {
-        float4 p;
-        p = lds_v4(side_addr(qd, 2 * h)); D[0] = p.x; D[1] = p.y; D[2] = p.z; D[3] = p.w;
-        p = lds_v4(side_addr(qd, 2 * h + 1)); D[4] = p.x; D[5] = p.y; D[6] = p.z; D[7] = p.w;
-        if (qd < 2) {
-          p = lds_v4(side_addr(3 + qd, 2 * h)); cor[0] = p.x; cor[1] = p.y; cor[2] = p.z; cor[3] = p.w;
-          p = lds_v4(side_addr(3 + qd, 2 * h + 1)); cor[4] = p.x; cor[5] = p.y; cor[6] = p.z; cor[7] = p.w;
-        } else {
-#pragma unroll
-          for (int r = 0; r < 8; ++r) cor[r] = 0.f;
-        }
-        const uint32_t bca = gbase + L.bc + (uint32_t)((2 * qd) * TC_GN + 8 * h) * 4;
-        p = lds_v4(bca); bb[0] = p.x; bb[1] = p.y; bb[2] = p.z; bb[3] = p.w;
-        p = lds_v4(bca + 16); bb[4] = p.x; bb[5] = p.y; bb[6] = p.z; bb[7] = p.w;
-        p = lds_v4(bca + TC_GN * 4); bt[0] = p.x; bt[1] = p.y; bt[2] = p.z; bt[3] = p.w;
-        p = lds_v4(bca + TC_GN * 4 + 16); bt[4] = p.x; bt[5] = p.y; bt[6] = p.z; bt[7] = p.w;
-      }
-      const float Aq = M.rc.A[qd] * Nf;
+      lds8(side_addr(qd, 2 * h), side_addr(qd, 2 * h + 1), D);
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        const float G = Nf * (__shfl_down_sync(0xffffffffu, X[r], 1) - X[r]);
-        float Fup = (nn[r] + b3) - D[r] * G;       // face lane+1
-        if (lane == N - 1) Fup = bt[r];
+        const float dq = __shfl_down_sync(0xffffffffu, X[r], 1) - X[r];
+        float Fup = fmaf(-D[r], dq, nn[r] + b3);
+        if (lane == 31) Fup = bnd[r];
         float Fdn = __shfl_up_sync(0xffffffffu, Fup, 1);
-        if (lane == 0) Fdn = bb[r];
-        dx[r] = cor[r] - Aq * (Fup - Fdn);
+        if (lane == 0) Fdn = bnd[r];
+        dx[r] = fmaf(-Aq, Fup - Fdn, fmaf(cs, Xo[r], cm));
       }
     }
+    tick(6);
   };
 
   if (a.rhs_only) {
@@ -508,6 +562,9 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
     if (a.traj != nullptr && tm.save_stride > 0) { save_frame(0); frame = 1; }
     if (a.ckpt != nullptr) { save_ckpt(0); ci = 1; }
     write_X();
+    // start the second column group roughly half an RHS evaluation late so that its epilogues overlap the first group's
+    // MMAs; contention for the tensor pipe keeps the two apart afterwards
+    if (g == 1 && ta.stagger_ns > 0) __nanosleep(ta.stagger_ns);
     for (int n = 0; n < tm.n_steps; ++n) {
       for (int sub = 0; sub < tm.n_substeps; ++sub) {
         const float tbase = tm.t0 + (float)n * tm.dt + (float)sub * hstep;
@@ -539,6 +596,7 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
             }
             write_X();
           }
+          tick(7);
         }
       }
       const int step = n + 1;

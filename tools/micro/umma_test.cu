@@ -98,7 +98,7 @@ struct Out {
 // Ahi/Alo: [128][96] row-major (m,k). Bhi/Blo: [32][96] (n,k). A3: [3][32][24]; B3: [16][24]
 __global__ void __launch_bounds__(128, 1) umma_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                      const float* __restrict__ Ar, const float* __restrict__ Br,
-                                                     const float* __restrict__ A3, const float* __restrict__ B3, Out* out, int test) {
+                                                     const float* __restrict__ A3, const float* __restrict__ B3, Out* out, int test, int variant) {
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -284,6 +284,86 @@ __global__ void __launch_bounds__(128, 1) umma_kernel(const float* __restrict__ 
   tc_before();
   __syncthreads();
   }
+  // ---------------- T6: TS with MN-major B ([column block of 4][row][4]), N=16, arbitrary K window start ----------------
+  if (test == 6) {
+    const int ROWS = 160, KST = 50, KW = 56;   // window rows 50..105 of a 160-row operand
+    // A (TMEM cols 0..55): A[m][kk] = A[m*96 + kk] ; B rows: Bv[n][row] = B[(n%32)*96 + (row % 96)] for n < 16
+    {
+      const int m = warp * 32 + lane;
+      for (int k0 = 0; k0 < KW; k0 += 8) {
+        float v[8];
+        for (int j = 0; j < 8; ++j) v[j] = A[m * K_ + k0 + j];
+        tmem_st8(tb + ((uint32_t)(warp * 32) << 16) + k0, v);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < 16 * ROWS; i += 128) {
+      const int n = i / ROWS, row = i % ROWS;
+      *reinterpret_cast<float*>(sB + (n / 4) * ROWS * 16 + row * 16 + (n % 4) * 4) = B[n * K_ + (row % K_)];
+    }
+    fence_async();
+    tc_before();
+    __syncthreads();
+    const uint32_t D6 = tb + 400;
+    if (warp == 0) {
+      tc_after();
+      uint32_t el = 0;
+      asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(el));
+      if (el) {
+        const uint32_t id = make_idesc(128, 16) | (1u << 16);  // B MN-major
+        const uint64_t bd = (uint64_t)(((smem_u32(sB) + KST * 16) >> 4) & 0x3FFF) | ((uint64_t)((variant == 0 ? 128u : (uint32_t)ROWS * 16u) >> 4) << 16) | ((uint64_t)((variant == 0 ? (uint32_t)ROWS * 16u : 128u) >> 4) << 32) | (1ull << 46);
+        for (int s = 0; s < KW / 8; ++s) mma_ts(D6, tb + 8 * s, bd + 8 * s, id, s > 0);
+        mma_commit(&bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(&bar, parity); parity ^= 1;
+    tc_after();
+    {
+      float v[32];
+      tmem_ld32(D6 + ((uint32_t)(warp * 32) << 16), v);
+      for (int n = 0; n < 32; ++n) out->d1[(warp * 32 + lane) * 32 + n] = v[n];
+    }
+    tc_before();
+    __syncthreads();
+  }
+  // ---------------- T7: address probe. A = 8x8 identity (other rows 0), smem word i holds float(i): D[m][n] = word index of B(n, k=m)
+  if (test == 7) {
+    {
+      const int m = warp * 32 + lane;
+      float v[8];
+      for (int j = 0; j < 8; ++j) v[j] = (m == j) ? 1.f : 0.f;
+      tmem_st8(tb + ((uint32_t)(warp * 32) << 16), v);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < 8192; i += 128) reinterpret_cast<float*>(sB)[i] = (float)i;
+    fence_async();
+    tc_before();
+    __syncthreads();
+    const uint32_t D7 = tb + 400;
+    if (warp == 0) {
+      tc_after();
+      uint32_t el = 0;
+      asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(el));
+      if (el) {
+        const uint32_t id = make_idesc(128, 16) | ((variant & 1) ? (1u << 16) : 0u);
+        const uint32_t lbo = 2048, sbo = 512;
+        const uint64_t bd = (uint64_t)((smem_u32(sB) >> 4) & 0x3FFF) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+        mma_ts(D7, tb, bd, id, 0);
+        mma_commit(&bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(&bar, parity); parity ^= 1;
+    tc_after();
+    {
+      float v[32];
+      tmem_ld32(D7 + ((uint32_t)(warp * 32) << 16), v);
+      for (int n = 0; n < 32; ++n) out->d1[(warp * 32 + lane) * 32 + n] = v[n];
+    }
+    tc_before();
+    __syncthreads();
+  }
   // ---------------- T5: timings (warp-uniform issue + elect.sync, descriptors advanced by adds) ----------------
   if (test == 5) {
   if (warp == 0) {
@@ -382,7 +462,7 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(dB3, B3.data(), B3.size() * 4, cudaMemcpyHostToDevice));
   const int smem = 2 * 49152 + 2 * 12800 + 9216 + 8192;
   CK(cudaFuncSetAttribute(umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  umma_kernel<<<1, 128, smem>>>(dA, dB, dAr, dBr, dA3, dB3, dout, test);
+  umma_kernel<<<1, 128, smem>>>(dA, dB, dAr, dBr, dA3, dB3, dout, test, argc > 2 ? atoi(argv[2]) : 0);
   printf("test %d\n", test);
   CK(cudaDeviceSynchronize());
   std::vector<char> hb(sizeof(Out));
@@ -425,6 +505,23 @@ int main(int argc, char** argv) {
       ref_max = fmax(ref_max, fabs(r));
     }
   printf("T4 3xTF32: max abs err %.3g (1xTF32 would be %.3g), max |ref| %.3g -> rel %.3g\n", e4, e4t, ref_max, e4 / ref_max);
+  if (test == 7) {
+    printf("T7 probe (byte offsets of B(n,k), LBO=2048 SBO=512): rows k=0..7, cols n=0..15\n");
+    for (int m = 0; m < 8; ++m) {
+      for (int n = 0; n < 16; ++n) printf("%6d", (int)(o->d1[m * 32 + n] * 4));
+      printf("\n");
+    }
+  }
+  if (test == 6) {
+    double e6 = 0;
+    for (int m = 0; m < 128; ++m)
+      for (int n = 0; n < 16; ++n) {
+        double r = 0;
+        for (int kk = 0; kk < 56; ++kk) r += (double)A[m * 96 + kk] * B[n * 96 + ((50 + kk) % 96)];
+        e6 = fmax(e6, fabs(o->d1[m * 32 + n] - r));
+      }
+    printf("T6 TS + MN-major B window: max abs err %.3g\n", e6);
+  }
   printf("T5 cycles total(issue-only): 72 SS N32 %lld(%lld) | 72 TS N32 %lld(%lld) | 72 SS N16 %lld(%lld) | 72 TS N16 %lld(%lld) | 144 TS N16 %lld(%lld) | 144 TS N32 %lld(%lld) | 144 TS N64 %lld(%lld) | 1 MMA rt %lld | ld.x32 %lld\n",
          o->t[1], o->t[9], o->t[2], o->t[10], o->t[3], o->t[11], o->t[4], o->t[12], o->t[5], o->t[13], o->t[6], o->t[14], o->t[7], o->t[15], o->t[0], o->t[8]);
   return 0;
