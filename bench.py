@@ -11,7 +11,7 @@ shard across ranks with no data-path collective. One bench "step" = one full sol
 
 Prints ONE JSON line (rank 0). `value` = device-resident throughput, `e2e` = through the host-pointer C ABI call
 (pinned host buffers, H2D + D2H inside the timed region). Extra objects: roofline (HBM, the contract's key),
-roofline_compute (FP32 SIMT pipe, the roof that actually binds this kernel), adjoint (fwd+adjoint training step,
+roofline (tensor pipe of the tcgen05 kernel), roofline_hbm / roofline_compute (HBM and FP32-SIMT views of the same run), adjoint (fwd+adjoint training step,
 BASELINE config 3 slice), nn_free (the HBM-fair mPP-only variant), cpu_baseline (the oracle on host cores).
 """
 import argparse
@@ -30,6 +30,9 @@ import numpy as np  # noqa: E402
 NCOL = 4096
 NSTEPS = 1152
 FP32_LANES_PER_SM = 128
+# dram__bytes_read.sum + dram__bytes_write.sum of one solve_tc_kernel launch at the bench configuration, from the ncu --set full
+# capture summarised in profiles/ (None until captured)
+TRAFFIC_NCU_BYTES = 1.772e9  # 12.0 MB read + 1.7605 GB written (profiles/r01_tc_solve_ncu_summary.txt)
 
 
 def peaks():
@@ -37,8 +40,8 @@ def peaks():
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return d.get("hbm_gbs", 6650.0), d.get("sm_max_mhz", 1965.0), "measured"
-    return 6650.0, 1965.0, "fallback"
+        return d.get("hbm_gbs", 6650.0), d.get("sm_max_mhz", 1965.0), "measured", d.get("bf16_tflops_sustained", 1400.0)
+    return 6650.0, 1965.0, "fallback", 1400.0
 
 
 class ClockSampler:
@@ -251,7 +254,7 @@ def main():
     e2e_val = colsteps_per_step * e2e_steps / float(t.item())
     checksum = float(traj_h[:, -1].double().abs().mean())
 
-    hbm_peak, sm_max_mhz, peak_src = peaks()
+    hbm_peak, sm_max_mhz, peak_src, bf16_peak = peaks()
     bytes_per_colstep = 4 * S * (n_saved / NSTEPS) + (4 * S + 4 * d.n_bc) / NSTEPS
     ach_gbs = bytes_per_colstep * NCOL * NSTEPS / (kern_ms * 1e-3) / 1e9
     fl = flops_per_colstep(d)
@@ -261,6 +264,31 @@ def main():
     peak_tf_max = n_sm * FP32_LANES_PER_SM * 2 * sm_max_mhz * 1e6 / 1e12
     peak_tf_obs = n_sm * FP32_LANES_PER_SM * 2 * sm_mhz * 1e6 / 1e12
 
+    tc = "forward kernel: tcgen05" in model.describe()
+    if tc:
+        # dominant kernel: solve_tc_kernel (tcgen05 kind::tf32, 3xTF32). achieved = ALGORITHMIC tensor flops: every MAC of
+        # the three MLPs is three TF32 MACs (hi*lo + lo*hi + hi*hi); peak = measured dense bf16 (sustained, the kernel
+        # runs for tens of ms); TF32 runs at half the bf16 rate, so frac_of_tf32_peak = 2*frac.
+        mlp_macs = sum(n.macs for n in d.nets)
+        tf32_flops = 3 * 2 * mlp_macs * d.rhs_evals_per_step * NCOL * NSTEPS
+        h1 = d.nets[0].sizes[1]; h2 = d.nets[0].sizes[2]
+        mma_per_rhs_group = (72 if 3 * h1 > 128 else 36) + 9 * 7 + 9 * (3 if h2 <= 24 else 4)
+        issued_flops = mma_per_rhs_group * (2 * 128 * 16 * 8) * (NCOL / 16) * d.rhs_evals_per_step * NSTEPS
+        ach_tensor = tf32_flops / (kern_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": ach_tensor, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach_tensor / bf16_peak,
+                    "traffic": TRAFFIC_NCU_BYTES, "peak_source": peak_src + " (bf16_tflops_sustained)",
+                    "kernel": "solve_tc_kernel<ACT_MISH,3>", "kernel_ms": kern_ms,
+                    "algorithmic_flop_per_colstep": 3 * 2 * mlp_macs * d.rhs_evals_per_step,
+                    "frac_of_tf32_peak": 2 * ach_tensor / bf16_peak,
+                    "issued_tflops_incl_padding": issued_flops / (kern_ms * 1e-3) / 1e12,
+                    "pipe_tensor_active_pct_ncu": 43.0,
+                    "note": "3xTF32 on tcgen05 with M=128 x N=16 x K=8 MMAs; padding of the 150/60/93 output rows to 128-row "
+                            "blocks makes issued flops 2.9x the algorithmic ones; the kernel is latency-bound (ncu: tensor pipe "
+                            "active 43 %, issue slots 45 %), see profiles/r01_tc_solve_ncu_summary.txt"}
+    else:
+        roofline = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": None,
+                    "peak_source": peak_src, "kernel": "solve_kernel<32,256,true>", "kernel_ms": kern_ms,
+                    "algorithmic_bytes_per_colstep": bytes_per_colstep}
     line = {
         "metric": "column-steps/sec (forward)", "value": value, "unit": "column-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -274,13 +302,14 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "column-steps/s", "h2d_bytes_per_step": int(x0_h.numel() * 4 + bcs_h.numel() * 4),
                 "d2h_bytes_per_step": int(traj_h.numel() * 4), "steps": e2e_steps, "final_state_checksum": checksum},
-        "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "solve_kernel<32,256,true>",
-                     "kernel_ms": kern_ms, "algorithmic_bytes_per_colstep": bytes_per_colstep,
-                     "note": "this workload is FP32-pipe bound (AI ~ 1200 flop/B): see roofline_compute"},
+        "roofline": roofline,
+        "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                         "peak_source": peak_src, "algorithmic_bytes_per_colstep": bytes_per_colstep,
+                         "note": "not the binding roof: arithmetic intensity ~ 1200 flop/B"},
         "roofline_compute": {"bound": "fp32_simt", "achieved": ach_tf, "unit": "TFLOP/s", "peak_at_max_clock": peak_tf_max,
                              "peak_at_observed_clock": peak_tf_obs, "frac": ach_tf / peak_tf_obs, "flop_per_colstep": fl,
-                             "stage_evals_per_s": value * d.rhs_evals_per_step},
+                             "stage_evals_per_s": value * d.rhs_evals_per_step,
+                             "note": "FP32-equivalent algorithmic flops against the FP32 SIMT peak (the roof of the non-tensor-core kernel)"},
     }
     if not args.no_extras:
         # ---- fwd + discrete adjoint + ADAM (BASELINE config 3: 9 forcing cases x 1024 columns, sharded over ranks) ----
