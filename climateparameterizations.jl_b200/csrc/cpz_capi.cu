@@ -155,6 +155,8 @@ int cpz_ctx_create(int device, void* stream, cpz_ctx** out) {
 int cpz_ctx_destroy(cpz_ctx* ctx) {
   if (!ctx) return CPZ_OK;
   cudaSetDevice(ctx->device);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (auto& e : ctx->chunk_ev) if (e) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return CPZ_OK;
@@ -375,11 +377,53 @@ int cpz_solve(cpz_model* m, const float* x0, const float* bcs, const float* diur
   if (!x0 || !bcs || !traj) return fail(CPZ_ERR_INVALID, "null array");
   if ((rc = bind_device(m->ctx))) return rc;
   if ((rc = upload_inputs(m, x0, bcs, diurnal_Q, ncol))) return rc;
-  const size_t n = ncol * (size_t)n_saved_of(m->tm) * (size_t)m->fwd.M.S;
+  const size_t S = (size_t)m->fwd.M.S;
+  const int n_saved = n_saved_of(m->tm);
+  const size_t n = ncol * (size_t)n_saved * S;
   if ((rc = ensure(m->b_traj, n))) return rc;
-  if ((rc = cpz_solve_dev(m, m->b_x0.p, m->b_bcs.p, diurnal_Q ? m->b_q.p : nullptr, m->b_traj.p, ncol))) return rc;
-  CPZ_CUDA(cudaMemcpyAsync(traj, m->b_traj.p, n * sizeof(float), cudaMemcpyDeviceToHost, m->ctx->stream));
-  CPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  const float* dQ = diurnal_Q ? m->b_q.p : nullptr;
+  // Long solves that save frames are cut into time chunks: while chunk k+1 integrates, the frames of chunk k go to the
+  // host on a second stream (the trajectory is [ncol][n_saved][S], so a chunk is a 2-D sub-block).
+  const TimeD tm_full = m->tm;
+  const int n_frames = tm_full.save_stride > 0 ? tm_full.n_steps / tm_full.save_stride : 0;
+  int n_chunks = 1;
+  if (tm_full.save_stride > 0 && tm_full.n_steps % tm_full.save_stride == 0 && n * sizeof(float) >= ((size_t)64 << 20)) n_chunks = std::min(8, n_frames / 16);
+  if (n_chunks <= 1) {
+    if ((rc = cpz_solve_dev(m, m->b_x0.p, m->b_bcs.p, dQ, m->b_traj.p, ncol))) return rc;
+    CPZ_CUDA(cudaMemcpyAsync(traj, m->b_traj.p, n * sizeof(float), cudaMemcpyDeviceToHost, m->ctx->stream));
+    CPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    return CPZ_OK;
+  }
+  cpz_ctx* c = m->ctx;
+  if (!c->copy_stream) {
+    CPZ_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : c->chunk_ev) CPZ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  const size_t pitch = (size_t)n_saved * S * sizeof(float);
+  const int fpc = (n_frames + n_chunks - 1) / n_chunks;  // frames per chunk
+  int f0 = 0;                                            // frames (after the initial one) already integrated
+  for (int k = 0; f0 < n_frames; ++k) {
+    const int nf = std::min(fpc, n_frames - f0);
+    SolveArgs a{};
+    a.theta = m->d_theta; a.bcs = m->b_bcs.p; a.Q = dQ; a.ncol = (int)ncol; a.n_saved = n_saved; a.n_ckpt = 0; a.rhs_only = 0;
+    if (k == 0) { a.x0 = m->b_x0.p; a.traj = m->b_traj.p; }
+    else { a.x0 = m->b_traj.p + (size_t)f0 * S; a.x0_stride = (size_t)n_saved * S; a.skip_frame0 = 1; a.traj = m->b_traj.p + (size_t)(f0 + 1) * S; }
+    m->tm = tm_full;
+    m->tm.t0 = tm_full.t0 + (float)(f0 * tm_full.save_stride) * tm_full.dt;
+    m->tm.n_steps = nf * tm_full.save_stride;
+    rc = launch_solve(m, a);
+    m->tm = tm_full;
+    if (rc) return rc;
+    cudaEvent_t ev = c->chunk_ev[k & 1];
+    CPZ_CUDA(cudaEventRecord(ev, c->stream));
+    CPZ_CUDA(cudaStreamWaitEvent(c->copy_stream, ev, 0));
+    const int first = k == 0 ? 0 : f0 + 1, count = k == 0 ? nf + 1 : nf;  // chunk 0 also carries the initial frame
+    CPZ_CUDA(cudaMemcpy2DAsync(traj + (size_t)first * S, pitch, m->b_traj.p + (size_t)first * S, pitch, (size_t)count * S * sizeof(float), ncol,
+                               cudaMemcpyDeviceToHost, c->copy_stream));
+    f0 += nf;
+  }
+  CPZ_CUDA(cudaStreamSynchronize(c->copy_stream));
+  CPZ_CUDA(cudaStreamSynchronize(c->stream));
   return CPZ_OK;
 }
 

@@ -18,6 +18,8 @@ struct cpz_ctx {
   int rank = 0, world = 1;
   uint64_t launches = 0;
   int sm_count = 0;
+  cudaStream_t copy_stream = nullptr;  // D2H of finished trajectory chunks, overlapped with the next chunk's kernel
+  cudaEvent_t chunk_ev[2] = {nullptr, nullptr};
   size_t smem_optin = 0;
 };
 

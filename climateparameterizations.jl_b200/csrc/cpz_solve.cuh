@@ -19,6 +19,8 @@ struct SolveArgs {
   int rhs_only;
   float t_rhs;
   unsigned long long* prof;  // optional [8] cycle counters (CTA 0, thread 0): set CPZ_PROF=1 in the environment
+  size_t x0_stride;          // floats between consecutive columns of x0 (0 = S); a trajectory frame can be the start state
+  int skip_frame0;           // continuation of a chunked solve: the start state is already in the trajectory, do not store it
 };
 
 #define CPZ_PROF_BEGIN() const long long prof_t0__ = (a.prof && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0
@@ -143,7 +145,7 @@ __device__ __forceinline__ void solve_body(const ModelD& M, const ModelD& Mp, co
     qs[threadIdx.x] = (a.Q != nullptr) ? __ldg(a.Q + col) : 0.f;
   }
   __syncthreads();
-  load_tile<CT, NT>(xs, xa, bar, parity, a.x0, (size_t)S, S, col0, a.ncol);
+  load_tile<CT, NT>(xs, xa, bar, parity, a.x0, a.x0_stride ? a.x0_stride : (size_t)S, S, col0, a.ncol);
   __syncthreads();
 
   const int ns = tab.n_stages;
@@ -168,7 +170,7 @@ __device__ __forceinline__ void solve_body(const ModelD& M, const ModelD& Mp, co
   int frame = 0, ci = 0;
   const size_t traj_stride = (size_t)a.n_saved * S;
   // frame 0 = initial condition; checkpoint 0
-  if (a.traj != nullptr && tm.save_stride > 0) {
+  if (a.traj != nullptr && tm.save_stride > 0 && !a.skip_frame0) {
     store_tile<CT, NT>(xs, xa, a.traj, traj_stride, S, col0, a.ncol);
     if (threadIdx.x < CT) bulk_wait_read0();
     frame = 1;

@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const int col = min(col0 + cg0 + r, a.ncol - 1);
-    x[r] = qd < 3 ? __ldg(a.x0 + (size_t)col * 96 + 32 * qd + lane) : 0.f;
+    x[r] = qd < 3 ? __ldg(a.x0 + (size_t)col * (a.x0_stride ? a.x0_stride : (size_t)96) + 32 * qd + lane) : 0.f;
     X[r] = x[r];
     float raw[6], eff[6];
 #pragma unroll
@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
         dst[1] = make_float4(x[4], x[5], x[6], x[7]);
       }
     };
-    if (a.traj != nullptr && tm.save_stride > 0) { save_frame(0); frame = 1; }
+    if (a.traj != nullptr && tm.save_stride > 0 && !a.skip_frame0) { save_frame(0); frame = 1; }
     if (a.ckpt != nullptr) { save_ckpt(0); ci = 1; }
     write_X();
     // start the second column group roughly half an RHS evaluation late so that its epilogues overlap the first group's

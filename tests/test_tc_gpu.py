@@ -118,3 +118,22 @@ def test_tc_solve_sharding_invariant_bitwise(ctx):
     b = m.solve(x0[37:], bcs[37:])
     m.close()
     np.testing.assert_array_equal(full, np.concatenate([a, b]))
+
+
+@pytest.mark.parametrize("net", ["uvT_small", "uvT_test"])
+def test_host_solve_chunked_pipeline_matches_single_launch(ctx, net):
+    """cpz_solve cuts long solves into time chunks so the D2H of finished frames overlaps the next chunk's kernel
+    (trajectories >= 64 MB); the chunked result must be bitwise the single-launch result (both forward kernels)."""
+    d = syn.wind_mixing_desc(variant=RHS_INFER, net=net, n_steps=96, save_stride=1)
+    th = syn.theta_random(d, scale=0.3)
+    ncol = 2048 + 7
+    x0, bcs = syn.columns(d, ncol)
+    m = engine.Model(ctx, d, th)
+    host = m.solve(x0, bcs)                       # 2055 x 97 x 96 floats = 76.5 MB -> chunked
+    x0d, bcsd = torch.tensor(x0, device="cuda"), torch.tensor(bcs, device="cuda")
+    traj = torch.empty((ncol, d.n_saved, d.S), device="cuda")
+    m.solve_dev(x0d, bcsd, traj)
+    ctx.synchronize()
+    m.close()
+    np.testing.assert_array_equal(host, traj.cpu().numpy())
+    np.testing.assert_array_equal(host[:, 0], x0)
