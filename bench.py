@@ -138,7 +138,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": "column-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference Julia path cannot run in this image (no julia, no LES data); restated-reference CPU oracle timed instead",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline(syn, RHS_INFER):
@@ -162,7 +162,27 @@ def cpu_baseline(syn, RHS_INFER):
             "sample": f"{reps} x ({ncol_s} columns x {nsteps_s} steps x {d.n_substeps} sub-steps), FP32 torch-CPU oracle batched over columns"}
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything a library prints to fd 1 (e.g. NCCL's version banner) goes to stderr; the one JSON line is written to
+    the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -378,7 +398,7 @@ def main():
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"error": repr(e)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
