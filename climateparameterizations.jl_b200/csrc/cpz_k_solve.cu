@@ -41,7 +41,9 @@ static int launch_solve_t(cpz_model* m, const SolveArgs& a) {
 int launch_solve(cpz_model* m, const SolveArgs& a) {
   static const bool prof = getenv("CPZ_PROF") != nullptr;
   if (!prof) {
-    const int rc = launch_solve_tc(m, a);  // tcgen05 path for the production u/v/T nets
+    int rc = launch_solve_tc(m, a);  // tcgen05 path for the production u/v/T nets
+    if (rc <= 0) return rc;
+    rc = launch_solve_nnfree(m, a);  // NN-free u/v/T model
     if (rc <= 0) return rc;
   }
   if (m->fwd.M.w_in_smem) return launch_solve_t<32, 256, true>(m, a);

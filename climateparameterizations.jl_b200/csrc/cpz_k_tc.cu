@@ -5,8 +5,28 @@
 
 #include "cpz_launch.h"
 #include "cpz_tc.cuh"
+#include "cpz_nnfree.cuh"
 
 namespace cpz {
+
+// face-diffusivity mode and folded constants (see side_column in cpz_tc.cuh)
+static void side_constants(const ModelD& M, int& side_mode, SideC& C) {
+  const RhsC& rc = M.rc;
+  const bool mpp = (M.flags & F_MPP) || M.variant == RHS_INFER;
+  const bool ca = (M.flags & F_CA) != 0;
+  side_mode = SIDE_NONE;
+  if (mpp) side_mode = (M.variant == RHS_INFER && ca) ? ((M.flags & F_CA_LITERAL_U) ? SIDE_MPP_CA_U : SIDE_MPP_CA_T) : SIDE_MPP;
+  else if (ca) side_mode = SIDE_CA_ONLY;
+  const double Nf = rc.Nf, L2E = 1.4426950408889634;
+  C.e = M.variant == RHS_TRAIN ? (float)(rc.eps / Nf) : 0.f;
+  C.su2 = (float)((double)rc.sig_u * rc.sig_u); C.sv2 = (float)((double)rc.sig_v * rc.sig_v);
+  C.k1 = (float)(2.0 * rc.inv_dRi * (rc.BzC / Nf) * L2E);
+  C.k2 = (float)(2.0 * rc.inv_dRi * rc.Ric * L2E);
+  C.a0 = (float)(Nf * rc.c[0] * rc.nu0); C.a1 = (float)(Nf * rc.c[0] * rc.nu_m);
+  C.b0 = (float)(Nf * rc.c[1] * rc.nu0); C.b1 = (float)(Nf * rc.c[1] * rc.nu_m);
+  C.t0 = (float)(Nf * rc.c[2] * rc.inv_Pr * rc.nu0); C.t1 = (float)(Nf * rc.c[2] * rc.inv_Pr * rc.nu_m);
+  C.kap = (float)(Nf * rc.c[2] * rc.kappa);
+}
 
 // The tcgen05 kernel covers the production wind_mixing nets (wind_mixing/train_NDE.jl:103: three Chains
 // Dense(96,h1,act) -> Dense(h1,h2,act) -> Dense(h2,31)) with 3*h1 <= 160 and h2 <= 32; everything else runs on the
@@ -55,24 +75,7 @@ bool tc_plan(const cpz_model* m, TcD& T, std::string& why) {
     ++found;
   }
   if (found != 9) { why = "plan"; return false; }
-  {  // face-diffusivity mode and folded constants (see side_column)
-    const RhsC& rc = M.rc;
-    const bool mpp = (M.flags & F_MPP) || M.variant == RHS_INFER;
-    const bool ca = (M.flags & F_CA) != 0;
-    T.side_mode = SIDE_NONE;
-    if (mpp) T.side_mode = (M.variant == RHS_INFER && ca) ? ((M.flags & F_CA_LITERAL_U) ? SIDE_MPP_CA_U : SIDE_MPP_CA_T) : SIDE_MPP;
-    else if (ca) T.side_mode = SIDE_CA_ONLY;
-    const double Nf = rc.Nf, L2E = 1.4426950408889634;
-    SideC& C = T.sc;
-    C.e = M.variant == RHS_TRAIN ? (float)(rc.eps / Nf) : 0.f;
-    C.su2 = (float)((double)rc.sig_u * rc.sig_u); C.sv2 = (float)((double)rc.sig_v * rc.sig_v);
-    C.k1 = (float)(2.0 * rc.inv_dRi * (rc.BzC / Nf) * L2E);
-    C.k2 = (float)(2.0 * rc.inv_dRi * rc.Ric * L2E);
-    C.a0 = (float)(Nf * rc.c[0] * rc.nu0); C.a1 = (float)(Nf * rc.c[0] * rc.nu_m);
-    C.b0 = (float)(Nf * rc.c[1] * rc.nu0); C.b1 = (float)(Nf * rc.c[1] * rc.nu_m);
-    C.t0 = (float)(Nf * rc.c[2] * rc.inv_Pr * rc.nu0); C.t1 = (float)(Nf * rc.c[2] * rc.inv_Pr * rc.nu_m);
-    C.kap = (float)(Nf * rc.c[2] * rc.kappa);
-  }
+  side_constants(M, T.side_mode, T.sc);
   const TcSmem L = tc_smem_layout(T, m->tab.n_stages);
   if ((size_t)L.total > m->ctx->smem_optin) { why = "shared memory"; return false; }
   return true;
@@ -83,6 +86,9 @@ std::string tc_describe(const cpz_model* m) {
   std::string why;
   char line[512];
   if (getenv("CPZ_NO_TC") != nullptr) return "forward kernel: fp32-simt (CPZ_NO_TC set)\n";
+  if (m->desc.n_nets == 0 && m->desc.n_fields == 3 && m->desc.Nz == 32 && m->desc.variant != CPZ_RHS_FREE_CONVECTION &&
+      !(m->desc.flags & (CPZ_FLAG_SMOOTH_NN | CPZ_FLAG_SMOOTH_RI)))
+    return "forward kernel: nn-free warp-per-columns (2 columns per warp, no block barriers)\n";
   if (!tc_plan(m, T, why)) return "forward kernel: fp32-simt (tcgen05 path not eligible: " + why + ")\n";
   const TcSmem L = tc_smem_layout(T, m->tab.n_stages);
   snprintf(line, sizeof(line),
@@ -127,6 +133,25 @@ static int launch_tc_t(cpz_model* m, const TcD& T, const SolveArgs& a, const TcA
     return CPZ_OK;
   }
   kern<<<n_tiles, TC_NT, L.total, m->ctx->stream>>>(m->fwd.M, T, m->tab, m->tm, a, ta);
+  CPZ_CUDA(cudaGetLastError());
+  m->ctx->launches++;
+  return CPZ_OK;
+}
+
+// NN-free u/v/T model (`DE`): warp-per-columns kernel without block barriers. 1 = not eligible.
+int launch_solve_nnfree(cpz_model* m, const SolveArgs& a) {
+  const cpz_model_desc& d = m->desc;
+  if (getenv("CPZ_NO_TC") != nullptr) return 1;
+  if (d.n_nets != 0 || d.n_fields != 3 || d.Nz != 32) return 1;
+  if (d.variant != CPZ_RHS_TRAIN && d.variant != CPZ_RHS_INFER) return 1;
+  if (d.flags & (CPZ_FLAG_SMOOTH_NN | CPZ_FLAG_SMOOTH_RI)) return 1;
+  SideC sc; int mode;
+  side_constants(m->fwd.M, mode, sc);
+  constexpr int NC = 2;
+  const int warps = (a.ncol + NC - 1) / NC;
+  const int grid = (warps + NF_WARPS - 1) / NF_WARPS;
+  const size_t smem = (size_t)m->tab.n_stages * NF_WARPS * 32 * 3 * NC * sizeof(float);
+  solve_nnfree_kernel<NC><<<grid, NF_WARPS * 32, smem, m->ctx->stream>>>(m->fwd.M, sc, mode, m->tab, m->tm, a);
   CPZ_CUDA(cudaGetLastError());
   m->ctx->launches++;
   return CPZ_OK;
