@@ -1,7 +1,10 @@
 // Closure kernel instantiations and launcher.
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "cpz_launch.h"
+#include "cpz_closure_tc.cuh"
 
 namespace cpz {
 
@@ -19,7 +22,76 @@ static int launch_closure_t(cpz_model* m, const ClosureD& cd, const ClosureArgs&
   return CPZ_OK;
 }
 
+// tcgen05 closure: T-only model, one net Nz -> h1 -> h2 -> Nz-1 with h1, h2 <= 128 (free_convection/train_free_convection_nde.jl:119-121).
+static bool closure_tc_plan(const cpz_model* m, ClosureTcD& C) {
+  const cpz_model_desc& d = m->desc;
+  if (getenv("CPZ_NO_TC") != nullptr) return false;
+  if (d.n_fields != 1 || d.n_nets != 1 || d.Nz != 32) return false;
+  const cpz_net_desc& n = d.nets[0];
+  if (n.n_layers != 3 || n.sizes[0] != 32 || n.sizes[3] != 31 || n.act[2] != CPZ_ACT_IDENTITY) return false;
+  if (n.sizes[1] < 1 || n.sizes[1] > 128 || n.sizes[2] < 1 || n.sizes[2] > 128) return false;
+  C = ClosureTcD{};
+  C.h1 = n.sizes[1]; C.h2 = n.sizes[2]; C.nout = 31;
+  C.n1 = (C.h1 + 15) & ~15; C.n2 = (C.h2 + 15) & ~15; C.n3 = 32;
+  C.k2 = (C.h1 + 7) & ~7; C.k3 = (C.h2 + 7) & ~7;
+  C.act1 = n.act[0]; C.act2 = n.act[1];
+  const ModelD& M = m->fwd.M;
+  int found = 0;
+  for (int i = 0; i < M.n_gemm; ++i) {
+    const GemmD& g = M.gemm[i];
+    if (g.net != 0 || g.layer < 0 || g.layer > 2) return false;
+    C.w_off[g.layer] = g.w_off; C.b_off[g.layer] = g.b_off; ++found;
+  }
+  if (found != 3) return false;
+  int o = 0;
+  auto take = [&](int bytes) { int r = o; o += (bytes + 127) & ~127; return r; };
+  C.o_w1h = take(C.n1 * 32 * 4); C.o_w1l = take(C.n1 * 32 * 4);
+  C.o_w2h = take(C.n2 * C.k2 * 4); C.o_w2l = take(C.n2 * C.k2 * 4);
+  C.o_w3h = take(C.n3 * C.k3 * 4); C.o_w3l = take(C.n3 * C.k3 * 4);
+  C.o_b = take((C.n1 + C.n2 + C.n3) * 4);
+  C.img_bytes = o;
+  return (size_t)o + 1024 <= m->ctx->smem_optin;
+}
+
+template <int ACT>
+static int launch_closure_tc_t(cpz_model* m, const ClosureTcD& C, const ClosureD& cd, ClosureArgs a) {
+  auto kern = closure_tc_kernel<ACT>;
+  CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C.img_bytes));
+  a.n_tiles = (a.ncol + CTC_NT - 1) / CTC_NT;
+  const int grid = std::min(a.n_tiles, m->ctx->sm_count);
+  kern<<<grid, CTC_NT, C.img_bytes, m->ctx->stream>>>(C, cd, a, m->b_cimg.p);
+  CPZ_CUDA(cudaGetLastError());
+  m->ctx->launches++;
+  return CPZ_OK;
+}
+
+bool closure_uses_tc(const cpz_model* m) {
+  ClosureTcD C;
+  return closure_tc_plan(m, C);
+}
+
 int launch_closure(cpz_model* m, const ClosureD& cd, const ClosureArgs& a) {
+  ClosureTcD C;
+  if (closure_tc_plan(m, C)) {
+    const size_t need = (size_t)C.img_bytes / 4;
+    if (m->b_cimg.cap < need) {
+      if (m->b_cimg.p) cudaFree(m->b_cimg.p);
+      m->b_cimg.p = nullptr; m->b_cimg.cap = 0; m->cimg_ver = 0;
+      CPZ_CUDA(cudaMalloc(&m->b_cimg.p, need * sizeof(float)));
+      m->b_cimg.cap = need;
+    }
+    if (m->cimg_ver != m->theta_ver) {  // weights changed since the image was built
+      const int n_el = C.n1 * 32 + C.n2 * C.k2 + C.n3 * C.k3 + C.n1 + C.n2 + C.n3;
+      closure_tc_image_kernel<<<(n_el + 255) / 256, 256, 0, m->ctx->stream>>>(C, a.theta, m->b_cimg.p);
+      CPZ_CUDA(cudaGetLastError());
+      m->ctx->launches++;
+      m->cimg_ver = m->theta_ver;
+    }
+    const bool same = C.act1 == C.act2;
+    if (same && C.act1 == ACT_RELU) return launch_closure_tc_t<ACT_RELU>(m, C, cd, a);
+    if (same && C.act1 == ACT_MISH) return launch_closure_tc_t<ACT_MISH>(m, C, cd, a);
+    return launch_closure_tc_t<-1>(m, C, cd, a);
+  }
   if (m->fwd.M.w_in_smem) return launch_closure_t<32, 256, true>(m, cd, a);
   return launch_closure_t<32, 256, false>(m, cd, a);
 }

@@ -183,7 +183,7 @@ struct TcArgs {
 // ---- weight image ---------------------------------------------------------------------------------------------
 // wimg[c][l] = value of TMEM column c, lane l (see the map in the header comment). Flux stores W (out x in) column-major:
 // element (o, k) of net/layer at theta[w_off + k*out + o].
-__global__ void tc_image_kernel(const __grid_constant__ TcD T, const float* __restrict__ theta, float* __restrict__ wimg) {
+static __global__ void tc_image_kernel(const __grid_constant__ TcD T, const float* __restrict__ theta, float* __restrict__ wimg) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= TC_WCOLS * 128) return;
   const int c = idx >> 7, l = idx & 127;
