@@ -2,8 +2,9 @@
 // implicit convective adjustment + neural-network temperature-flux forcing for every column of an (Nx,Ny,Nz) field,
 // replacing convective_adjustment! and compute_neural_network_forcing! (free_convection/double_gyre_nn.jl:27-62,149-168).
 //
-// A field has tens of thousands of columns per GPU, so here the COLUMNS are the M side of the MMA: one CTA of 128
-// threads owns a tile of 128 consecutive columns, thread t <-> column t <-> TMEM lane t. Everything a column needs stays
+// A field has tens of thousands of columns per GPU, so here the COLUMNS are the M side of the MMA: one CTA owns a tile of
+// 128 consecutive columns, thread t (< 128) <-> column t <-> TMEM lane t; a second set of four warps shares the lanes and
+// takes every other 32-output chunk of the hidden-layer epilogues. Everything a column needs stays
 // in that thread's registers (the 32-level profile, the Thomas solve, the flux divergence); the three Dense layers are
 //     D[128 columns][N outputs] = act[128][K] * W[K][N]      (tcgen05.mma kind::tf32, 3xTF32, FP32 accumulators in TMEM)
 // with the activations as the A operand IN TENSOR MEMORY (written by tcgen05.st straight from the epilogue registers:
@@ -89,7 +90,8 @@ __device__ __forceinline__ uint64_t ctc_desc(uint32_t saddr, uint32_t sbo) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
 
-constexpr int CTC_NT = 128;
+constexpr int CTC_TILE = 128;  // columns per tile = TMEM lanes
+constexpr int CTC_NT = 256;    // two warps per TMEM lane quadrant: they split the output chunks of the hidden-layer epilogues
 
 template <int ACT>
 __global__ void __launch_bounds__(CTC_NT, 1) closure_tc_kernel(const __grid_constant__ ClosureTcD C, const ClosureD cd, const ClosureArgs a,
@@ -98,6 +100,8 @@ __global__ void __launch_bounds__(CTC_NT, 1) closure_tc_kernel(const __grid_cons
   __shared__ __align__(8) uint64_t bars[2];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int hh = warp >> 2;        // 0: owns the columns (profile, Thomas solve, forcing); 1: epilogue helper
+  const int ltid = tid & 127;      // column / TMEM lane inside the tile
   constexpr int N = 32;
   uint64_t* bar_w = &bars[0];    // weight image landed
   uint64_t* bar_mma = &bars[1];  // MMA chain complete
@@ -118,11 +122,10 @@ __global__ void __launch_bounds__(CTC_NT, 1) closure_tc_kernel(const __grid_cons
     mbar_expect_tx(bar_w, (uint32_t)C.img_bytes);
     for (int o = 0; o < C.img_bytes; o += 32768) bulk_g2s(sm + o, reinterpret_cast<const char*>(img) + o, (uint32_t)min(32768, C.img_bytes - o), bar_w);
   }
-  const uint32_t tl = tb + ((uint32_t)(32 * warp) << 16);  // this warp's TMEM lanes
+  const uint32_t tl = tb + ((uint32_t)(32 * (warp & 3)) << 16);  // this warp's TMEM lanes
   const uint32_t XA = 0, D12 = 64, HAh = 192, HAl = 320, D3 = 448;
   const float* bias = reinterpret_cast<const float*>(sm + C.o_b);
   uint32_t par = 0;
-  bool weights_ready = false;
 
   // one MMA chain: D[128][n] (+)= A(TMEM, K = 8*steps) * B(smem planes): lo*hi + hi*lo + hi*hi
   auto chain = [&](uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t bh_off, uint32_t bl_off, int K, int n) {
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(CTC_NT, 1) closure_tc_kernel(const __grid_cons
   };
   // hidden-layer epilogue: accumulator row -> bias, activation, hi/lo split -> A operand of the next layer
   auto hidden = [&](int n_cols, int b_off, int act) {
-    for (int j = 0; j < n_cols; j += 32) {
+    for (int j = 32 * hh; j < n_cols; j += 64) {
       float v[32], lo[32];
       tmem_ld32(tl + D12 + j, v);
 #pragma unroll
@@ -155,15 +158,20 @@ __global__ void __launch_bounds__(CTC_NT, 1) closure_tc_kernel(const __grid_cons
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   };
 
-  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    const int col = tile * CTC_NT + tid;
-    const int colc = min(col, a.ncol - 1);
-    const bool live = col < a.ncol;
-    // ---- column profile (coalesced across the 128 threads of the tile) ----
+  // per-tile column state of this warp set (set = hh): the two sets alternate tiles, so that the profile load and the
+  // Thomas solve of tile i+1 run while layer 2 of tile i is in the tensor pipe
+  float T_top = 0.f;
+  int col = 0, colc = 0;
+  bool live = false;
+  // column part: profile load, implicit convective adjustment, adjusted T out, scaled NN input -> TMEM A operand
+  auto column_part = [&](int tile) {
+    col = tile * CTC_TILE + ltid;
+    colc = min(col, a.ncol - 1);
+    live = col < a.ncol;
     float T[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) T[k] = __ldg(a.T + (size_t)k * a.ncol + colc);
-    // ---- implicit convective adjustment (oceananigans_nn.jl:13-40; free_convection/convective_adjustment.jl:106-129) ----
+    // implicit convective adjustment (oceananigans_nn.jl:13-40; free_convection/convective_adjustment.jl:106-129)
     {
       float kap[N];
 #pragma unroll
@@ -174,9 +182,9 @@ __global__ void __launch_bounds__(CTC_NT, 1) closure_tc_kernel(const __grid_cons
       }
       float cp[N], dp[N];
       {
-        const float diag = 1.f + cd.r * (kap[0] + kap[1]);
-        cp[0] = -cd.r * kap[1] / diag;
-        dp[0] = T[0] / diag;
+        const float inv = rcp_fast(1.f + cd.r * (kap[0] + kap[1]));
+        cp[0] = -cd.r * kap[1] * inv;
+        dp[0] = T[0] * inv;
       }
 #pragma unroll
       for (int k = 1; k < N; ++k) {
@@ -184,30 +192,34 @@ __global__ void __launch_bounds__(CTC_NT, 1) closure_tc_kernel(const __grid_cons
         const float kn = (k + 1 < N) ? kap[k + 1] : 0.f;
         const float diag = (k < N - 1) ? 1.f + cd.r * (kap[k] + kn) : 1.f + cd.r * kap[k];
         const float up = (k < N - 1) ? -cd.r * kn : 0.f;
-        const float den = diag - lo * cp[k - 1];
-        cp[k] = up / den;
-        dp[k] = (T[k] - lo * dp[k - 1]) / den;
+        const float inv = rcp_fast(diag - lo * cp[k - 1]);  // MUFU.RCP (2 ulp): diagonally dominant system, den >= 1
+        cp[k] = up * inv;
+        dp[k] = (T[k] - lo * dp[k - 1]) * inv;
       }
       T[N - 1] = dp[N - 1];
 #pragma unroll
       for (int k = N - 2; k >= 0; --k) T[k] = dp[k] - cp[k] * T[k + 1];
     }
-    // ---- adjusted T out; NN input T_scaling(T_shift + T/T_div) (double_gyre_nn.jl:155-158) -> TMEM A operand ----
-    {
-      float hi[N], lo[N];
+    // adjusted T out; NN input T_scaling(T_shift + T/T_div) (double_gyre_nn.jl:155-158) -> TMEM A operand
+    float hi[N], lo[N];
 #pragma unroll
-      for (int k = 0; k < N; ++k) {
-        if (live) a.T_out[(size_t)k * a.ncol + col] = T[k];
-        const float x = ((cd.T_shift + T[k] * cd.inv_T_div) - cd.mu_T) * cd.inv_sig_T;
-        hi[k] = tf32_hi(x);
-        lo[k] = x - hi[k];
-      }
-      tmem_st32(tl + XA, hi);
-      tmem_st32(tl + XA + 32, lo);
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    for (int k = 0; k < N; ++k) {
+      if (live) a.T_out[(size_t)k * a.ncol + col] = T[k];
+      const float x = ((cd.T_shift + T[k] * cd.inv_T_div) - cd.mu_T) * cd.inv_sig_T;
+      hi[k] = tf32_hi(x);
+      lo[k] = x - hi[k];
     }
-    const float T_top = T[N - 1];
-    if (!weights_ready) { mbar_wait(bar_w, 0); weights_ready = true; }
+    tmem_st32(tl + XA, hi);
+    tmem_st32(tl + XA + 32, lo);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    T_top = T[N - 1];
+  };
+
+  int it = 0;
+  if ((int)blockIdx.x < a.n_tiles && hh == 0) column_part(blockIdx.x);
+  mbar_wait(bar_w, 0);
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+    const int owner = it & 1;
     tc_fence_before();
     __syncthreads();
     // ---- layer 1 ----
@@ -233,6 +245,8 @@ __global__ void __launch_bounds__(CTC_NT, 1) closure_tc_kernel(const __grid_cons
       }
       __syncwarp();
     }
+    // while layer 2 runs: the other warp set prepares the next tile (layer 1 has released the X operand)
+    if (tile + (int)gridDim.x < a.n_tiles && hh == (owner ^ 1)) column_part(tile + gridDim.x);
     mbar_wait(bar_mma, par); par ^= 1u;
     tc_fence_after();
     hidden(C.n2, C.n1, C.act2);
@@ -250,7 +264,7 @@ __global__ void __launch_bounds__(CTC_NT, 1) closure_tc_kernel(const __grid_cons
     mbar_wait(bar_mma, par); par ^= 1u;
     tc_fence_after();
     // ---- wT = [0; inv(wT_scaling)(NN); surface_flux]; forcing = d(wT)/dz at centres (double_gyre_nn.jl:159-166,140-147) ----
-    {
+    if (hh == owner) {
       float nn[32];
       tmem_ld32(tl + D3, nn);
       const float* b3 = bias + C.n1 + C.n2;
@@ -266,11 +280,7 @@ __global__ void __launch_bounds__(CTC_NT, 1) closure_tc_kernel(const __grid_cons
         lo = hi;
       }
     }
-    tc_fence_before();
-    __syncthreads();  // the next tile overwrites the X operand and the accumulators
-    tc_fence_after();
   }
-  if (!weights_ready) mbar_wait(bar_w, 0);  // never leave with a bulk copy in flight
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512));

@@ -57,7 +57,7 @@ template <int ACT>
 static int launch_closure_tc_t(cpz_model* m, const ClosureTcD& C, const ClosureD& cd, ClosureArgs a) {
   auto kern = closure_tc_kernel<ACT>;
   CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C.img_bytes));
-  a.n_tiles = (a.ncol + CTC_NT - 1) / CTC_NT;
+  a.n_tiles = (a.ncol + CTC_TILE - 1) / CTC_TILE;
   const int grid = std::min(a.n_tiles, m->ctx->sm_count);
   kern<<<grid, CTC_NT, C.img_bytes, m->ctx->stream>>>(C, cd, a, m->b_cimg.p);
   CPZ_CUDA(cudaGetLastError());
