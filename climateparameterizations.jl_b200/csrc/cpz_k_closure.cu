@@ -5,6 +5,7 @@
 
 #include "cpz_launch.h"
 #include "cpz_closure_tc.cuh"
+#include "cpz_fc_tc.cuh"
 
 namespace cpz {
 
@@ -70,23 +71,60 @@ bool closure_uses_tc(const cpz_model* m) {
   return closure_tc_plan(m, C);
 }
 
+static int ensure_image(cpz_model* m, const ClosureTcD& C, const float* theta) {
+  const size_t need = (size_t)C.img_bytes / 4;
+  if (m->b_cimg.cap < need) {
+    if (m->b_cimg.p) cudaFree(m->b_cimg.p);
+    m->b_cimg.p = nullptr; m->b_cimg.cap = 0; m->cimg_ver = 0;
+    CPZ_CUDA(cudaMalloc(&m->b_cimg.p, need * sizeof(float)));
+    m->b_cimg.cap = need;
+  }
+  if (m->cimg_ver != m->theta_ver) {  // weights changed since the image was built
+    const int n_el = C.n1 * 32 + C.n2 * C.k2 + C.n3 * C.k3 + C.n1 + C.n2 + C.n3;
+    closure_tc_image_kernel<<<(n_el + 255) / 256, 256, 0, m->ctx->stream>>>(C, theta, m->b_cimg.p);
+    CPZ_CUDA(cudaGetLastError());
+    m->ctx->launches++;
+    m->cimg_ver = m->theta_ver;
+  }
+  return CPZ_OK;
+}
+
+template <int ACT>
+static int launch_fc_tc_t(cpz_model* m, const ClosureTcD& C, const SolveArgs& a) {
+  auto kern = solve_fc_tc_kernel<ACT>;
+  CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C.img_bytes));
+  const int n_tiles = (a.ncol + CTC_TILE - 1) / CTC_TILE;
+  kern<<<n_tiles, CTC_NT, C.img_bytes, m->ctx->stream>>>(C, m->fwd.M, m->tab, m->tm, a, m->b_cimg.p, m->b_fcscr.p);
+  CPZ_CUDA(cudaGetLastError());
+  m->ctx->launches++;
+  return CPZ_OK;
+}
+
+// T-only free-convection forward solve / RHS on tcgen05 (same net limits as the closure). 1 = not eligible.
+int launch_solve_fc_tc(cpz_model* m, const SolveArgs& a) {
+  ClosureTcD C;
+  if (m->desc.variant != CPZ_RHS_FREE_CONVECTION || !closure_tc_plan(m, C)) return 1;
+  int rc = ensure_image(m, C, a.theta);
+  if (rc) return rc;
+  const size_t n_tiles = (size_t)(a.ncol + CTC_TILE - 1) / CTC_TILE;
+  const size_t need = n_tiles * (size_t)m->tab.n_stages * 32 * CTC_TILE;
+  if (m->b_fcscr.cap < need) {
+    if (m->b_fcscr.p) cudaFree(m->b_fcscr.p);
+    m->b_fcscr.p = nullptr; m->b_fcscr.cap = 0;
+    CPZ_CUDA(cudaMalloc(&m->b_fcscr.p, need * sizeof(float)));
+    m->b_fcscr.cap = need;
+  }
+  const bool same = C.act1 == C.act2;
+  if (same && C.act1 == ACT_RELU) return launch_fc_tc_t<ACT_RELU>(m, C, a);
+  if (same && C.act1 == ACT_MISH) return launch_fc_tc_t<ACT_MISH>(m, C, a);
+  return launch_fc_tc_t<-1>(m, C, a);
+}
+
 int launch_closure(cpz_model* m, const ClosureD& cd, const ClosureArgs& a) {
   ClosureTcD C;
   if (closure_tc_plan(m, C)) {
-    const size_t need = (size_t)C.img_bytes / 4;
-    if (m->b_cimg.cap < need) {
-      if (m->b_cimg.p) cudaFree(m->b_cimg.p);
-      m->b_cimg.p = nullptr; m->b_cimg.cap = 0; m->cimg_ver = 0;
-      CPZ_CUDA(cudaMalloc(&m->b_cimg.p, need * sizeof(float)));
-      m->b_cimg.cap = need;
-    }
-    if (m->cimg_ver != m->theta_ver) {  // weights changed since the image was built
-      const int n_el = C.n1 * 32 + C.n2 * C.k2 + C.n3 * C.k3 + C.n1 + C.n2 + C.n3;
-      closure_tc_image_kernel<<<(n_el + 255) / 256, 256, 0, m->ctx->stream>>>(C, a.theta, m->b_cimg.p);
-      CPZ_CUDA(cudaGetLastError());
-      m->ctx->launches++;
-      m->cimg_ver = m->theta_ver;
-    }
+    const int rci = ensure_image(m, C, a.theta);
+    if (rci) return rci;
     const bool same = C.act1 == C.act2;
     if (same && C.act1 == ACT_RELU) return launch_closure_tc_t<ACT_RELU>(m, C, cd, a);
     if (same && C.act1 == ACT_MISH) return launch_closure_tc_t<ACT_MISH>(m, C, cd, a);

@@ -45,6 +45,8 @@ int launch_solve(cpz_model* m, const SolveArgs& a) {
     if (rc <= 0) return rc;
     rc = launch_solve_nnfree(m, a);  // NN-free u/v/T model
     if (rc <= 0) return rc;
+    rc = launch_solve_fc_tc(m, a);   // T-only free-convection nets
+    if (rc <= 0) return rc;
   }
   if (m->fwd.M.w_in_smem) return launch_solve_t<32, 256, true>(m, a);
   return launch_solve_t<32, 256, false>(m, a);

@@ -8,7 +8,9 @@
 namespace cpz {
 int launch_solve(cpz_model* m, const SolveArgs& a);
 int launch_solve_tc(cpz_model* m, const SolveArgs& a);
-int launch_solve_nnfree(cpz_model* m, const SolveArgs& a);  // NN-free u/v/T model; 1 = not eligible
+int launch_solve_nnfree(cpz_model* m, const SolveArgs& a);
+int launch_solve_fc_tc(cpz_model* m, const SolveArgs& a);   // T-only nets on tcgen05; 1 = not eligible
+bool closure_uses_tc(const cpz_model* m);  // NN-free u/v/T model; 1 = not eligible
 // one line for cpz_model_describe: which forward kernel this model runs on and why
 std::string tc_describe(const cpz_model* m);  // 1 = not eligible, use the SIMT kernel
 int launch_adjoint(cpz_model* m, const AdjArgs& a, int grid);
