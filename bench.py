@@ -392,6 +392,70 @@ def main():
             m0.close()
         except Exception as e:  # noqa: BLE001
             line["nn_free"] = {"error": repr(e)}
+        # ---- BASELINE config 4 slice: FreeConvectionNDE inference, 131072 columns per GPU (tcgen05, columns on the M side) ----
+        try:
+            NC4 = 131072
+            d4 = syn.free_convection_desc(ca=False, n_steps=NSTEPS, save_stride=9)
+            m4 = engine.Model(ctx, d4, syn.theta_init(d4, seed=42, scale=1e-5))
+            x4, b4 = syn.columns(d4, NC4, seed=1000 + rank)
+            x4_d, b4_d = torch.tensor(x4, device="cuda"), torch.tensor(b4, device="cuda")
+            t4_d = torch.empty((NC4, d4.n_saved, d4.S), dtype=torch.float32, device="cuda")
+            m4.solve_dev(x4_d, b4_d, t4_d)
+            barrier()
+            a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(2):
+                m4.solve_dev(x4_d, b4_d, t4_d)
+            a1.record()
+            barrier()
+            t4 = torch.tensor([a0.elapsed_time(a1)], device="cuda")
+            if dist is not None:
+                dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+            ms4 = float(t4.item()) / 2
+            macs4 = sum(n.macs for n in d4.nets)
+            line["free_convection"] = {
+                "metric": "column-steps/sec (forward, T-only FreeConvectionNDE)", "value": NC4 * NSTEPS * world / (ms4 * 1e-3),
+                "ms_per_step": ms4, "scaling": "weak",
+                "config": {"workload": "BASELINE config 4 slice: 131072 columns per GPU x 1152 steps, 32->128->128->31 relu, Tsit5, save every 9th frame",
+                           "kernel": m4.describe().splitlines()[0]},
+                "tensor_tflops_tf32_algorithmic": 3 * 2 * macs4 * d4.rhs_evals_per_step * NC4 * NSTEPS / (ms4 * 1e-3) / 1e12}
+            m4.close()
+        except Exception as e:  # noqa: BLE001
+            line["free_convection"] = {"error": repr(e)}
+        # ---- BASELINE config 5 slice: per-step closure on a 512 x 64 x 32 y-slab (one call per host-model step) ----
+        try:
+            from cpz_b200.desc import ClosureDesc
+            d5 = syn.free_convection_desc(ca=False)
+            m5 = engine.Model(ctx, d5, syn.theta_init(d5, seed=42, scale=1e-5))
+            nx5, ny5 = 512, 64
+            T5, y5 = syn.gyre_field(nx5, ny5, 32)
+            cd5 = ClosureDesc(Nx=nx5, Ny=ny5, Nz=32)
+            T5_d, y5_d = torch.tensor(T5, device="cuda"), torch.tensor(y5, device="cuda")
+            f5_d, o5_d = torch.empty_like(T5_d), torch.empty_like(T5_d)
+            for _ in range(20):
+                m5.closure_step_dev(cd5, T5_d, y5_d, f5_d, o5_d)
+            barrier()
+            n5 = 500
+            a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(n5):
+                m5.closure_step_dev(cd5, T5_d, y5_d, f5_d, o5_d)
+            a1.record()
+            barrier()
+            t5 = torch.tensor([a0.elapsed_time(a1)], device="cuda")
+            if dist is not None:
+                dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+            us5 = float(t5.item()) / n5 * 1e3
+            gb5 = 3 * nx5 * ny5 * 128 / (us5 * 1e-6) / 1e9
+            line["closure"] = {
+                "metric": "column-steps/sec (NN closure applied every host-model step)", "value": nx5 * ny5 * world / (us5 * 1e-6),
+                "us_per_call": us5, "scaling": "weak",
+                "config": {"workload": "BASELINE config 5 slice: 512 x 64 x 32 y-slab per GPU, implicit convective adjustment + NN forcing, T read / T' + forcing written every call"},
+                "roofline": {"bound": "hbm", "achieved": gb5, "peak": hbm_peak, "unit": "GB/s", "frac": gb5 / hbm_peak,
+                             "algorithmic_bytes_per_colstep": 384}}
+            m5.close()
+        except Exception as e:  # noqa: BLE001
+            line["closure"] = {"error": repr(e)}
     if rank == 0 and not args.no_extras:
         try:
             line["cpu_baseline"] = cpu_baseline(syn, RHS_INFER)

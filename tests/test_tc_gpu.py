@@ -137,3 +137,38 @@ def test_host_solve_chunked_pipeline_matches_single_launch(ctx, net):
     m.close()
     np.testing.assert_array_equal(host, traj.cpu().numpy())
     np.testing.assert_array_equal(host[:, 0], x0)
+
+
+@pytest.mark.parametrize("ncol", [1, 127, 128, 129, 300])
+@pytest.mark.parametrize("ca", [False, True])
+def test_fc_tcgen05_solve_ragged_sizes_and_simt_agreement(ctx, ncol, ca):
+    """T-only free-convection nets run on the tcgen05 kernel with the columns on the M side (128-column tiles)."""
+    d = syn.free_convection_desc(ca=ca, n_steps=27, save_stride=9)
+    th = syn.theta_random(d, scale=0.3)
+    x0, bcs = syn.columns(d, ncol)
+    m = engine.Model(ctx, d, th)
+    assert "forward kernel: tcgen05" in m.describe(), m.describe()
+    got = m.solve(x0, bcs)
+    dx = m.rhs(x0, bcs, t=0.0)
+    with _simt():
+        simt = m.solve(x0, bcs)
+    m.close()
+    ref = oracle_solve(d, th, x0, bcs)
+    e_tc, e_simt = rel_inf(got, ref), rel_inf(simt, ref)
+    e_rhs = rel_inf(dx, oracle_rhs(d, th, x0, bcs, 0.0))
+    print(f"fc ncol={ncol} ca={ca}: tcgen05 solve {e_tc:.2e} (simt {e_simt:.2e})  rhs {e_rhs:.2e}")
+    np.testing.assert_array_equal(got[:, 0], x0)
+    assert e_rhs <= 1e-5 and e_tc <= 1e-4
+
+
+@pytest.mark.parametrize("h1,h2,act", [(128, 128, "mish"), (40, 72, "tanh"), (16, 16, "relu")])
+def test_fc_tcgen05_net_shapes(ctx, h1, h2, act):
+    d = syn.free_convection_desc(ca=True, n_steps=18, save_stride=9, net=None)
+    d.nets = [NetDesc([32, h1, h2, 31], [act, act, "identity"])]
+    th = syn.theta_random(d, scale=0.5)
+    x0, bcs = syn.columns(d, 200)
+    m = engine.Model(ctx, d, th)
+    assert "forward kernel: tcgen05" in m.describe()
+    got = m.solve(x0, bcs)
+    m.close()
+    assert rel_inf(got, oracle_solve(d, th, x0, bcs)) <= 1e-4
