@@ -456,7 +456,7 @@ def main():
             m5.close()
         except Exception as e:  # noqa: BLE001
             line["closure"] = {"error": repr(e)}
-    if rank == 0 and not args.no_extras:
+    if rank == 0 and world == 1 and not args.no_extras:  # the CPU baseline is reported at N = 1 only
         try:
             line["cpu_baseline"] = cpu_baseline(syn, RHS_INFER)
         except Exception as e:  # noqa: BLE001
