@@ -172,3 +172,19 @@ def test_fc_tcgen05_net_shapes(ctx, h1, h2, act):
     got = m.solve(x0, bcs)
     m.close()
     assert rel_inf(got, oracle_solve(d, th, x0, bcs)) <= 1e-4
+
+
+def test_fc_host_solve_chunked_pipeline_matches_single_launch(ctx):
+    """The time-chunked host solve (>= 64 MB of trajectory) restarts the T-only tcgen05 kernel from trajectory frames."""
+    d = syn.free_convection_desc(ca=True, n_steps=72, save_stride=1)
+    th = syn.theta_random(d, scale=0.3)
+    ncol = 8192 + 5
+    x0, bcs = syn.columns(d, ncol)
+    m = engine.Model(ctx, d, th)
+    host = m.solve(x0, bcs)   # 8197 x 73 x 32 floats = 76.6 MB -> chunked
+    x0d, bcsd = torch.tensor(x0, device="cuda"), torch.tensor(bcs, device="cuda")
+    traj = torch.empty((ncol, d.n_saved, d.S), device="cuda")
+    m.solve_dev(x0d, bcsd, traj)
+    ctx.synchronize()
+    m.close()
+    np.testing.assert_array_equal(host, traj.cpu().numpy())
