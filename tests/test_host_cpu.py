@@ -119,3 +119,41 @@ def test_shard_columns_partitions_exactly():
         assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
         sizes = [hi - lo for lo, hi in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+# ---- data path: mirrors the reference's own test/test_coarse_graining.jl:1-36 ------------------------
+def test_coarse_grain_center_matches_reference_test():
+    from cpz_b200.ocean_parameterizations import Center, coarse_grain
+    y = 0.5 * np.arange(1, 101) - 3.0
+    yc = coarse_grain(y, 20, Center)
+    assert len(yc) == 20
+    assert np.allclose(np.diff(yc), np.diff(yc)[0])
+    assert np.isclose(y.mean(), yc.mean())
+    with pytest.raises(ValueError):
+        coarse_grain(y, 30, Center)
+
+
+def test_coarse_grain_linear_interpolation_face_matches_reference_test():
+    from cpz_b200.ocean_parameterizations import Face, coarse_grain_linear_interpolation
+    x = np.arange(1, 101)
+    y_lin, y_quad = 0.5 * x - 3.0, 0.5 * x ** 2 - 3.0 * x + 5.0
+    yc = coarse_grain_linear_interpolation(y_lin, 20, Face)
+    yq = coarse_grain_linear_interpolation(y_quad, 20, Face)
+    assert len(yc) == 20 and len(yq) == 20
+    assert np.allclose(np.diff(yc), np.diff(yc)[0])
+    assert np.isclose(y_lin.mean(), yc.mean())
+    assert yc[0] == y_lin[0] and yc[-1] == y_lin[-1]
+    # 129 -> 33 faces of the LES regridding (data_containers.jl:343-427): every 4th face exactly
+    f = np.linspace(-256.0, 0.0, 129)
+    assert np.allclose(coarse_grain_linear_interpolation(f, 33, Face), f[::4])
+
+
+def test_coarse_grain_face_preserves_end_points_and_block_means():
+    from cpz_b200.ocean_parameterizations import Face, coarse_grain
+    y = np.arange(1.0, 131.0)            # N = 130: (N-2)/(n-2) = 128/32 = 4 exactly
+    yc = coarse_grain(y, 34, Face)
+    assert yc[0] == 1.0 and yc[-1] == 130.0
+    assert np.allclose(yc[1:-1], y[1:-1].reshape(32, 4).mean(axis=1))
+    z = np.arange(1.0, 102.0)            # N = 101, n = 12: non-integer ratio -> rounded windows
+    zc = coarse_grain(z, 12, Face)
+    assert zc[0] == 1.0 and zc[-1] == 101.0 and np.all(np.diff(zc) > 0)
