@@ -10,22 +10,28 @@
 
 namespace cpz {
 
+// Two 128-column tiles per CTA, one per warp set (4 warps each), run half a phase apart: while one set's tile is in its MLP
+// section (operands and accumulators in TMEM: hidden activations hi [0,128) lo [128,256), accumulators [256,384); the
+// stage input X sits in the first 32 columns of the activation planes, the layer-3 accumulator in the first 32
+// accumulator columns), the other set does its column work in registers (flux divergence, Runge-Kutta combination
+// against the global stage slots, frame stores). Phases are separated by CTA barriers; TMEM is owned by one set per phase.
 template <int ACT>
 __global__ void __launch_bounds__(CTC_NT, 1) solve_fc_tc_kernel(const __grid_constant__ ClosureTcD C, const __grid_constant__ ModelD M,
                                                                 const __grid_constant__ TableauD tab, const TimeD tm, const SolveArgs a,
                                                                 const float* __restrict__ img, float* __restrict__ kscr) {
   extern __shared__ __align__(1024) uint8_t sm[];
-  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ __align__(8) uint64_t bars[3];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int hh = warp >> 2;
-  const int ltid = tid & 127;
+  const int set = warp >> 2;       // warp set = tile of the pair
+  const int ltid = tid & 127;      // column / TMEM lane inside the tile
   constexpr int N = 32;
   uint64_t* bar_w = &bars[0];
-  uint64_t* bar_mma = &bars[1];
+  uint64_t* bar_mma = &bars[1 + set];
   if (tid == 0) {
-    mbar_init(bar_w, 1);
-    mbar_init(bar_mma, 1);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -41,9 +47,10 @@ __global__ void __launch_bounds__(CTC_NT, 1) solve_fc_tc_kernel(const __grid_con
     for (int o = 0; o < C.img_bytes; o += 32768) bulk_g2s(sm + o, reinterpret_cast<const char*>(img) + o, (uint32_t)min(32768, C.img_bytes - o), bar_w);
   }
   const uint32_t tl = tb + ((uint32_t)(32 * (warp & 3)) << 16);
-  const uint32_t XA = 0, D12 = 64, HAh = 192, HAl = 320, D3 = 448;
+  const uint32_t HAh = 0, HAl = 128, D12 = 256;
   const float* bias = reinterpret_cast<const float*>(sm + C.o_b);
   uint32_t par = 0;
+  const int set_bar = 1 + set;  // named barrier of this warp set (128 threads)
 
   auto chain = [&](uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t bh_off, uint32_t bl_off, int K, int n) {
     const uint32_t id = tc_idesc(128, n);
@@ -58,7 +65,7 @@ __global__ void __launch_bounds__(CTC_NT, 1) solve_fc_tc_kernel(const __grid_con
     for (int s = 0; s < steps; ++s) tc_mma_ts(d, a_hi + 8 * s, bh + 16 * s, id, 1);
   };
   auto hidden = [&](int n_cols, int b_off, int act) {
-    for (int j = 32 * hh; j < n_cols; j += 64) {
+    for (int j = 0; j < n_cols; j += 32) {
       float v[32], lo[32];
       tmem_ld32(tl + D12 + j, v);
 #pragma unroll
@@ -74,12 +81,14 @@ __global__ void __launch_bounds__(CTC_NT, 1) solve_fc_tc_kernel(const __grid_con
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   };
   auto mma_layer = [&](int layer) {
-    if (warp == 0) {
+    tc_fence_before();
+    bar_sync_named(set_bar, 128);
+    if ((warp & 3) == 0) {
       tc_fence_after();
       if (elect_one()) {
-        if (layer == 0) chain(tb + D12, tb + XA, tb + XA + 32, C.o_w1h, C.o_w1l, 32, C.n1);
+        if (layer == 0) chain(tb + D12, tb + HAh, tb + HAl, C.o_w1h, C.o_w1l, 32, C.n1);
         else if (layer == 1) chain(tb + D12, tb + HAh, tb + HAl, C.o_w2h, C.o_w2l, C.k2, C.n2);
-        else chain(tb + D3, tb + HAh, tb + HAl, C.o_w3h, C.o_w3l, C.k3, C.n3);
+        else chain(tb + D12, tb + HAh, tb + HAl, C.o_w3h, C.o_w3l, C.k3, C.n3);
         tc_commit(bar_mma);
       }
       __syncwarp();
@@ -89,80 +98,73 @@ __global__ void __launch_bounds__(CTC_NT, 1) solve_fc_tc_kernel(const __grid_con
   };
 
   // ---- this thread's column ----
-  const int tile = blockIdx.x;
+  const int tile = 2 * blockIdx.x + set;
   const int col = tile * CTC_TILE + ltid;
   const int colc = min(col, a.ncol - 1);
-  const bool own = hh == 0;
-  const bool live = own && col < a.ncol;
+  const bool live = col < a.ncol;
   const size_t xs = a.x0_stride ? a.x0_stride : (size_t)N;
   float x[N], X[N];
-  float bc_b = 0.f, bc_t = 0.f;
-  if (own) {
 #pragma unroll
-    for (int k4 = 0; k4 < N / 4; ++k4) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(a.x0 + (size_t)colc * xs) + k4);
-      x[4 * k4] = v.x; x[4 * k4 + 1] = v.y; x[4 * k4 + 2] = v.z; x[4 * k4 + 3] = v.w;
-    }
-    bc_b = __ldg(a.bcs + (size_t)colc * 2);
-    bc_t = __ldg(a.bcs + (size_t)colc * 2 + 1);
-  } else {
-#pragma unroll
-    for (int k = 0; k < N; ++k) x[k] = 0.f;
+  for (int k4 = 0; k4 < N / 4; ++k4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(a.x0 + (size_t)colc * xs) + k4);
+    x[4 * k4] = v.x; x[4 * k4 + 1] = v.y; x[4 * k4 + 2] = v.z; x[4 * k4 + 3] = v.w;
   }
+  const float bc_b = __ldg(a.bcs + (size_t)colc * 2), bc_t = __ldg(a.bcs + (size_t)colc * 2 + 1);
 #pragma unroll
   for (int k = 0; k < N; ++k) X[k] = x[k];
   const bool ca = (M.flags & F_CA) != 0;
   const float ANf = M.rc.A[2] * M.rc.Nf, Nf = M.rc.Nf, Kca = M.rc.K_ca;
   mbar_wait(bar_w, 0);
+  __syncthreads();
 
-  // one RHS evaluation at X: dx[k] = -A Nz (E[k+1] - E[k]), E = [bottom; NN(X) - [CA] min(0, K dT/dz); top]
-  auto rhs = [&](float (&dx)[N]) {
-    if (own) {
+  // MLP section (this set owns TMEM): X -> three layers -> NN fluxes in registers
+  auto mlp = [&](float (&nn)[32]) {
+    {
       float hi[N], lo[N];
 #pragma unroll
       for (int k = 0; k < N; ++k) { hi[k] = tf32_hi(X[k]); lo[k] = X[k] - hi[k]; }
-      tmem_st32(tl + XA, hi);
-      tmem_st32(tl + XA + 32, lo);
+      tmem_st32(tl + HAh, hi);
+      tmem_st32(tl + HAl, lo);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
-    tc_fence_before();
-    __syncthreads();
     mma_layer(0);
     hidden(C.n1, 0, C.act1);
-    tc_fence_before();
-    __syncthreads();
     mma_layer(1);
     hidden(C.n2, C.n1, C.act2);
-    tc_fence_before();
-    __syncthreads();
     mma_layer(2);
-    if (own) {
-      float nn[32];
-      tmem_ld32(tl + D3, nn);
-      const float* b3 = bias + C.n1 + C.n2;
-      float Elo = bc_b;
+    tmem_ld32(tl + D12, nn);
+    tc_fence_before();
+  };
+  // dx[k] = -A Nz (E[k+1] - E[k]), E = [bottom; NN(X) - [CA] min(0, K dT/dz); top]
+  auto tendencies = [&](const float (&nn)[32], float (&dx)[N]) {
+    const float* b3 = bias + C.n1 + C.n2;
+    float Elo = bc_b;
 #pragma unroll
-      for (int k = 0; k < N; ++k) {
-        float Ehi;
-        if (k == N - 1) Ehi = bc_t;
-        else {
-          Ehi = nn[k] + b3[k];                                                  // face k+1
-          if (ca) Ehi -= fminf(0.f, Kca * (Nf * (X[k + 1] - X[k])));
-        }
-        dx[k] = -ANf * (Ehi - Elo);
-        Elo = Ehi;
+    for (int k = 0; k < N; ++k) {
+      float Ehi;
+      if (k == N - 1) Ehi = bc_t;
+      else {
+        Ehi = nn[k] + b3[k];
+        if (ca) Ehi -= fminf(0.f, Kca * (Nf * (X[k + 1] - X[k])));
       }
+      dx[k] = -ANf * (Ehi - Elo);
+      Elo = Ehi;
     }
   };
+  auto phase_bar = [&]() { __syncthreads(); tc_fence_after(); };
 
+  if (set == 1) phase_bar();  // set 1 runs one phase behind set 0
   if (a.rhs_only) {
-    float dx[N];
-    rhs(dx);
+    float nn[32], dx[N];
+    mlp(nn);
+    phase_bar();
+    tendencies(nn, dx);
     if (live) {
 #pragma unroll
       for (int k4 = 0; k4 < N / 4; ++k4)
         reinterpret_cast<float4*>(a.dxdt + (size_t)col * N)[k4] = make_float4(dx[4 * k4], dx[4 * k4 + 1], dx[4 * k4 + 2], dx[4 * k4 + 3]);
     }
+    phase_bar();
   } else {
     const float h = tm.dt / (float)tm.n_substeps;
     const int ns = tab.n_stages;
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(CTC_NT, 1) solve_fc_tc_kernel(const __grid_con
       }
     };
     auto save_ckpt = [&](int c) {  // adjoint tile layout: [tile of 32 columns][n_ckpt][S][32]
-      if (own && col < ((a.ncol + 31) & ~31)) {  // the adjoint's 32-column tiles, padded columns replicate the last one
+      if (col < ((a.ncol + 31) & ~31)) {
         const int t32 = col >> 5, ct = col & 31;
 #pragma unroll
         for (int k = 0; k < N; ++k) a.ckpt[(((size_t)t32 * a.n_ckpt + c) * N + k) * 32 + ct] = x[k];
@@ -189,39 +191,45 @@ __global__ void __launch_bounds__(CTC_NT, 1) solve_fc_tc_kernel(const __grid_con
       for (int sub = 0; sub < tm.n_substeps; ++sub) {
 #pragma unroll 1
         for (int i = 0; i < ns; ++i) {
+          float nn[32];
+          mlp(nn);
+          phase_bar();
+          // ---- column work, overlapped with the other set's MLP section ----
           float dx[N];
-          rhs(dx);
-          if (own) {
-            const bool last = (i + 1 == ns);
-            float acc[N];
-            const float ci_ = last ? tab.b[i] : tab.a[(i + 1) % CPZ_MAX_STAGES][i];
+          tendencies(nn, dx);
+          const bool last = (i + 1 == ns);
+          float acc[N];
+          const float ci_ = last ? tab.b[i] : tab.a[(i + 1) % CPZ_MAX_STAGES][i];
 #pragma unroll
-            for (int k = 0; k < N; ++k) acc[k] = ci_ * dx[k];
+          for (int k = 0; k < N; ++k) acc[k] = ci_ * dx[k];
 #pragma unroll 1
-            for (int j = 0; j < i; ++j) {
-              const float cj = last ? tab.b[j] : tab.a[(i + 1) % CPZ_MAX_STAGES][j];
-              const float* kj = ks + (size_t)j * N * CTC_TILE;
+          for (int j = 0; j < i; ++j) {
+            const float cj = last ? tab.b[j] : tab.a[(i + 1) % CPZ_MAX_STAGES][j];
+            const float* kj = ks + (size_t)j * N * CTC_TILE;
 #pragma unroll
-              for (int k = 0; k < N; ++k) acc[k] = fmaf(cj, kj[k * CTC_TILE], acc[k]);
-            }
-            if (!last) {
-              float* ki = ks + (size_t)i * N * CTC_TILE;
+            for (int k = 0; k < N; ++k) acc[k] = fmaf(cj, kj[k * CTC_TILE], acc[k]);
+          }
+          if (!last) {
+            float* ki = ks + (size_t)i * N * CTC_TILE;
 #pragma unroll
-              for (int k = 0; k < N; ++k) { ki[k * CTC_TILE] = dx[k]; X[k] = fmaf(h, acc[k], x[k]); }
-            } else {
+            for (int k = 0; k < N; ++k) { ki[k * CTC_TILE] = dx[k]; X[k] = fmaf(h, acc[k], x[k]); }
+          } else {
 #pragma unroll
-              for (int k = 0; k < N; ++k) { x[k] = fmaf(h, acc[k], x[k]); X[k] = x[k]; }
+            for (int k = 0; k < N; ++k) { x[k] = fmaf(h, acc[k], x[k]); X[k] = x[k]; }
+            if (sub + 1 == tm.n_substeps) {
+              const int step = n + 1;
+              const bool do_save = a.traj != nullptr && ((tm.save_stride > 0 && step % tm.save_stride == 0) ||
+                                                          (tm.save_stride <= 0 && step == tm.n_steps));
+              if (do_save) { save_frame(frame); ++frame; }
+              if (a.ckpt != nullptr && (step % tm.ckpt_stride == 0 || step == tm.n_steps)) { save_ckpt(ci); ++ci; }
             }
           }
+          phase_bar();
         }
       }
-      const int step = n + 1;
-      const bool do_save = a.traj != nullptr && ((tm.save_stride > 0 && step % tm.save_stride == 0) ||
-                                                  (tm.save_stride <= 0 && step == tm.n_steps));
-      if (do_save) { save_frame(frame); ++frame; }
-      if (a.ckpt != nullptr && (step % tm.ckpt_stride == 0 || step == tm.n_steps)) { save_ckpt(ci); ++ci; }
     }
   }
+  if (set == 0) phase_bar();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512));

@@ -94,7 +94,7 @@ static int launch_fc_tc_t(cpz_model* m, const ClosureTcD& C, const SolveArgs& a)
   auto kern = solve_fc_tc_kernel<ACT>;
   CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C.img_bytes));
   const int n_tiles = (a.ncol + CTC_TILE - 1) / CTC_TILE;
-  kern<<<n_tiles, CTC_NT, C.img_bytes, m->ctx->stream>>>(C, m->fwd.M, m->tab, m->tm, a, m->b_cimg.p, m->b_fcscr.p);
+  kern<<<(n_tiles + 1) / 2, CTC_NT, C.img_bytes, m->ctx->stream>>>(C, m->fwd.M, m->tab, m->tm, a, m->b_cimg.p, m->b_fcscr.p);
   CPZ_CUDA(cudaGetLastError());
   m->ctx->launches++;
   return CPZ_OK;
@@ -106,7 +106,7 @@ int launch_solve_fc_tc(cpz_model* m, const SolveArgs& a) {
   if (m->desc.variant != CPZ_RHS_FREE_CONVECTION || !closure_tc_plan(m, C)) return 1;
   int rc = ensure_image(m, C, a.theta);
   if (rc) return rc;
-  const size_t n_tiles = (size_t)(a.ncol + CTC_TILE - 1) / CTC_TILE;
+  const size_t n_tiles = 2 * (((size_t)(a.ncol + CTC_TILE - 1) / CTC_TILE + 1) / 2);  // tile pairs
   const size_t need = n_tiles * (size_t)m->tab.n_stages * 32 * CTC_TILE;
   if (m->b_fcscr.cap < need) {
     if (m->b_fcscr.p) cudaFree(m->b_fcscr.p);
