@@ -104,7 +104,7 @@ std::string tc_describe(const cpz_model* m) {
 template <int ACT, int K3S>
 static int launch_tc_t(cpz_model* m, const TcD& T, const SolveArgs& a, const TcArgs& ta) {
   const TcSmem L = tc_smem_layout(T, m->tab.n_stages);
-  auto kern = solve_tc_kernel<ACT, K3S>;
+  auto kern = a.rhs_only ? solve_tc_kernel<ACT, K3S, false, true> : solve_tc_kernel<ACT, K3S, false, false>;
   CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
   const int n_tiles = (a.ncol + TC_CT - 1) / TC_CT;
   if (getenv("CPZ_TC_PROF") != nullptr && !a.rhs_only) {  // debug: per-phase cycle counters of CTA 0

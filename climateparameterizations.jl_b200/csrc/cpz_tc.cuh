@@ -240,7 +240,11 @@ __device__ __forceinline__ void side_column(const SideC& C, float du, float dv, 
 }
 
 // ---- the solve kernel ---------------------------------------------------------------------------------------------
-template <int ACT, int K3S, bool PROF = false>  // ACT: shared hidden activation (-1: T.act1/T.act2 at run time); K3S: layer-3 K steps
+// out of line: the full-range sinf keeps its slow path (and local-memory table) away from the hot loop
+static __device__ __noinline__ float tc_diurnal_top(const ModelD& M, float Q, float t) { return diurnal_top_eff(M, Q, t); }
+
+// ACT: shared hidden activation (-1: T.act1/T.act2 at run time); K3S: layer-3 K steps; RHS_ONLY: single evaluation (cpz_rhs)
+template <int ACT, int K3S, bool PROF = false, bool RHS_ONLY = false>
 __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constant__ ModelD M, const __grid_constant__ TcD T,
                                                             const __grid_constant__ TableauD tab, const TimeD tm,
                                                             const SolveArgs a, const TcArgs ta) {
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
     if (diurnal && qd == 2 && lane == 31) {
       const float* Qs = reinterpret_cast<const float*>(smem_tc + g * L.grp_bytes + L.bc) + 8 * h;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) bnd[r] = diurnal_top_eff(M, Qs[r], t_stage);
+      for (int r = 0; r < 8; ++r) bnd[r] = tc_diurnal_top(M, Qs[r], t_stage);
     }
     // ---- layer 1 epilogue ----
     mbar_wait(mbar, parity); parity ^= 1u;
@@ -527,7 +531,7 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
     tick(6);
   };
 
-  if (a.rhs_only) {
+  if constexpr (RHS_ONLY) {
     write_X();
     float dx[8];
     rhs_eval(a.t_rhs, dx);
