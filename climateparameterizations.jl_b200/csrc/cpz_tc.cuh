@@ -160,9 +160,10 @@ __device__ __forceinline__ float tc_act(int act_rt, float x) {
 }
 
 // split 8 values (columns 8h..8h+7 of one operand row) into tf32 hi + residual lo and store them (16 B apart)
+template <int CNT = 8>
 __device__ __forceinline__ void store_row_hilo(uint32_t hi_addr, uint32_t lo_addr, const float* v) {
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
+  for (int r = 0; r < CNT; ++r) {
     const float hi = tf32_hi(v[r]);
     sts_f32(hi_addr + 16 * r, hi);
     sts_f32(lo_addr + 16 * r, v[r] - hi);
@@ -244,7 +245,8 @@ __device__ __forceinline__ void side_column(const SideC& C, float du, float dv, 
 static __device__ __noinline__ float tc_diurnal_top(const ModelD& M, float Q, float t) { return diurnal_top_eff(M, Q, t); }
 
 // ACT: shared hidden activation (-1: T.act1/T.act2 at run time); K3S: layer-3 K steps; RHS_ONLY: single evaluation (cpz_rhs)
-template <int ACT, int K3S, bool PROF = false, bool RHS_ONLY = false>
+// CPT: real columns per thread (8, or 7 so that 4 096 columns make 147 tiles of 28 and use every SM; the 8th slot is padding)
+template <int ACT, int K3S, bool PROF = false, bool RHS_ONLY = false, int CPT = 8>
 __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constant__ ModelD M, const __grid_constant__ TcD T,
                                                             const __grid_constant__ TableauD tab, const TimeD tm,
                                                             const SolveArgs a, const TcArgs ta) {
@@ -256,8 +258,8 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
   const uint32_t gbase = sbase + g * L.grp_bytes;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_tc + L.misc) + g;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_tc + L.misc + 64);
-  const int tile = blockIdx.x, col0 = tile * TC_CT;
-  const int cg0 = TC_GN * g + 8 * h;  // first of this thread's 8 columns inside the tile
+  const int tile = blockIdx.x, col0 = tile * (4 * CPT);
+  const int cg0 = 2 * CPT * g + CPT * h;  // first of this thread's CPT columns inside the tile
 
   // ---- prologue: zero shared memory, barriers, TMEM allocation, weights -> TMEM ----
   for (int i = tid; i < L.total / 16; i += TC_NT) reinterpret_cast<float4*>(smem_tc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -302,7 +304,9 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
   float x[8], X[8], bnd[8];
   const bool diurnal = (M.flags & F_DIURNAL) != 0;
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
+  for (int r = 0; r < 8; ++r) { x[r] = 0.f; X[r] = 0.f; bnd[r] = 0.f; }
+#pragma unroll
+  for (int r = 0; r < CPT; ++r) {
     const int col = min(col0 + cg0 + r, a.ncol - 1);
     x[r] = qd < 3 ? __ldg(a.x0 + (size_t)col * (a.x0_stride ? a.x0_stride : (size_t)96) + 32 * qd + lane) : 0.f;
     X[r] = x[r];
@@ -341,7 +345,7 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
 
   auto write_X = [&]() {  // stage input -> B operand (hi/lo) + full-precision copy
     if (qd < 3) {
-      store_row_hilo(gbase + L.xh + xb, gbase + L.xl + xb, X);
+      store_row_hilo<CPT>(gbase + L.xh + xb, gbase + L.xl + xb, X);
       sts_v4(side_addr(3 + qd, 2 * h), X[0], X[1], X[2], X[3]);
       sts_v4(side_addr(3 + qd, 2 * h + 1), X[4], X[5], X[6], X[7]);
     }
@@ -432,7 +436,7 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
     if (diurnal && qd == 2 && lane == 31) {
       const float* Qs = reinterpret_cast<const float*>(smem_tc + g * L.grp_bytes + L.bc) + 8 * h;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) bnd[r] = tc_diurnal_top(M, Qs[r], t_stage);
+      for (int r = 0; r < CPT; ++r) bnd[r] = tc_diurnal_top(M, Qs[r], t_stage);
     }
     // ---- layer 1 epilogue ----
     mbar_wait(mbar, parity); parity ^= 1u;
@@ -444,15 +448,15 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
       tmem_ld8(dg + ((uint32_t)(32 * qd) << 16) + 8 * h, v);
       tick(12);
 #pragma unroll
-      for (int r = 0; r < 8; ++r) v[r] = tc_act<ACT>(act1, v[r] + b1a);
-      store_row_hilo(gbase + L.h1h + h1a, gbase + L.h1l + h1a, v);
+      for (int r = 0; r < CPT; ++r) v[r] = tc_act<ACT>(act1, v[r] + b1a);
+      store_row_hilo<CPT>(gbase + L.h1h + h1a, gbase + L.h1l + h1a, v);
       tick(13);
       if (qd == 3 && T.n1b > 0) {
         tmem_ld8(dg + ((uint32_t)96 << 16) + 16 + 8 * h, v);
         if (lane < T.n1b) {
 #pragma unroll
-          for (int r = 0; r < 8; ++r) v[r] = tc_act<ACT>(act1, v[r] + b1b);
-          store_row_hilo(gbase + L.h1h + h1b, gbase + L.h1l + h1b, v);
+          for (int r = 0; r < CPT; ++r) v[r] = tc_act<ACT>(act1, v[r] + b1b);
+          store_row_hilo<CPT>(gbase + L.h1h + h1b, gbase + L.h1l + h1b, v);
         }
       }
     }
@@ -486,8 +490,8 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
       tmem_ld8(dg + ((uint32_t)(32 * qd) << 16) + 16 * qd + 8 * h, v);
       if (lane < T.h2) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) v[r] = tc_act<ACT>(act2, v[r] + b2);
-        store_row_hilo(gbase + L.h2h + h2a, gbase + L.h2l + h2a, v);
+        for (int r = 0; r < CPT; ++r) v[r] = tc_act<ACT>(act2, v[r] + b2);
+        store_row_hilo<CPT>(gbase + L.h2h + h2a, gbase + L.h2l + h2a, v);
       }
     }
     fence_proxy_async();
@@ -519,7 +523,7 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
       tmem_ld8(dg + ((uint32_t)(32 * qd) << 16) + 16 * qd + 8 * h, nn);
       lds8(side_addr(qd, 2 * h), side_addr(qd, 2 * h + 1), D);
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
+      for (int r = 0; r < CPT; ++r) {
         const float dq = __shfl_down_sync(0xffffffffu, X[r], 1) - X[r];
         float Fup = fmaf(-D[r], dq, nn[r] + b3);
         if (lane == 31) Fup = bnd[r];
@@ -534,10 +538,11 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
   if constexpr (RHS_ONLY) {
     write_X();
     float dx[8];
+    dx[7] = 0.f;
     rhs_eval(a.t_rhs, dx);
     if (qd < 3) {
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
+      for (int r = 0; r < CPT; ++r) {
         const int col = col0 + cg0 + r;
         if (col < a.ncol) a.dxdt[(size_t)col * 96 + 32 * qd + lane] = dx[r];
       }
@@ -550,7 +555,7 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
     auto save_frame = [&](int fr) {
       if (qd < 3) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < CPT; ++r) {
           const int col = col0 + cg0 + r;
           if (col < a.ncol) a.traj[(size_t)col * traj_stride + (size_t)fr * 96 + 32 * qd + lane] = x[r];
         }
@@ -575,13 +580,14 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
 #pragma unroll 1
         for (int i = 0; i < ns; ++i) {
           float dx[8];
+          dx[7] = 0.f;
           rhs_eval(tbase + tab.c[i] * hstep, dx);
           if (qd < 3) {
             const bool last = (i + 1 == ns);
             float acc[8];
             const float ci_ = last ? tab.b[i] : tab.a[(i + 1) % CPZ_MAX_STAGES][i];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) acc[r] = ci_ * dx[r];
+            for (int r = 0; r < 8; ++r) acc[r] = r < CPT ? ci_ * dx[r] : 0.f;
 #pragma unroll 1
             for (int j = 0; j < i; ++j) {
               const float cj = last ? tab.b[j] : tab.a[(i + 1) % CPZ_MAX_STAGES][j];
@@ -593,10 +599,10 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
               sts_v4(ks_base + i * ks_stride, dx[0], dx[1], dx[2], dx[3]);
               sts_v4(ks_base + i * ks_stride + 16, dx[4], dx[5], dx[6], dx[7]);
 #pragma unroll
-              for (int r = 0; r < 8; ++r) X[r] = fmaf(hstep, acc[r], x[r]);
+              for (int r = 0; r < CPT; ++r) X[r] = fmaf(hstep, acc[r], x[r]);
             } else {
 #pragma unroll
-              for (int r = 0; r < 8; ++r) { x[r] = fmaf(hstep, acc[r], x[r]); X[r] = x[r]; }
+              for (int r = 0; r < CPT; ++r) { x[r] = fmaf(hstep, acc[r], x[r]); X[r] = x[r]; }
             }
             write_X();
           }
