@@ -32,7 +32,7 @@ NSTEPS = 1152
 FP32_LANES_PER_SM = 128
 # dram__bytes_read.sum + dram__bytes_write.sum of one solve_tc_kernel launch at the bench configuration, from the ncu --set full
 # capture summarised in profiles/ (None until captured)
-TRAFFIC_NCU_BYTES = 1.772e9  # 12.0 MB read + 1.7605 GB written (profiles/r01_tc_solve_ncu_summary.txt)
+TRAFFIC_NCU_BYTES = 1.769e9  # 10.9 MB read + 1.7584 GB written (profiles/r01_tc_solve_ncu_summary.txt)
 
 
 def peaks():
@@ -301,10 +301,10 @@ def main():
                     "algorithmic_flop_per_colstep": 3 * 2 * mlp_macs * d.rhs_evals_per_step,
                     "frac_of_tf32_peak": 2 * ach_tensor / bf16_peak,
                     "issued_tflops_incl_padding": issued_flops / (kern_ms * 1e-3) / 1e12,
-                    "pipe_tensor_active_pct_ncu": 43.0,
+                    "pipe_tensor_active_pct_ncu": 44.7,
                     "note": "3xTF32 on tcgen05 with M=128 x N=16 x K=8 MMAs; padding of the 150/60/93 output rows to 128-row "
                             "blocks makes issued flops 2.9x the algorithmic ones; the kernel is latency-bound (ncu: tensor pipe "
-                            "active 43 %, issue slots 45 %), see profiles/r01_tc_solve_ncu_summary.txt"}
+                            "active 45 %, issue slots 43 %), see profiles/r01_tc_solve_ncu_summary.txt"}
     else:
         roofline = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": None,
                     "peak_source": peak_src, "kernel": "solve_kernel<32,256,true>", "kernel_ms": kern_ms,
