@@ -317,6 +317,7 @@ def main():
                    "Nz": 32, "columns_per_gpu": NCOL, "n_steps": NSTEPS, "n_substeps": d.n_substeps, "integrator": d.integrator,
                    "rhs_evals_per_step": d.rhs_evals_per_step, "nets": "3 x (96->50 mish->20 mish->31), P=19563",
                    "rhs": "inference (solve_NDE_mutating), mPP base, zero_weights BCs",
+                   "arithmetic": "FP32 state/stencil/Runge-Kutta; MLP as 3xTF32 on tcgen05 (hi/lo operand split, FP32 accumulate in TMEM), RHS within 6e-7 of the FP64 oracle",
                    "l2": "no explicit flush: each solve writes a 1.81 GB trajectory (> 126 MB L2)", "parallelism": f"columns x{world}"},
         "gpu_launches": int(launches),
         "clocks": clocks,
