@@ -18,7 +18,7 @@ namespace cpz {
 template <int ACT>
 __global__ void __launch_bounds__(CTC_NT, 1) solve_fc_tc_kernel(const __grid_constant__ ClosureTcD C, const __grid_constant__ ModelD M,
                                                                 const __grid_constant__ TableauD tab, const TimeD tm, const SolveArgs a,
-                                                                const float* __restrict__ img, float* __restrict__ kscr) {
+                                                                const float* __restrict__ img, float* __restrict__ kscr, const int n_pair_ctas) {
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ __align__(8) uint64_t bars[3];
   __shared__ uint32_t tmem_slot;
@@ -99,10 +99,13 @@ __global__ void __launch_bounds__(CTC_NT, 1) solve_fc_tc_kernel(const __grid_con
   auto cta_sync = [&]() { tc_fence_before(); __syncthreads(); tc_fence_after(); };
 
   // ---- this thread's column ----
-  const int tile = 2 * blockIdx.x + set;
+  // CTAs [0, n_pair_ctas) own two tiles; the rest (a last partial wave) own one tile and skip the second set's MLP phases
+  const bool two_tiles = (int)blockIdx.x < n_pair_ctas;
+  const int tile = two_tiles ? 2 * blockIdx.x + set : 2 * n_pair_ctas + ((int)blockIdx.x - n_pair_ctas);
   const int col = tile * CTC_TILE + ltid;
   const int colc = min(col, a.ncol - 1);
-  const bool live = col < a.ncol;
+  const bool active = two_tiles || set == 0;  // in a single-tile CTA the second warp set only helps with the epilogues
+  const bool live = active && col < a.ncol;
   const size_t xs = a.x0_stride ? a.x0_stride : (size_t)N;
   float x[N], X[N], nn[32];
 #pragma unroll
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(CTC_NT, 1) solve_fc_tc_kernel(const __grid_con
     }
   };
   auto save_ckpt = [&](int c) {  // adjoint tile layout: [tile of 32 columns][n_ckpt][S][32]
-    if (col < ((a.ncol + 31) & ~31)) {
+    if (active && col < ((a.ncol + 31) & ~31)) {
       const int t32 = col >> 5, ct = col & 31;
 #pragma unroll
       for (int k = 0; k < N; ++k) a.ckpt[(((size_t)t32 * a.n_ckpt + c) * N + k) * 32 + ct] = x[k];
@@ -208,8 +211,8 @@ __global__ void __launch_bounds__(CTC_NT, 1) solve_fc_tc_kernel(const __grid_con
   for (int p = 0; p <= 2 * K; ++p) {
     const int owner = p & 1;
     const bool mine = owner == set;
-    const bool has_mlp = (p >> 1) < K;                        // the owner tile still has an evaluation to run
-    const bool has_col = !mine && p >= 1 && ((p - 1) >> 1) < K;  // this set has column work pending from its last MLP section
+    const bool has_mlp = (p >> 1) < K && (owner == 0 || two_tiles);  // the owner tile still has an evaluation to run
+    const bool has_col = !mine && p >= 1 && ((p - 1) >> 1) < K && (set == 0 || two_tiles);  // column work pending from this set's last MLP section
     if (has_mlp) {
       if (mine) {
         float hi[N], lo[N];

@@ -94,7 +94,13 @@ static int launch_fc_tc_t(cpz_model* m, const ClosureTcD& C, const SolveArgs& a)
   auto kern = solve_fc_tc_kernel<ACT>;
   CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C.img_bytes));
   const int n_tiles = (a.ncol + CTC_TILE - 1) / CTC_TILE;
-  kern<<<(n_tiles + 1) / 2, CTC_NT, C.img_bytes, m->ctx->stream>>>(C, m->fwd.M, m->tab, m->tm, a, m->b_cimg.p, m->b_fcscr.p);
+  // full waves of two-tile CTAs; a remainder that fits one wave of single-tile CTAs runs as such (a single tile per CTA
+  // finishes an evaluation sooner than a pair)
+  const int sms = m->ctx->sm_count > 0 ? m->ctx->sm_count : 148;
+  int n_pair = (n_tiles + 1) / 2, n_single = 0;
+  const int full = n_tiles / (2 * sms), rem = n_tiles - full * 2 * sms;
+  if (rem > 0 && rem <= sms) { n_pair = full * sms; n_single = rem; }
+  kern<<<n_pair + n_single, CTC_NT, C.img_bytes, m->ctx->stream>>>(C, m->fwd.M, m->tab, m->tm, a, m->b_cimg.p, m->b_fcscr.p, n_pair);
   CPZ_CUDA(cudaGetLastError());
   m->ctx->launches++;
   return CPZ_OK;
