@@ -265,6 +265,19 @@ __device__ __noinline__ void mlp_backward_layer(const ModelD& M, int l, const fl
                                                    float* __restrict__ xb, const float* __restrict__ wsm,
                                                    const float* __restrict__ theta, float* __restrict__ gpart) {
   constexpr int NCG = CT / 4;
+  // gemms of layer l (at most one per net, three nets) and the prefix sums of their tile counts; unused slots repeat
+  // the total so that the slot search below never selects them
+  int gl[3] = {0, 0, 0}, end[4] = {0, 0, 0, 0}, wend[4] = {0, 0, 0, 0}, bend[4] = {0, 0, 0, 0}, ng = 0;
+  for (int gi = 0; gi < M.n_gemm && ng < 3; ++gi) {
+    const GemmD& g = M.gemm[gi];
+    if (g.layer != l) continue;
+    gl[ng] = gi;
+    end[ng + 1] = end[ng] + ((g.K + 3) / 4) * NCG;
+    wend[ng + 1] = wend[ng] + ((g.K + 3) / 4) * ((g.N + 3) / 4);
+    bend[ng + 1] = bend[ng] + g.N;
+    ++ng;
+  }
+  for (int q = ng + 1; q < 4; ++q) { end[q] = end[ng]; wend[q] = wend[ng]; bend[q] = bend[ng]; }
   // (a) backward-data
   if (l == 0) {
     const int S = M.S;
@@ -293,60 +306,63 @@ __device__ __noinline__ void mlp_backward_layer(const ModelD& M, int l, const fl
       }
     }
   } else {
-    for (int gi = 0; gi < M.n_gemm; ++gi) {
-      const GemmD& g = M.gemm[gi];
-      if (g.layer != l) continue;
+    // the nets' gemms of layer l share one flattened tile space, so that 3 x 40 tiles fill one pass of the CTA instead of
+    // three passes of 40 threads (the nets touch disjoint rows of zarena)
+    for (int t = threadIdx.x; t < end[ng]; t += NT) {
+      const int q = (t >= end[1]) + (t >= end[2]);
+      const GemmD& g = M.gemm[q == 0 ? gl[0] : (q == 1 ? gl[1] : gl[2])];
+      const int tile = t - (q == 0 ? 0 : (q == 1 ? end[1] : end[2]));
       // the producer of this gemm's input is the gemm of the same net at layer l-1
       int gp = -1;
       for (int gj = 0; gj < M.n_gemm; ++gj)
         if (M.gemm[gj].net == g.net && M.gemm[gj].layer == l - 1) gp = gj;
       const int actp = M.gemm[gp].act;
       const float* W = WS ? wsm + g.sw_off : theta + g.w_off;
-      const int nkg = (g.K + 3) / 4;
       float* zprev = zarena + g.in_off * CT;
-      for (int tile = threadIdx.x; tile < nkg * NCG; tile += NT) {
-        const int cg = tile % NCG, k0 = (tile / NCG) * 4;
-        float acc[4][4];
+      const int cg = tile % NCG, k0 = (tile / NCG) * 4;
+      float acc[4][4];
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
+      for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) acc[kk][cc] = 0.f;
-        bwd_data_tile<WS, CT>(g, W, zarena + g.out_off * CT, k0, cg, acc);
+        for (int cc = 0; cc < 4; ++cc) acc[kk][cc] = 0.f;
+      bwd_data_tile<WS, CT>(g, W, zarena + g.out_off * CT, k0, cg, acc);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          if (k0 + kk < g.K) {
-            float4* p = reinterpret_cast<float4*>(zprev + (k0 + kk) * CT + 4 * cg);
-            const float4 z = *p;
-            float4 d;
-            d.x = acc[kk][0] * act_grad(actp, z.x);
-            d.y = acc[kk][1] * act_grad(actp, z.y);
-            d.z = acc[kk][2] * act_grad(actp, z.z);
-            d.w = acc[kk][3] * act_grad(actp, z.w);
-            *p = d;
-          }
+      for (int kk = 0; kk < 4; ++kk) {
+        if (k0 + kk < g.K) {
+          float4* p = reinterpret_cast<float4*>(zprev + (k0 + kk) * CT + 4 * cg);
+          const float4 z = *p;
+          float4 d;
+          d.x = acc[kk][0] * act_grad(actp, z.x);
+          d.y = acc[kk][1] * act_grad(actp, z.y);
+          d.z = acc[kk][2] * act_grad(actp, z.z);
+          d.w = acc[kk][3] * act_grad(actp, z.w);
+          *p = d;
         }
       }
     }
   }
-  // (b) weight and bias gradients of layer l (read delta_l and a_{l-1}; neither is written by (a))
-  for (int gi = 0; gi < M.n_gemm; ++gi) {
-    const GemmD& g = M.gemm[gi];
-    if (g.layer != l) continue;
+  // (b) weight and bias gradients of layer l (read delta_l and a_{l-1}; neither is written by (a)), again over one
+  // flattened tile space; the bias sums go to the threads at the top of the CTA, which own the fewest weight tiles
+  for (int t = threadIdx.x; t < wend[ng]; t += NT) {
+    const int q = (t >= wend[1]) + (t >= wend[2]);
+    const GemmD& g = M.gemm[q == 0 ? gl[0] : (q == 1 ? gl[1] : gl[2])];
+    const int tile = t - (q == 0 ? 0 : (q == 1 ? wend[1] : wend[2]));
     const float* a = g.in_off < 0 ? Xin : arena + g.in_off * CT;
+    const int njg = (g.N + 3) / 4;
+    const int jg = tile % njg, kg = tile / njg;
+    bwd_weight_tile<CT>(g, a, zarena + g.out_off * CT, kg * 4, jg * 4, gpart + g.gw_off + (size_t)tile * 16);
+  }
+  for (int t = NT - 1 - (int)threadIdx.x; t < bend[ng]; t += NT) {
+    const int q = (t >= bend[1]) + (t >= bend[2]);
+    const GemmD& g = M.gemm[q == 0 ? gl[0] : (q == 1 ? gl[1] : gl[2])];
+    const int j = t - (q == 0 ? 0 : (q == 1 ? bend[1] : bend[2]));
     const float* delta = zarena + g.out_off * CT;
-    const int nkg = (g.K + 3) / 4, njg = (g.N + 3) / 4;
-    for (int tile = threadIdx.x; tile < nkg * njg; tile += NT) {
-      const int jg = tile % njg, kg = tile / njg;
-      bwd_weight_tile<CT>(g, a, delta, kg * 4, jg * 4, gpart + g.gw_off + (size_t)tile * 16);
+    float s = 0.f;
+    for (int c = 0; c < CT; c += 4) {
+      const float4 d = *reinterpret_cast<const float4*>(delta + j * CT + c);
+      s += (d.x + d.y) + (d.z + d.w);
     }
-    for (int j = threadIdx.x; j < g.N; j += NT) {
-      float s = 0.f;
-      for (int c = 0; c < CT; c += 4) {
-        const float4 d = *reinterpret_cast<const float4*>(delta + j * CT + c);
-        s += (d.x + d.y) + (d.z + d.w);
-      }
-      gpart[g.gb_off + j] += s;  // thread j owns this entry
-    }
+    gpart[g.gb_off + j] += s;  // exactly one thread per CTA owns this entry
   }
 }
 
