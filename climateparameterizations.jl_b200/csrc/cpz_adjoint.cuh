@@ -342,17 +342,30 @@ __device__ __noinline__ void mlp_backward_layer(const ModelD& M, int l, const fl
     }
   }
   // (b) weight and bias gradients of layer l (read delta_l and a_{l-1}; neither is written by (a)), again over one
-  // flattened tile space; the bias sums go to the threads at the top of the CTA, which own the fewest weight tiles
-  for (int t = threadIdx.x; t < wend[ng]; t += NT) {
-    const int q = (t >= wend[1]) + (t >= wend[2]);
-    const GemmD& g = M.gemm[q == 0 ? gl[0] : (q == 1 ? gl[1] : gl[2])];
-    const int tile = t - (q == 0 ? 0 : (q == 1 ? wend[1] : wend[2]));
-    const float* a = g.in_off < 0 ? Xin : arena + g.in_off * CT;
-    const int njg = (g.N + 3) / 4;
-    const int jg = tile % njg, kg = tile / njg;
-    bwd_weight_tile<CT>(g, a, zarena + g.out_off * CT, kg * 4, jg * 4, gpart + g.gw_off + (size_t)tile * 16);
+  // flattened tile space. No barrier separates (a) from (b), so (b) is dealt from the top of the CTA downwards: the
+  // threads that had no (or one fewer) (a) tile take the first weight tiles. At layer 0 an (a) tile sums over every
+  // net and costs about sum(N)/CT weight tiles, so the threads without one take that many extra tiles up front.
+  {
+    const int u = NT - 1 - (int)threadIdx.x;
+    int idle = 0, extra = 0;
+    if (l == 0) {
+      idle = NT - min(NT, ((M.S + 3) / 4) * NCG);
+      extra = idle > 0 ? min(bend[ng] / CT, wend[ng] / idle) : 0;
+    }
+    const int head = idle * extra, mine = u < idle ? extra : 0;
+    for (int i = 0;; ++i) {
+      const int t = i < mine ? u + i * idle : head + u + (i - mine) * NT;
+      if (t >= wend[ng]) break;
+      const int q = (t >= wend[1]) + (t >= wend[2]);
+      const GemmD& g = M.gemm[q == 0 ? gl[0] : (q == 1 ? gl[1] : gl[2])];
+      const int tile = t - (q == 0 ? 0 : (q == 1 ? wend[1] : wend[2]));
+      const float* a = g.in_off < 0 ? Xin : arena + g.in_off * CT;
+      const int njg = (g.N + 3) / 4;
+      const int jg = tile % njg, kg = tile / njg;
+      bwd_weight_tile<CT>(g, a, zarena + g.out_off * CT, kg * 4, jg * 4, gpart + g.gw_off + (size_t)tile * 16);
+    }
   }
-  for (int t = NT - 1 - (int)threadIdx.x; t < bend[ng]; t += NT) {
+  for (int t = threadIdx.x; t < bend[ng]; t += NT) {
     const int q = (t >= bend[1]) + (t >= bend[2]);
     const GemmD& g = M.gemm[q == 0 ? gl[0] : (q == 1 ? gl[1] : gl[2])];
     const int j = t - (q == 0 ? 0 : (q == 1 ? bend[1] : bend[2]));
