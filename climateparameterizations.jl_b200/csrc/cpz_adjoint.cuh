@@ -20,6 +20,7 @@ struct AdjArgs {
   const float* Q;
   const float* targets;  // [ncol][n_saved][S]
   const float* ckpt;     // [n_tiles][n_ckpt][S][CT]
+  const float* kstore;   // [n_tiles][n_rk_steps][n_stages][S][CT] stage tendencies of the forward pass, or null (recompute)
   float* kslots;         // [grid][n_stages][S][CT]
   float* segx;           // [grid][seg_len][S][CT]
   float* gpart;          // [grid][M.slab] gradient slabs in tile layout (zeroed by the host)
@@ -519,9 +520,12 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, 
       __syncthreads();
       // ---- forward recompute of the segment's Runge–Kutta step starts (all but the last need a forward step)
       store_state(segx, xs);
+      const size_t nrk = (size_t)tm.n_steps * tm.n_substeps;
+      const float* kst = a.kstore != nullptr ? a.kstore + ((size_t)tile * nrk + (size_t)n0 * tm.n_substeps) * ns * SC : nullptr;
       for (int r = 0; r + 1 < R; ++r) {
         const float tb = tm.t0 + (float)(n0 + r / tm.n_substeps) * tm.dt + (float)(r % tm.n_substeps) * h;
-        for (int i = 0; i < ns; ++i) {
+        const float* kfw = kst != nullptr ? kst + (size_t)r * ns * SC : slots;  // stored k_i, or recomputed below
+        for (int i = 0; i < ns && kst == nullptr; ++i) {
           const float* in = xs;
           if (i > 0) { stage_input<CT, NT>(tab, i, h, xs, slots, SC, xin); __syncthreads(); in = xin; }
           rhs_mlp<CT, NT, WS>(M, pc, in, arena, wsm, a.theta, bcf, qs, tb + tab.c[i] * h);
@@ -538,7 +542,7 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, 
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
           for (int i = 0; i < ns; ++i) {
             const float bi = tab.b[i];
-            const float4 kv = __ldcg(reinterpret_cast<const float4*>(slots + (size_t)i * SC) + e4);
+            const float4 kv = __ldcg(reinterpret_cast<const float4*>(kfw + (size_t)i * SC) + e4);
             acc.x = fmaf(bi, kv.x, acc.x); acc.y = fmaf(bi, kv.y, acc.y); acc.z = fmaf(bi, kv.z, acc.z); acc.w = fmaf(bi, kv.w, acc.w);
           }
           float4 xv = reinterpret_cast<float4*>(xs)[e4];
@@ -555,7 +559,8 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, 
         const float tb = tm.t0 + (float)nstep * tm.dt + (float)sub * h;
         // (a) forward stages 0..ns-2 -> k_i into the slots
         const long long pa0 = CPZ_APROF_T();
-        for (int i = 0; i + 1 < ns; ++i) {
+        const float* kfw = kst != nullptr ? kst + (size_t)r * ns * SC : slots;
+        for (int i = 0; i + 1 < ns && kst == nullptr; ++i) {
           const float* in = xs;
           if (i > 0) { stage_input<CT, NT>(tab, i, h, xs, slots, SC, xin); __syncthreads(); in = xin; }
           rhs_mlp<CT, NT, WS>(M, pc, in, arena, wsm, a.theta, bcf, qs, tb + tab.c[i] * h);
@@ -573,7 +578,7 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, 
         for (int i = ns - 1; i >= 0; --i) {
           const long long pb0 = CPZ_APROF_T();
           const float* in = xs;
-          if (i > 0) { stage_input<CT, NT>(tab, i, h, xs, slots, SC, xin); in = xin; }
+          if (i > 0) { stage_input<CT, NT>(tab, i, h, xs, kfw, SC, xin); in = xin; }
           // kbar_i = h (b_i xbar + sum_{j>i} a_ji Xbar_j)   (slots j>i hold Xbar_j)
           for (int e4 = threadIdx.x; e4 < SC / 4; e4 += NT) {
             const float bi = tab.b[i];

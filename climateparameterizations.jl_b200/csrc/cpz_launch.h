@@ -8,6 +8,7 @@
 namespace cpz {
 int launch_solve(cpz_model* m, const SolveArgs& a);
 int launch_solve_tc(cpz_model* m, const SolveArgs& a);
+bool solve_tc_eligible(cpz_model* m);
 int launch_solve_nnfree(cpz_model* m, const SolveArgs& a);
 int launch_solve_fc_tc(cpz_model* m, const SolveArgs& a);   // T-only nets on tcgen05; 1 = not eligible
 bool closure_uses_tc(const cpz_model* m);  // NN-free u/v/T model; 1 = not eligible

@@ -584,6 +584,12 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
           rhs_eval(tbase + tab.c[i] * hstep, dx);
           if (qd < 3) {
             const bool last = (i + 1 == ns);
+            if (a.kstore != nullptr) {  // k_i for the adjoint's reverse sweep (same tile-native layout as the checkpoints)
+              const size_t rk = (size_t)n * tm.n_substeps + sub, nrk = (size_t)tm.n_steps * tm.n_substeps;
+              float4* dst = reinterpret_cast<float4*>(a.kstore + ((((size_t)tile * nrk + rk) * ns + i) * 96 + 32 * qd + lane) * TC_CT + cg0);
+              __stcs(dst, make_float4(dx[0], dx[1], dx[2], dx[3]));
+              __stcs(dst + 1, make_float4(dx[4], dx[5], dx[6], dx[7]));
+            }
             float acc[8];
             const float ci_ = last ? tab.b[i] : tab.a[(i + 1) % CPZ_MAX_STAGES][i];
 #pragma unroll

@@ -159,3 +159,23 @@ def test_training_reduces_loss(ctx):
     m.close()
     print("losses", losses[0], losses[-1])
     assert losses[-1] < losses[0]
+
+
+def test_grad_stored_stage_tendencies_match_recompute(ctx, monkeypatch):
+    """The tcgen05 forward pass hands its stage tendencies k_i to the reverse sweep; with CPZ_NO_KSTORE the adjoint
+    recomputes them in FP32 SIMT. Both must give the same loss and (to FP32 noise) the same gradient."""
+    d = syn.wind_mixing_desc(variant=RHS_TRAIN, n_steps=18, save_stride=9, ckpt_stride=3)
+    th = syn.theta_random(d, scale=0.3)
+    ncol = 77
+    x0, bcs = syn.columns(d, ncol, seed=5)
+    tgt = np.ascontiguousarray(np.repeat(x0[:, None, :], d.n_saved, axis=1)) * np.float32(0.9)
+    w = np.array([1, 1, 1, 5e-3, 5e-3, 5e-3], dtype=np.float32)
+    m = engine.Model(ctx, d, th)
+    assert "tcgen05" in m.describe()
+    l1, g1 = m.loss_grad(x0, bcs, tgt, w)
+    monkeypatch.setenv("CPZ_NO_KSTORE", "1")
+    l2, g2 = m.loss_grad(x0, bcs, tgt, w)
+    m.close()
+    assert np.all(np.isfinite(g1)) and np.linalg.norm(g1) > 0
+    assert abs(l1[6] - l2[6]) <= 1e-6 * abs(l2[6])
+    assert np.linalg.norm(g1 - g2) <= 2e-5 * np.linalg.norm(g2)
