@@ -177,7 +177,10 @@ int cpz_solve_dev(cpz_model* m, const float* x0, const float* bcs, const float* 
  * nde_loss (free_convection/src/training.jl:55-62).
  * targets: [ncol][n_saved][nf*Nz]; loss_w[6]: weights of (u,v,T,du/dz,dv/dz,dT/dz) (loss.jl:33-42);
  * loss_out[7]: the six weighted components then their sum; grad_out[P] (destructure order) or NULL for loss only.
- * With an allreduce hook set, sums are global over ranks (ncol_global = sum of ncol). */
+ * With an allreduce hook set, sums are global over ranks (ncol_global = sum of ncol).
+ * Device scratch kept by the model between calls: the step checkpoints, and -- when the tcgen05 solve runs and the
+ * device has the room plus 8 GB to spare -- the stage tendencies of the forward pass
+ * (ceil(ncol/32)*32 * n_steps * n_substeps * n_stages * nf*Nz floats; CPZ_NO_KSTORE=1 in the environment disables it). */
 int cpz_loss_grad(cpz_model* m, const float* x0, const float* bcs, const float* diurnal_Q, const float* targets,
                   size_t ncol, const float* loss_w, float* loss_out, float* grad_out);
 int cpz_loss_grad_dev(cpz_model* m, const float* x0, const float* bcs, const float* diurnal_Q, const float* targets,
