@@ -167,7 +167,6 @@ int launch_solve_nnfree(cpz_model* m, const SolveArgs& a) {
   return CPZ_OK;
 }
 
-// returns 1 when the model is not eligible (caller falls back to the SIMT kernel), 0 on success, <0 on error
 // true when launch_solve_tc would take a checkpointing solve of this model
 bool solve_tc_eligible(cpz_model* m) {
   if (getenv("CPZ_NO_TC") != nullptr) return false;
@@ -176,6 +175,7 @@ bool solve_tc_eligible(cpz_model* m) {
   return tc_plan(m, T, why);
 }
 
+// returns 1 when the model is not eligible (caller falls back to the SIMT kernel), 0 on success, <0 on error
 int launch_solve_tc(cpz_model* m, const SolveArgs& a) {
   if (getenv("CPZ_NO_TC") != nullptr) return 1;
   TcD T;
