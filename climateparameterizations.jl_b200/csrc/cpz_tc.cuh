@@ -584,7 +584,9 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
           rhs_eval(tbase + tab.c[i] * hstep, dx);
           if (qd < 3) {
             const bool last = (i + 1 == ns);
-            if (a.kstore != nullptr) {  // k_i for the adjoint's reverse sweep (same tile-native layout as the checkpoints)
+            // k_i for the adjoint's reverse sweep (same tile-native layout as the checkpoints); checkpointing solves
+            // always run the 32-column tiles, so the 28-column instantiation carries no trace of this
+            if (CPT == 8 && a.kstore != nullptr) {
               const size_t rk = (size_t)n * tm.n_substeps + sub, nrk = (size_t)tm.n_steps * tm.n_substeps;
               float4* dst = reinterpret_cast<float4*>(a.kstore + ((((size_t)tile * nrk + rk) * ns + i) * 96 + 32 * qd + lane) * TC_CT + cg0);
               __stcs(dst, make_float4(dx[0], dx[1], dx[2], dx[3]));
