@@ -19,8 +19,8 @@ struct AdjArgs {
   const float* bcs;
   const float* Q;
   const float* targets;  // [ncol][n_saved][S]
-  const float* ckpt;     // [n_tiles][n_ckpt][S][CT]
-  const float* kstore;   // [n_tiles][n_rk_steps][n_stages][S][CT] stage tendencies of the forward pass, or null (recompute)
+  const float* ckpt;     // [n_tiles32][n_ckpt][S][32]: global layout in 32-column tiles whatever the kernel's tile width CT
+  const float* kstore;   // [n_tiles32][n_rk_steps][n_stages][S][32] stage tendencies of the forward pass, or null (recompute)
   float* kslots;         // [grid][n_stages][S][CT]
   float* segx;           // [grid][seg_len][S][CT]
   float* gpart;          // [grid][M.slab] gradient slabs in tile layout (zeroed by the host)
@@ -74,9 +74,12 @@ __device__ __noinline__ void faces_vjp(const ModelD& M, const float* __restrict_
       if (f > 0 && f < N) {
         const float eb = AN * (kbar[f * CT + c] - kbar[(f - 1) * CT + c]);
         if (has_nn) nb[(f - 1) * CT + c] = eb;
-        if (M.flags & F_CA) {
-          const float G = M.rc.Nf * (X[f * CT + c] - X[(f - 1) * CT + c]);
-          if (M.rc.K_ca * G < 0.f) g = -M.rc.K_ca * eb;
+        const float G = M.rc.Nf * (X[f * CT + c] - X[(f - 1) * CT + c]);
+        if ((M.flags & F_CA) && M.rc.K_ca * G < 0.f) g = -M.rc.K_ca * eb;
+        if (M.flags & F_MPP) {  // F -= c nu(G) G
+          float dcnu;
+          const float cnu = fc_mpp_cnu(M, G, &dcnu);
+          g -= eb * fmaf(dcnu, G, cnu);
         }
       }
       gbar[i] = g;
@@ -421,16 +424,31 @@ __device__ __noinline__ void loss_frame(const ModelD& M, const AdjArgs& a, const
   }
 }
 
-// x_in = xs + h * sum_{j<i} a_ij k_j  (k_j from the global slots)
+// Global arrays shared with the forward kernels (checkpoints, stored stage tendencies) are laid out in 32-column tiles
+// [tile32][...][S][32] whatever this kernel's tile width CT is (CT divides 32): float4 number e4 of a [S][CT] tile sits at
+// row e4 / (CT/4), float4 e4 % (CT/4) of a row of `ld` floats. The CTA's private scratch uses ld = CT (contiguous).
+constexpr int LT = 32;
+template <int CT>
+__device__ __forceinline__ const float4* row4(const float* base, int ld, int e4) {
+  constexpr int Q = CT / 4;
+  return reinterpret_cast<const float4*>(base + (size_t)(e4 / Q) * ld) + (e4 % Q);
+}
+struct KSrc {  // where the forward stage tendencies k_j of the current Runge–Kutta step are
+  const float* p;
+  int ld;          // row stride (CT: private slots, 32: stored by the forward pass)
+  size_t stride;   // floats between stages
+};
+
+// x_in = xs + h * sum_{j<i} a_ij k_j
 template <int CT, int NT>
 __device__ __noinline__ void stage_input(const TableauD& tab, int i, float h, const float* __restrict__ xs,
-                                            const float* __restrict__ slots, int SC, float* __restrict__ xin) {
+                                            const KSrc ks, int SC, float* __restrict__ xin) {
   for (int e4 = threadIdx.x; e4 < SC / 4; e4 += NT) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int j = 0; j < i; ++j) {
       const float aij = tab.a[i][j];
       if (aij != 0.f) {
-        const float4 kv = __ldcg(reinterpret_cast<const float4*>(slots + (size_t)j * SC) + e4);
+        const float4 kv = __ldcg(row4<CT>(ks.p + (size_t)j * ks.stride, ks.ld, e4));
         acc.x = fmaf(aij, kv.x, acc.x); acc.y = fmaf(aij, kv.y, acc.y);
         acc.z = fmaf(aij, kv.z, acc.z); acc.w = fmaf(aij, kv.w, acc.w);
       }
@@ -475,8 +493,8 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, 
   if (WS) load_weights_smem<NT>(M, wsm, a.theta);
   __syncthreads();
 
-  auto load_state = [&](float* dst, const float* src) {  // tile-native [S][CT] copy from global
-    for (int i = threadIdx.x; i < SC / 4; i += NT) reinterpret_cast<float4*>(dst)[i] = __ldcg(reinterpret_cast<const float4*>(src) + i);
+  auto load_state = [&](float* dst, const float* src, int ld) {  // [S][CT] tile from global (rows of ld floats)
+    for (int i = threadIdx.x; i < SC / 4; i += NT) reinterpret_cast<float4*>(dst)[i] = __ldcg(row4<CT>(src, ld, i));
   };
   auto store_state = [&](float* dst, const float* src) {
     for (int i = threadIdx.x; i < SC / 4; i += NT) __stcg(reinterpret_cast<float4*>(dst) + i, reinterpret_cast<const float4*>(src)[i]);
@@ -499,8 +517,10 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, 
       qs[threadIdx.x] = (a.Q != nullptr) ? __ldg(a.Q + col) : 0.f;
     }
     for (int i = threadIdx.x; i < SC; i += NT) xbar[i] = 0.f;
-    const float* ck = a.ckpt + (size_t)tile * a.n_ckpt * SC;
-    load_state(xs, ck + (size_t)(a.n_ckpt - 1) * SC);  // x_N
+    const int tile32 = col0 / LT, coff = col0 % LT;
+    const size_t SL = (size_t)S * LT;  // floats of one state in the global 32-column-tile layout
+    const float* ck = a.ckpt + (size_t)tile32 * a.n_ckpt * SL + coff;
+    load_state(xs, ck + (size_t)(a.n_ckpt - 1) * SL, LT);  // x_N
     __syncthreads();
     {
       const int fr = frame_of(tm.n_steps);
@@ -516,18 +536,19 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, 
     for (int seg = nseg - 1; seg >= 0; --seg) {
       const int n0 = seg * cs, n1 = min(n0 + cs, tm.n_steps);
       const int R = (n1 - n0) * tm.n_substeps;
-      load_state(xs, ck + (size_t)seg * SC);
+      load_state(xs, ck + (size_t)seg * SL, LT);
       __syncthreads();
       // ---- forward recompute of the segment's Runge–Kutta step starts (all but the last need a forward step)
       store_state(segx, xs);
       const size_t nrk = (size_t)tm.n_steps * tm.n_substeps;
-      const float* kst = a.kstore != nullptr ? a.kstore + ((size_t)tile * nrk + (size_t)n0 * tm.n_substeps) * ns * SC : nullptr;
+      const float* kst = a.kstore != nullptr ? a.kstore + ((size_t)tile32 * nrk + (size_t)n0 * tm.n_substeps) * ns * SL + coff : nullptr;
+      const KSrc own{slots, CT, (size_t)SC};
       for (int r = 0; r + 1 < R; ++r) {
         const float tb = tm.t0 + (float)(n0 + r / tm.n_substeps) * tm.dt + (float)(r % tm.n_substeps) * h;
-        const float* kfw = kst != nullptr ? kst + (size_t)r * ns * SC : slots;  // stored k_i, or recomputed below
+        const KSrc kfw = kst != nullptr ? KSrc{kst + (size_t)r * ns * SL, LT, SL} : own;  // stored k_i, or recomputed below
         for (int i = 0; i < ns && kst == nullptr; ++i) {
           const float* in = xs;
-          if (i > 0) { stage_input<CT, NT>(tab, i, h, xs, slots, SC, xin); __syncthreads(); in = xin; }
+          if (i > 0) { stage_input<CT, NT>(tab, i, h, xs, own, SC, xin); __syncthreads(); in = xin; }
           rhs_mlp<CT, NT, WS>(M, pc, in, arena, wsm, a.theta, bcf, qs, tb + tab.c[i] * h);
           float* slot_i = slots + (size_t)i * SC;
           rhs_tendencies<CT, NT, NF>(Mp, in, arena, bcf, [=](int k0, int c, const float (&dx)[NF][4]) {
@@ -542,7 +563,7 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, 
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
           for (int i = 0; i < ns; ++i) {
             const float bi = tab.b[i];
-            const float4 kv = __ldcg(reinterpret_cast<const float4*>(kfw + (size_t)i * SC) + e4);
+            const float4 kv = __ldcg(row4<CT>(kfw.p + (size_t)i * kfw.stride, kfw.ld, e4));
             acc.x = fmaf(bi, kv.x, acc.x); acc.y = fmaf(bi, kv.y, acc.y); acc.z = fmaf(bi, kv.z, acc.z); acc.w = fmaf(bi, kv.w, acc.w);
           }
           float4 xv = reinterpret_cast<float4*>(xs)[e4];
@@ -554,15 +575,15 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, 
       }
       // ---- reverse sweep over the segment
       for (int r = R - 1; r >= 0; --r) {
-        if (R > 1) { load_state(xs, segx + (size_t)r * SC); __syncthreads(); }
+        if (R > 1) { load_state(xs, segx + (size_t)r * SC, CT); __syncthreads(); }
         const int nstep = n0 + r / tm.n_substeps, sub = r % tm.n_substeps;
         const float tb = tm.t0 + (float)nstep * tm.dt + (float)sub * h;
         // (a) forward stages 0..ns-2 -> k_i into the slots
         const long long pa0 = CPZ_APROF_T();
-        const float* kfw = kst != nullptr ? kst + (size_t)r * ns * SC : slots;
+        const KSrc kfw = kst != nullptr ? KSrc{kst + (size_t)r * ns * SL, LT, SL} : own;
         for (int i = 0; i + 1 < ns && kst == nullptr; ++i) {
           const float* in = xs;
-          if (i > 0) { stage_input<CT, NT>(tab, i, h, xs, slots, SC, xin); __syncthreads(); in = xin; }
+          if (i > 0) { stage_input<CT, NT>(tab, i, h, xs, own, SC, xin); __syncthreads(); in = xin; }
           rhs_mlp<CT, NT, WS>(M, pc, in, arena, wsm, a.theta, bcf, qs, tb + tab.c[i] * h);
           float* slot_i = slots + (size_t)i * SC;
           rhs_tendencies<CT, NT, NF>(Mp, in, arena, bcf, [=](int k0, int c, const float (&dx)[NF][4]) {

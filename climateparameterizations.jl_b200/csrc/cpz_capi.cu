@@ -72,7 +72,7 @@ static int rebuild_plans(cpz_model* m) {
   std::string err;
   fill_tableau(m->desc.integrator, m->tab);
   m->tm.dt = m->desc.dt; m->tm.t0 = m->desc.t0; m->tm.n_steps = m->desc.n_steps; m->tm.n_substeps = m->desc.n_substeps;
-  m->tm.save_stride = m->desc.save_stride; m->tm.ckpt_stride = m->desc.ckpt_stride;
+  m->tm.save_stride = m->desc.save_stride; m->tm.ckpt_stride = m->desc.ckpt_stride; m->tm.step0 = 0;
   PlanOptions fo;
   fo.CT = m->CT; fo.NT = m->NT; fo.keep_all = false;
   fo.smem_budget = m->ctx->smem_optin;
@@ -83,6 +83,22 @@ static int rebuild_plans(cpz_model* m) {
   bo.smem_budget = m->ctx->smem_optin;
   bo.other_smem_bytes = adjoint_other_smem(m->desc.n_fields * m->desc.Nz, m->desc.n_fields == 3 ? 6 : 2, m->CT);
   m->has_bwd = build_plan(m->desc, bo, m->bwd, m->bwd_err);
+  {
+    const int cs = cpz_model::CT_SMALL;
+    PlanOptions fs = fo, bs = bo;
+    std::string es;
+    fs.CT = cs; fs.other_smem_bytes = solve_other_smem(m->desc, cs, m->tab.n_stages);
+    bs.CT = cs; bs.other_smem_bytes = adjoint_other_smem(m->desc.n_fields * m->desc.Nz, m->desc.n_fields == 3 ? 6 : 2, cs);
+    m->has_small = m->has_bwd && build_plan(m->desc, fs, m->fwd_s, es) && build_plan(m->desc, bs, m->bwd_s, es);
+    // both adjoint plans must describe the same gradient slab (one index map, one reduction kernel)
+    if (m->has_small) {
+      const ModelD &A = m->bwd.M, &B = m->bwd_s.M;
+      bool same = A.slab == B.slab && A.n_gemm == B.n_gemm;
+      for (int gi = 0; same && gi < A.n_gemm; ++gi)
+        same = A.gemm[gi].gw_off == B.gemm[gi].gw_off && A.gemm[gi].gb_off == B.gemm[gi].gb_off && A.gemm[gi].w_off == B.gemm[gi].w_off;
+      m->has_small = same;
+    }
+  }
   if (m->has_bwd && m->P > 0) {
     std::vector<int> map(m->P, 0);
     const ModelD& B = m->bwd.M;
@@ -155,6 +171,7 @@ int cpz_ctx_create(int device, void* stream, cpz_ctx** out) {
 int cpz_ctx_destroy(cpz_ctx* ctx) {
   if (!ctx) return CPZ_OK;
   cudaSetDevice(ctx->device);
+  if (ctx->d_nonfinite) cudaFree(ctx->d_nonfinite);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto& e : ctx->chunk_ev) if (e) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -179,6 +196,18 @@ int cpz_ctx_synchronize(cpz_ctx* ctx) {
 int cpz_ctx_stream(cpz_ctx* ctx, void** stream_out) {
   if (!ctx || !stream_out) return fail(CPZ_ERR_INVALID, "null pointer");
   *stream_out = (void*)ctx->stream;
+  return CPZ_OK;
+}
+
+int cpz_ctx_nonfinite_count(cpz_ctx* ctx, uint64_t* n) {
+  if (!ctx || !n) return fail(CPZ_ERR_INVALID, "null pointer");
+  *n = 0;
+  if (!ctx->d_nonfinite) return CPZ_OK;
+  CPZ_CUDA(cudaSetDevice(ctx->device));
+  unsigned int v = 0;
+  CPZ_CUDA(cudaMemcpyAsync(&v, ctx->d_nonfinite, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+  CPZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  *n = v;
   return CPZ_OK;
 }
 
@@ -264,6 +293,11 @@ int cpz_model_describe(const cpz_model* m, char* buf, size_t buf_len) {
   dump("forward", m->fwd, solve_other_smem(m->desc, m->CT, m->tab.n_stages));
   if (m->has_bwd) dump("adjoint", m->bwd, adjoint_other_smem(m->desc.n_fields * m->desc.Nz, m->desc.n_fields == 3 ? 6 : 2, m->CT));
   else s += "adjoint plan: unavailable (" + m->bwd_err + ")\n";
+  if (m->has_small) {
+    snprintf(line, sizeof(line), "small-batch training pass: %d-column tiles (FP32 forward + adjoint) up to %d columns\n", cpz_model::CT_SMALL,
+             cpz_model::CT_SMALL * (m->ctx->sm_count > 0 ? m->ctx->sm_count : 148));
+    s += line;
+  }
   snprintf(buf, buf_len, "%s", s.c_str());
   return CPZ_OK;
 }
@@ -307,7 +341,7 @@ int cpz_model_set_time(cpz_model* m, int32_t integrator, float dt, float t0, int
   if (replan) return rebuild_plans(m);
   fill_tableau(d.integrator, m->tab);
   m->tm.dt = dt; m->tm.t0 = t0; m->tm.n_steps = n_steps; m->tm.n_substeps = n_substeps;
-  m->tm.save_stride = save_stride; m->tm.ckpt_stride = ckpt_stride;
+  m->tm.save_stride = save_stride; m->tm.ckpt_stride = ckpt_stride; m->tm.step0 = 0;
   return CPZ_OK;
 }
 
@@ -368,7 +402,10 @@ int cpz_solve_dev(cpz_model* m, const float* x0, const float* bcs, const float* 
   SolveArgs a{};
   a.theta = m->d_theta; a.x0 = x0; a.bcs = bcs; a.Q = diurnal_Q; a.traj = traj; a.ncol = (int)ncol;
   a.n_saved = n_saved_of(m->tm); a.n_ckpt = 0; a.rhs_only = 0;
-  return launch_solve(m, a);
+  if ((rc = launch_solve(m, a))) return rc;
+  // CPZ_ERR_NONFINITE reporting: the last saved frame is scanned on the device (a diverged explicit step shows up there)
+  const size_t S = (size_t)m->fwd.M.S;
+  return launch_check_finite(m->ctx, traj + (size_t)(a.n_saved - 1) * S, (size_t)a.n_saved * S, (int)ncol, (int)S);
 }
 
 int cpz_solve(cpz_model* m, const float* x0, const float* bcs, const float* diurnal_Q, float* traj, size_t ncol) {
@@ -376,6 +413,9 @@ int cpz_solve(cpz_model* m, const float* x0, const float* bcs, const float* diur
   if (rc) return rc;
   if (ncol == 0) return CPZ_OK;
   if (!x0 || !bcs || !traj) return fail(CPZ_ERR_INVALID, "null array");
+  // the same argument checks as cpz_solve_dev, made here because the chunked path below launches the kernels directly
+  if ((m->desc.flags & CPZ_FLAG_DIURNAL) && !diurnal_Q) return fail(CPZ_ERR_INVALID, "diurnal model needs diurnal_Q");
+  if (ncol > (size_t)INT32_MAX / 512) return fail(CPZ_ERR_INVALID, "ncol too large");
   if ((rc = bind_device(m->ctx))) return rc;
   if ((rc = upload_inputs(m, x0, bcs, diurnal_Q, ncol))) return rc;
   const size_t S = (size_t)m->fwd.M.S;
@@ -389,11 +429,19 @@ int cpz_solve(cpz_model* m, const float* x0, const float* bcs, const float* diur
   const int n_frames = tm_full.save_stride > 0 ? tm_full.n_steps / tm_full.save_stride : 0;
   int n_chunks = 1;
   if (tm_full.save_stride > 0 && tm_full.n_steps % tm_full.save_stride == 0 && n * sizeof(float) >= ((size_t)64 << 20)) n_chunks = std::min(8, n_frames / 16);
+  if (n_chunks > 1) {
+    // The overlap needs a page-locked destination: cudaMemcpy2DAsync into pageable memory blocks the host until the copy
+    // is done, so the next chunk's kernel would only be launched afterwards and chunking would be pure overhead.
+    cudaPointerAttributes pa{};
+    const cudaError_t pe = cudaPointerGetAttributes(&pa, traj);
+    if (pe != cudaSuccess) cudaGetLastError();
+    if (pe != cudaSuccess || pa.type != cudaMemoryTypeHost) n_chunks = 1;
+  }
   if (n_chunks <= 1) {
     if ((rc = cpz_solve_dev(m, m->b_x0.p, m->b_bcs.p, dQ, m->b_traj.p, ncol))) return rc;
     CPZ_CUDA(cudaMemcpyAsync(traj, m->b_traj.p, n * sizeof(float), cudaMemcpyDeviceToHost, m->ctx->stream));
     CPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));
-    return CPZ_OK;
+    return report_nonfinite(m->ctx, "the final frame of the solve");
   }
   cpz_ctx* c = m->ctx;
   if (!c->copy_stream) {
@@ -410,7 +458,7 @@ int cpz_solve(cpz_model* m, const float* x0, const float* bcs, const float* diur
     if (k == 0) { a.x0 = m->b_x0.p; a.traj = m->b_traj.p; }
     else { a.x0 = m->b_traj.p + (size_t)f0 * S; a.x0_stride = (size_t)n_saved * S; a.skip_frame0 = 1; a.traj = m->b_traj.p + (size_t)(f0 + 1) * S; }
     m->tm = tm_full;
-    m->tm.t0 = tm_full.t0 + (float)(f0 * tm_full.save_stride) * tm_full.dt;
+    m->tm.step0 = f0 * tm_full.save_stride;  // stage times are t0 + (step0 + n) dt, bitwise those of a single launch
     m->tm.n_steps = nf * tm_full.save_stride;
     rc = launch_solve(m, a);
     m->tm = tm_full;
@@ -423,9 +471,10 @@ int cpz_solve(cpz_model* m, const float* x0, const float* bcs, const float* diur
                                cudaMemcpyDeviceToHost, c->copy_stream));
     f0 += nf;
   }
+  if ((rc = launch_check_finite(c, m->b_traj.p + (size_t)(n_saved - 1) * S, (size_t)n_saved * S, (int)ncol, (int)S))) return rc;
   CPZ_CUDA(cudaStreamSynchronize(c->copy_stream));
   CPZ_CUDA(cudaStreamSynchronize(c->stream));
-  return CPZ_OK;
+  return report_nonfinite(c, "the final frame of the solve");
 }
 
 }  // extern "C"

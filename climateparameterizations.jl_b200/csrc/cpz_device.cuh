@@ -27,16 +27,16 @@ enum { ACT_ID = 0, ACT_RELU = 1, ACT_MISH = 2, ACT_SWISH = 3, ACT_LEAKY = 4, ACT
 // an order of magnitude inside the 1e-5 RHS tolerance, at a quarter of the instruction count of expf + IEEE divide.
 __device__ __forceinline__ float act_fwd(int act, float x) {
   switch (act) {
-    case ACT_RELU: return fmaxf(x, 0.f);
+    case ACT_RELU: return x < 0.f ? 0.f : x;  // NaN propagates, as Julia's max(0, x) does (fmaxf would return 0)
     case ACT_MISH: {  // x*tanh(softplus(x)) = x*n/(n+2), n = e^x(e^x+2)
       const float e = __expf(fminf(x, 20.f));
       const float n = e * (e + 2.f);
       return x * __fdividef(n, n + 2.f);
     }
     case ACT_SWISH: return __fdividef(x, 1.f + __expf(-x));
-    case ACT_LEAKY: return fmaxf(0.01f * x, x);
+    case ACT_LEAKY: return x < 0.f ? 0.01f * x : x;
     case ACT_TANH: {  // 1 - 2/(e^{2x}+1)
-      const float e = __expf(2.f * fminf(x, 40.f));
+      const float e = __expf(2.f * (x > 40.f ? 40.f : x));  // not fminf: a NaN argument must stay NaN
       return 1.f - __fdividef(2.f, e + 1.f);
     }
     default: return x;
@@ -186,6 +186,19 @@ __device__ __forceinline__ float nu_of_ri(const ModelD& M, float Ri) {
   return M.rc.nu0 + __fdividef(M.rc.nu_m, 1.f + __expf(y2));
 }
 
+// T-only model with the mPP base diffusivity (BASELINE config 1): the rule of NDE_training.jl:114-139 at u = v = 0, where
+// both shear gradients are D_face*0 + eps. Returns c_T nu/Pr at a face with scaled gradient G; *dG (optional) receives
+// d(c_T nu/Pr)/dG. The exponent is clamped: at these shear-free Richardson numbers (|Ri| ~ 1e15 |G|) the tanh step is
+// saturated everywhere except within ~1e-16 of G = -eps.
+__device__ __forceinline__ float fc_mpp_cnu(const ModelD& M, float G, float* dG = nullptr) {
+  const float k = M.rc.BzC * M.rc.fc_iS2;
+  const float y2 = 2.f * (k * (G + M.rc.eps) - M.rc.Ric) * M.rc.inv_dRi;
+  const float s = __fdividef(1.f, 1.f + __expf(y2 > 80.f ? 80.f : y2));
+  const float cp = M.rc.c[2] * M.rc.inv_Pr;
+  if (dG) *dG = -cp * M.rc.nu_m * s * (1.f - s) * (2.f * M.rc.inv_dRi * k);
+  return cp * (M.rc.nu0 + M.rc.nu_m * s);
+}
+
 // ---- face phase: E_q[k][c] for all faces k = 0..N ------------------------------------------------------------------
 // E is the total (NN + diffusive [+ boundary]) flux whose cell-difference gives the tendency.
 // nn rows come from the activation arena (M.nn_off), or are zero when the model has no nets.
@@ -197,7 +210,7 @@ __device__ __noinline__ void faces_phase(const ModelD& M, const float* __restric
   const bool has_nn = M.n_nets > 0;
   if (M.variant == RHS_FC) {
     const float* nn = has_nn ? arena + M.nn_off[0] * CT : nullptr;
-    const bool ca = M.flags & F_CA;
+    const bool ca = M.flags & F_CA, mpp1 = M.flags & F_MPP;
     for (int i = threadIdx.x; i < nfaces * CT; i += NT) {
       const int k = i / CT, c = i - k * CT;
       float e;
@@ -205,10 +218,9 @@ __device__ __noinline__ void faces_phase(const ModelD& M, const float* __restric
       else if (k == N) e = bcf[CT + c];
       else {
         e = has_nn ? nn[(k - 1) * CT + c] : 0.f;
-        if (ca) {
-          const float G = M.rc.Nf * (X[k * CT + c] - X[(k - 1) * CT + c]);
-          e -= fminf(0.f, M.rc.K_ca * G);
-        }
+        const float G = M.rc.Nf * (X[k * CT + c] - X[(k - 1) * CT + c]);
+        if (mpp1) e -= fc_mpp_cnu(M, G) * G;
+        if (ca) e -= fminf(0.f, M.rc.K_ca * G);
       }
       E[i] = e;
     }
@@ -326,7 +338,10 @@ __device__ __forceinline__ void stencil_fused(const ModelD& M, const float* __re
 #pragma unroll
       for (int q = 0; q < NF; ++q) G[q] = Nf * (xl[q][fi + 1] - xl[q][fi]);
       if constexpr (NF == 1) {
-        E[0][fi] = ca ? nn[0] - fminf(0.f, M.rc.K_ca * G[0]) : nn[0];
+        float e = nn[0];
+        if (M.flags & F_MPP) e -= fc_mpp_cnu(M, G[0]) * G[0];
+        if (ca) e -= fminf(0.f, M.rc.K_ca * G[0]);
+        E[0][fi] = e;
       } else {
         if (mpp) {
           const float su = M.rc.sig_u * (G[0] + eps), sv = M.rc.sig_v * (G[1] + eps);

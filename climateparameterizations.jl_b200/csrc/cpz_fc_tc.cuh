@@ -1,5 +1,6 @@
 // tcgen05 forward solve of the T-only free-convection NDEs (FreeConvectionNDE / ConvectiveAdjustmentNDE,
-// free_convection/src/free_convection_nde.jl:29-38, convective_adjustment_nde.jl:33-48; BASELINE configs 1 and 4).
+// free_convection/src/free_convection_nde.jl:29-38, convective_adjustment_nde.jl:33-48; BASELINE configs 1 and 4; with
+// CPZ_FLAG_MPP also the mPP base diffusivity of wind_mixing/src/NDE_training.jl:114-139 at u = v = 0).
 // Same orientation as the closure kernel (cpz_closure_tc.cuh): a CTA owns 128 columns for the whole integration,
 // thread t <-> column t <-> TMEM lane t holds the 32-level profile in registers; per RHS evaluation the scaled profile
 // goes to TMEM as the A operand (tcgen05.st), the three Dense layers run as 3xTF32 MMAs against the shared-memory
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(CTC_NT, 1) solve_fc_tc_kernel(const __grid_con
   const float bc_b = __ldg(a.bcs + (size_t)colc * 2), bc_t = __ldg(a.bcs + (size_t)colc * 2 + 1);
 #pragma unroll
   for (int k = 0; k < N; ++k) { X[k] = x[k]; nn[k] = 0.f; }
-  const bool ca = (M.flags & F_CA) != 0;
+  const bool ca = (M.flags & F_CA) != 0, mpp1 = (M.flags & F_MPP) != 0;
   const float ANf = M.rc.A[2] * M.rc.Nf, Nf = M.rc.Nf, Kca = M.rc.K_ca;
   const float h = tm.dt / (float)tm.n_substeps;
   const int ns = tab.n_stages;
@@ -157,7 +158,9 @@ __global__ void __launch_bounds__(CTC_NT, 1) solve_fc_tc_kernel(const __grid_con
         if (k == N - 1) Ehi = bc_t;
         else {
           Ehi = nn[k] + b3[k];
-          if (ca) Ehi -= fminf(0.f, Kca * (Nf * (X[k + 1] - X[k])));
+          const float G = Nf * (X[k + 1] - X[k]);
+          if (mpp1) Ehi -= fc_mpp_cnu(M, G) * G;   // mPP base at u = v = 0 (BASELINE config 1)
+          if (ca) Ehi -= fminf(0.f, Kca * G);
         }
         dx[k] = -ANf * (Ehi - Elo);
         Elo = Ehi;

@@ -13,7 +13,7 @@ namespace cpz {
 __device__ __forceinline__ float4 act_fwd4(int act, float4 z) {
   float4 r;
   switch (act) {
-    case ACT_RELU: r = make_float4(fmaxf(z.x, 0.f), fmaxf(z.y, 0.f), fmaxf(z.z, 0.f), fmaxf(z.w, 0.f)); break;
+    case ACT_RELU: r = make_float4(act_fwd(ACT_RELU, z.x), act_fwd(ACT_RELU, z.y), act_fwd(ACT_RELU, z.z), act_fwd(ACT_RELU, z.w)); break;  // NaN-propagating
     case ACT_MISH: r = make_float4(act_fwd(ACT_MISH, z.x), act_fwd(ACT_MISH, z.y), act_fwd(ACT_MISH, z.z), act_fwd(ACT_MISH, z.w)); break;
     case ACT_SWISH: r = make_float4(act_fwd(ACT_SWISH, z.x), act_fwd(ACT_SWISH, z.y), act_fwd(ACT_SWISH, z.z), act_fwd(ACT_SWISH, z.w)); break;
     case ACT_LEAKY: r = make_float4(act_fwd(ACT_LEAKY, z.x), act_fwd(ACT_LEAKY, z.y), act_fwd(ACT_LEAKY, z.z), act_fwd(ACT_LEAKY, z.w)); break;
@@ -230,7 +230,7 @@ template <bool WS, int CT, int NT>
 __device__ __forceinline__ TileCtx phase_ctx(const ModelD& M, int p, int round) {
   TileCtx t{};
 #define CPZ_CASE(tc, to, kq) \
-  case (tc * 10000 + to * 100 + kq): t = make_tile_ctx<tc, to, kq, WS, CT, NT>(M, p, round); break;
+  case (tc * 10000 + to * 100 + kq): if constexpr (tc <= CT) t = make_tile_ctx<tc, to, kq, WS, CT, NT>(M, p, round); break;
   switch (M.phase[p].TC * 10000 + M.phase[p].TO * 100 + M.phase[p].ksplit) {
     CPZ_SHAPES(CPZ_CASE)
     default: break;
@@ -279,7 +279,7 @@ __device__ __forceinline__ void run_phase(const ModelD& M, int p, const TilePack
   for (int r = 0; r < rounds; ++r) {
     const TileCtx t = (cached && r == 0) ? unpack_ctx(tp0) : phase_ctx<WS, CT, NT>(M, p, r);
 #define CPZ_CASE(tc, to, kq) \
-  case (tc * 10000 + to * 100 + kq): run_tile_g2<tc, to, kq, WS, CT, SAVE_Z>(t, X, arena, zarena, wbase); break;
+  case (tc * 10000 + to * 100 + kq): if constexpr (tc <= CT) run_tile_g2<tc, to, kq, WS, CT, SAVE_Z>(t, X, arena, zarena, wbase); break;
     switch (shape) {
       CPZ_SHAPES(CPZ_CASE)
       default: break;

@@ -21,6 +21,8 @@ struct cpz_ctx {
   cudaStream_t copy_stream = nullptr;  // D2H of finished trajectory chunks, overlapped with the next chunk's kernel
   cudaEvent_t chunk_ev[2] = {nullptr, nullptr};
   size_t smem_optin = 0;
+  unsigned int* d_nonfinite = nullptr;  // device counter of non-finite values seen in results (CPZ_ERR_NONFINITE)
+  unsigned int nonfinite_seen = 0;      // value of the counter at the last host read
 };
 
 struct DevBuf {
@@ -35,10 +37,15 @@ struct cpz_model {
   cpz::Plan fwd;  // forward plan (aliasing arena, free TO)
   cpz::Plan bwd;  // adjoint plan (all activations kept)
   bool has_bwd = false;
+  // the same two plans for CT_SMALL-column tiles: small batches (BASELINE config 1: one column; the reference's 9-18
+  // simulations) and shards too small to give every SM a 32-column tile run on these
+  cpz::Plan fwd_s, bwd_s;
+  bool has_small = false;
   std::string bwd_err;
   TableauD tab;
   TimeD tm;
   int CT = 32, NT = 256;
+  static constexpr int CT_SMALL = 4;
   // parameters and optimiser state (device)
   float* d_theta = nullptr;
   float* d_m = nullptr;

@@ -1,4 +1,5 @@
 // Adjoint kernel instantiations, small reduction / optimiser kernels and their launchers.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -36,7 +37,7 @@ __global__ void pack_loss_kernel(const float* __restrict__ lpart, int n_slabs, f
 
 // loss_out[0..6) = w_q * sum_q * inv_norm_q ; loss_out[6] = total
 __global__ void finalize_loss_kernel(const float* __restrict__ pack_tail, const W6 w6, float inv_prof,
-                                     float inv_grad, float* __restrict__ loss_out) {
+                                     float inv_grad, float* __restrict__ loss_out, unsigned int* __restrict__ nonfinite) {
   if (threadIdx.x == 0) {
     float tot = 0.f;
     const float inv_ncol = 1.f / pack_tail[6];
@@ -46,6 +47,7 @@ __global__ void finalize_loss_kernel(const float* __restrict__ pack_tail, const 
       tot += v;
     }
     loss_out[6] = tot;
+    if (tot - tot != 0.f) atomicAdd(nonfinite, 1u);  // NaN / Inf loss: reported as CPZ_ERR_NONFINITE by the host flavours
   }
 }
 
@@ -77,6 +79,18 @@ __global__ void loss_traj_kernel(const float* __restrict__ traj, const float* __
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[threadIdx.x][w];
     lpart[(size_t)blockIdx.x * 8 + threadIdx.x] = t;
   }
+}
+
+// non-finite values in a result (IEEE semantics are kept; this only reports: CPZ_ERR_NONFINITE)
+__global__ void check_finite_kernel(const float* __restrict__ p, size_t stride, int ncol, int S, unsigned int* __restrict__ counter) {
+  unsigned int bad = 0;
+  for (int col = blockIdx.x; col < ncol; col += gridDim.x)
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+      const float v = p[(size_t)col * stride + i];
+      bad += (v - v != 0.f) ? 1u : 0u;  // NaN or +-Inf
+    }
+  bad = __reduce_add_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(counter, bad);
 }
 
 // grad[p] *= scale
@@ -152,12 +166,36 @@ int launch_pack_loss(cpz_model* m, const float* lpart, int n_slabs, float ncol, 
 int launch_finalize_loss(cpz_model* m, const float* pack_tail, const float* w6, float inv_prof, float inv_grad, float* loss_out) {
   W6 w;
   for (int q = 0; q < 6; ++q) w.w[q] = w6[q];
-  finalize_loss_kernel<<<1, 32, 0, m->ctx->stream>>>(pack_tail, w, inv_prof, inv_grad, loss_out);
+  if (!m->ctx->d_nonfinite) {
+    CPZ_CUDA(cudaMalloc(&m->ctx->d_nonfinite, sizeof(unsigned int)));
+    CPZ_CUDA(cudaMemsetAsync(m->ctx->d_nonfinite, 0, sizeof(unsigned int), m->ctx->stream));
+  }
+  finalize_loss_kernel<<<1, 32, 0, m->ctx->stream>>>(pack_tail, w, inv_prof, inv_grad, loss_out, m->ctx->d_nonfinite);
   CPZ_LAUNCHED(m);
 }
 int launch_loss_traj(cpz_model* m, const float* traj, const float* tgt, int ncol, int n_saved, int S, int Nz, int nf, float* lpart) {
   loss_traj_kernel<<<(unsigned)ncol, 256, 0, m->ctx->stream>>>(traj, tgt, n_saved, S, Nz, nf, (float)Nz, lpart);
   CPZ_LAUNCHED(m);
+}
+int launch_check_finite(cpz_ctx* c, const float* p, size_t stride, int ncol, int S) {
+  if (!c->d_nonfinite) {
+    CPZ_CUDA(cudaMalloc(&c->d_nonfinite, sizeof(unsigned int)));
+    CPZ_CUDA(cudaMemsetAsync(c->d_nonfinite, 0, sizeof(unsigned int), c->stream));
+  }
+  check_finite_kernel<<<std::min(ncol, 592), 128, 0, c->stream>>>(p, stride, ncol, S, c->d_nonfinite);
+  CPZ_CUDA(cudaGetLastError());
+  c->launches++;
+  return CPZ_OK;
+}
+int report_nonfinite(cpz_ctx* c, const char* what) {
+  if (!c->d_nonfinite) return CPZ_OK;
+  unsigned int n = 0;
+  CPZ_CUDA(cudaMemcpyAsync(&n, c->d_nonfinite, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
+  CPZ_CUDA(cudaStreamSynchronize(c->stream));
+  const unsigned int fresh = n - c->nonfinite_seen;
+  c->nonfinite_seen = n;
+  if (fresh) return fail(CPZ_ERR_NONFINITE, "%u non-finite value(s) in %s (results are returned as computed)", fresh, what);
+  return CPZ_OK;
 }
 int launch_scale(cpz_model* m, float* g, int P, const float* pack_tail) {
   scale_kernel<<<(P + 255) / 256, 256, 0, m->ctx->stream>>>(g, P, pack_tail);

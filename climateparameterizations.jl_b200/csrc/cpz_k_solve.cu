@@ -38,6 +38,17 @@ static int launch_solve_t(cpz_model* m, const SolveArgs& a) {
   return CPZ_OK;
 }
 
+// Column tile of the training pass. 32 columns per CTA is the efficient shape; CT_SMALL-column tiles take over while
+// they still fit one wave of the device (ncol <= CT_SMALL * SMs): a 4-column tile runs several times faster than a
+// 32-column one, so small batches (one column in BASELINE config 1, the reference's 9-18 simulations) and small shards
+// (1 152 columns per GPU in config 3 on eight GPUs = 36 tiles of 32 on 148 SMs) finish sooner. CPZ_SMALL_NCOL overrides.
+int train_tile(const cpz_model* m, size_t ncol) {
+  if (!m->has_small) return m->CT;
+  const char* ov = getenv("CPZ_SMALL_NCOL");
+  const size_t lim = ov ? (size_t)atol(ov) : (size_t)cpz_model::CT_SMALL * (size_t)(m->ctx->sm_count > 0 ? m->ctx->sm_count : 148);
+  return ncol <= lim ? cpz_model::CT_SMALL : m->CT;
+}
+
 int launch_solve(cpz_model* m, const SolveArgs& a) {
   static const bool prof = getenv("CPZ_PROF") != nullptr;
   if (!prof) {
@@ -45,9 +56,14 @@ int launch_solve(cpz_model* m, const SolveArgs& a) {
     if (rc <= 0) return rc;
     rc = launch_solve_nnfree(m, a);  // NN-free u/v/T model
     if (rc <= 0) return rc;
-    rc = launch_solve_fc_tc(m, a);   // T-only free-convection nets
-    if (rc <= 0) return rc;
+    // a small-tile training pass of a T-only model: a handful of columns would occupy one 128-column tensor-core tile per
+    // CTA; the 4-column FP32 tiles are the lower-latency choice there (BASELINE config 1)
+    if (!(a.small_tiles && a.ckpt != nullptr && a.ncol <= 64)) {
+      rc = launch_solve_fc_tc(m, a);   // T-only free-convection nets
+      if (rc <= 0) return rc;
+    }
   }
+  if (a.small_tiles && a.ckpt != nullptr && m->has_small) return launch_solve_small(m, a);
   if (m->fwd.M.w_in_smem) return launch_solve_t<32, 256, true>(m, a);
   return launch_solve_t<32, 256, false>(m, a);
 }

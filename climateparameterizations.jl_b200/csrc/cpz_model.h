@@ -40,6 +40,7 @@ struct RhsC {
   float BzC;      // H*g*alpha*sigma_T                      (NDE_training.jl:49)
   float sig_u, sig_v;
   float nu0, nu_m, Ric, inv_dRi, inv_Pr, kappa, eps;
+  float fc_iS2;   // T-only model with the mPP base: 1 / ((sigma_u eps)^2 + (sigma_v eps)^2), the shear term at u = v = 0
   float K_ca;     // T-only convective adjustment K
   float Nf;       // float(Nz): 1/Delta with Delta = 1/Nz
   float di_w;     // 2*pi*tau/period
@@ -75,4 +76,5 @@ struct TableauD {
 struct TimeD {
   float dt, t0;
   int n_steps, n_substeps, save_stride, ckpt_stride;
+  int step0;  // index of this launch's first step inside the whole solve (chunked host solves): t = t0 + (step0 + n) dt
 };

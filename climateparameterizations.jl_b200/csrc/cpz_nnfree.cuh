@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(NF_WARPS * 32) solve_nnfree_kernel(const __gri
   if (a.ckpt != nullptr) { save_ckpt(0); ci = 1; }
   for (int n = 0; n < tm.n_steps; ++n) {
     for (int sub = 0; sub < tm.n_substeps; ++sub) {
-      const float tb = tm.t0 + (float)n * tm.dt + (float)sub * h;
+      const float tb = tm.t0 + (float)(tm.step0 + n) * tm.dt + (float)sub * h;
 #pragma unroll 1
       for (int i = 0; i < ns; ++i) {
         float dx[3][NC];

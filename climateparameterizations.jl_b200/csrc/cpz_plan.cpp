@@ -179,6 +179,10 @@ bool build_plan(const cpz_model_desc& d, const PlanOptions& opt, Plan& out, std:
   rc.inv_dRi = (float)(1.0 / (double)d.dRi);
   rc.inv_Pr = (float)(1.0 / (double)d.Pr);
   rc.kappa = d.kappa; rc.eps = d.eps; rc.K_ca = d.K_ca;
+  {
+    const double su = sg[0] * (double)d.eps, sv = sg[1] * (double)d.eps;
+    rc.fc_iS2 = (su * su + sv * sv) > 0.0 ? (float)(1.0 / (su * su + sv * sv)) : 0.f;
+  }
   rc.Nf = (float)N;
   rc.di_w = (float)(2.0 * M_PI * tau / (double)(d.diurnal_period > 0.f ? d.diurnal_period : 86400.f));
   rc.di_amp = (float)(1.0 / ((double)d.alpha * (double)d.g));

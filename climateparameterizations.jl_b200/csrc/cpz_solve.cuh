@@ -11,7 +11,7 @@ struct SolveArgs {
   const float* bcs;    // [ncol][nbc]
   const float* Q;      // [ncol] diurnal amplitudes or null
   float* traj;         // [ncol][n_saved][S] or null
-  float* ckpt;         // [n_tiles][n_ckpt][S][CT] (tile-native layout) or null
+  float* ckpt;         // [n_tiles32][n_ckpt][S][32] (32-column-tile layout whatever the kernel's tile width) or null
   float* dxdt;         // rhs_only: [ncol][S]
   int ncol;
   int n_saved;
@@ -21,6 +21,7 @@ struct SolveArgs {
   unsigned long long* prof;  // optional [8] cycle counters (CTA 0, thread 0): set CPZ_PROF=1 in the environment
   size_t x0_stride;          // floats between consecutive columns of x0 (0 = S); a trajectory frame can be the start state
   int skip_frame0;           // continuation of a chunked solve: the start state is already in the trajectory, do not store it
+  int small_tiles;           // host hint: a checkpointing solve whose adjoint runs on CT_SMALL-column tiles
   float* kstore;             // optional [n_tiles][n_rk_steps][n_stages][S][32]: every stage tendency k_i, for the adjoint (tcgen05 solve only)
 };
 
@@ -176,17 +177,20 @@ __device__ __forceinline__ void solve_body(const ModelD& M, const ModelD& Mp, co
     if (threadIdx.x < CT) bulk_wait_read0();
     frame = 1;
   }
-  if (a.ckpt != nullptr) {
-    float4* dst = reinterpret_cast<float4*>(a.ckpt + ((size_t)tile * a.n_ckpt + 0) * SC);
-    for (int i = threadIdx.x; i < SC / 4; i += NT) dst[i] = reinterpret_cast<const float4*>(xs)[i];
-    ci = 1;
-  }
+  // checkpoints go to the global 32-column-tile layout [tile32][n_ckpt][S][32] shared with the adjoint kernel
+  auto save_ckpt = [&](int c, const float* src) {
+    constexpr int Q = CT / 4;
+    float* base = a.ckpt + ((size_t)(col0 / 32) * a.n_ckpt + c) * (size_t)S * 32 + (col0 % 32);
+    for (int i = threadIdx.x; i < SC / 4; i += NT)
+      *(reinterpret_cast<float4*>(base + (size_t)(i / Q) * 32) + (i % Q)) = reinterpret_cast<const float4*>(src)[i];
+  };
+  if (a.ckpt != nullptr) { save_ckpt(0, xs); ci = 1; }
   __syncthreads();
 
   const long long prof_all0 = (a.prof && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0;
   for (int n = 0; n < tm.n_steps; ++n) {
     for (int sub = 0; sub < tm.n_substeps; ++sub) {
-      const float tb = tm.t0 + (float)n * tm.dt + (float)sub * h;
+      const float tb = tm.t0 + (float)(tm.step0 + n) * tm.dt + (float)sub * h;
       const float* in = xs;
       for (int i = 0; i < ns; ++i) {
         if (a.prof) {
@@ -241,11 +245,7 @@ __device__ __forceinline__ void solve_body(const ModelD& M, const ModelD& Mp, co
       ++frame;
       CPZ_PROF_END(5);
     }
-    if (a.ckpt != nullptr && (step % tm.ckpt_stride == 0 || step == tm.n_steps)) {
-      float4* dst = reinterpret_cast<float4*>(a.ckpt + ((size_t)tile * a.n_ckpt + ci) * SC);
-      for (int i = threadIdx.x; i < SC / 4; i += NT) dst[i] = reinterpret_cast<const float4*>(xs)[i];
-      ++ci;
-    }
+    if (a.ckpt != nullptr && (step % tm.ckpt_stride == 0 || step == tm.n_steps)) { save_ckpt(ci, xs); ++ci; }
   }
   if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[7] += (unsigned long long)(clock64() - prof_all0);
   if (threadIdx.x < CT) bulk_wait0();

@@ -153,7 +153,7 @@ __device__ __forceinline__ float tc_act(int act_rt, float x) {
     const float n = e * (e + 2.f);
     return x * n * rcp_fast(n + 2.f);
   } else if constexpr (ACT == ACT_RELU) {
-    return fmaxf(x, 0.f);
+    return x < 0.f ? 0.f : x;  // NaN propagates (fmaxf would swallow it)
   } else {
     return act_fwd(act_rt, x);
   }
@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
     if (g == 1 && ta.stagger_ns > 0) __nanosleep(ta.stagger_ns);
     for (int n = 0; n < tm.n_steps; ++n) {
       for (int sub = 0; sub < tm.n_substeps; ++sub) {
-        const float tbase = tm.t0 + (float)n * tm.dt + (float)sub * hstep;
+        const float tbase = tm.t0 + (float)(tm.step0 + n) * tm.dt + (float)sub * hstep;
 #pragma unroll 1
         for (int i = 0; i < ns; ++i) {
           float dx[8];

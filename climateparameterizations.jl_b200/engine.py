@@ -16,13 +16,16 @@ LIB_PATH = os.path.join(_HERE, "lib", "libcpz.so")
 
 EXPORTS = [
     "cpz_version", "cpz_last_error", "cpz_device_count", "cpz_sizeof_model_desc", "cpz_sizeof_closure_desc", "cpz_ctx_create", "cpz_ctx_destroy", "cpz_ctx_set_allreduce",
-    "cpz_ctx_synchronize", "cpz_ctx_stream", "cpz_ctx_launch_count", "cpz_model_create", "cpz_model_destroy",
+    "cpz_ctx_synchronize", "cpz_ctx_stream", "cpz_ctx_launch_count", "cpz_ctx_nonfinite_count", "cpz_model_create", "cpz_model_destroy",
     "cpz_model_n_params", "cpz_model_n_saved", "cpz_model_describe", "cpz_set_theta", "cpz_get_theta", "cpz_model_set_time", "cpz_rhs",
     "cpz_rhs_dev", "cpz_solve", "cpz_solve_dev", "cpz_loss_grad", "cpz_loss_grad_dev", "cpz_train_step",
     "cpz_train_step_dev", "cpz_adam_get_state", "cpz_adam_set_state", "cpz_closure_step", "cpz_closure_step_dev",
 ]
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+
+
+ERR_INVALID, ERR_CUDA, ERR_NONFINITE, ERR_COLLECTIVE = -1, -2, -3, -4
 
 
 class CpzError(RuntimeError):
@@ -53,6 +56,7 @@ def lib() -> C.CDLL:
     L.cpz_ctx_synchronize.argtypes = [vp]
     L.cpz_ctx_stream.argtypes = [vp, C.POINTER(vp)]
     L.cpz_ctx_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.cpz_ctx_nonfinite_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.cpz_model_create.argtypes = [vp, C.POINTER(CModelDesc), C.POINTER(vp)]
     L.cpz_model_destroy.argtypes = [vp]
     L.cpz_model_n_params.argtypes = [vp, C.POINTER(sz)]
@@ -152,6 +156,13 @@ class Context:
     def launch_count(self) -> int:
         n = C.c_uint64(0)
         _check(lib().cpz_ctx_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    @property
+    def nonfinite_count(self) -> int:
+        """Non-finite values seen so far in final frames / losses (synchronises the stream); see CPZ_ERR_NONFINITE."""
+        n = C.c_uint64(0)
+        _check(lib().cpz_ctx_nonfinite_count(self._h, C.byref(n)))
         return n.value
 
     def close(self) -> None:
@@ -271,6 +282,11 @@ class Model:
     def set_adam_state(self, mt, vt, beta_pow) -> None:
         _check(lib().cpz_adam_set_state(self._h, _ptr(_np(mt, (self.P,))), _ptr(_np(vt, (self.P,))),
                                         _ptr(_np(beta_pow, (2,))), self.P))
+
+    def reset_adam_state(self) -> None:
+        """Zero moments and uninitialised beta powers: the next train_step starts a fresh Flux.ADAM."""
+        z = np.zeros(self.P, dtype=np.float32)
+        self.set_adam_state(z, z, np.zeros(2, dtype=np.float32))
 
     def closure_step(self, cdesc: ClosureDesc, T, y):
         T = _np(T, (cdesc.Nz, cdesc.Ny, cdesc.Nx))

@@ -42,13 +42,20 @@ class _DevBuf:
 
 
 def attach_torch_allreduce(ctx, group=None) -> None:
-    """Installs a torch.distributed (NCCL) sum-allreduce as the context's hook. The context must have been created on a
-    torch-owned stream (Context(device, torch_stream.cuda_stream)) that is torch's current stream when the engine runs."""
+    """Installs a torch.distributed sum-allreduce (NCCL on GPUs) as the context's hook. The collective is enqueued on
+    the cudaStream_t the engine passes — the stream its adjoint / reduction kernels and the following scale + ADAM
+    launches run on — so it is ordered with them whatever torch's current stream is. The context must have been
+    created on an explicit stream (`Context(device, torch.cuda.Stream().cuda_stream)` or the library-owned one);
+    the legacy default stream (handle 0) is refused because torch cannot wrap it as an ExternalStream."""
     import torch
     import torch.distributed as dist
 
     def hook(ptr: int, n: int, stream: int) -> None:
+        if not stream:
+            raise RuntimeError("allreduce hook called with the legacy default stream; create the cpz context on an "
+                               "explicit (non-default) CUDA stream")
         t = torch.as_tensor(_DevBuf(ptr, n), device=f"cuda:{ctx.device}")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream, device=f"cuda:{ctx.device}")):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
     ctx.set_allreduce(hook, dist.get_rank(group), dist.get_world_size(group))

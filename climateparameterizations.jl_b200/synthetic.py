@@ -37,11 +37,17 @@ def n_substeps_for(desc: ModelDesc, dz: Optional[float] = None) -> int:
     lim = {"tsit5": 0.8, "rk4": 0.65, "euler": 0.45}[desc.integrator]
     dz = dz if dz is not None else desc.H / desc.Nz
     if desc.variant == RHS_FREE_CONVECTION:
-        if not desc.has(FLAG_CA):
-            return 1
-        # non-dimensional K on a unit-depth grid: K*dt_hat*Nz^2 * (sigma_wT/sigma_T*tau/H)
-        A = desc.sigma[5] / desc.sigma[2] * desc.tau / desc.H
-        r = A * desc.K_ca * desc.dt * desc.Nz ** 2
+        r = 0.0
+        if desc.has(FLAG_CA):
+            # non-dimensional K on a unit-depth grid: K*dt_hat*Nz^2 * (sigma_wT/sigma_T*tau/H)
+            A = desc.sigma[5] / desc.sigma[2] * desc.tau / desc.H
+            r += A * desc.K_ca * desc.dt * desc.Nz ** 2
+        if desc.has(FLAG_MPP):  # mPP base in the T-only model (BASELINE config 1): nu_max/Pr on unstable faces, added to K
+            r += (desc.nu0 + desc.nu_m) / desc.Pr * desc.dt * desc.tau / dz ** 2
+            if desc.has(FLAG_CA):
+                # two switched diffusivities (K at dT/dz < 0, nu_- at dT/dz < -eps) chatter at neutral faces; measured on
+                # the FP64 oracle: the tangent of the fixed-step map blows up at 0.71 of the linear limit and is clean at 0.61
+                lim *= 0.75
         return max(1, int(np.ceil(r / lim)))
     nu_max = desc.nu0 + desc.nu_m
     if desc.has(FLAG_CA):
@@ -70,12 +76,13 @@ def wind_mixing_desc(variant: int = RHS_INFER, net: str = "uvT_small", Nz: int =
 
 def free_convection_desc(ca: bool = True, Nz: int = 32, n_steps: int = 1152, save_stride: int = 9, ckpt_stride: int = 9,
                          integrator: str = "tsit5", net: Optional[str] = "T_only", n_substeps: Optional[int] = None,
-                         **kw) -> ModelDesc:
+                         mpp: bool = False, **kw) -> ModelDesc:
     """T-only model (free_convection): H = 100 m (free_convection/convective_adjustment.jl:70-72), tau = 8 days,
     Nt = 1153 frames so dt_hat = 1/1153 in the reference's tspan convention (free_convection_nde.jl:40);
-    we keep 1/1152 so one step is one 600-s frame interval."""
+    we keep 1/1152 so one step is one 600-s frame interval. mpp=True adds the mPP base diffusivity at u = v = 0
+    (BASELINE config 1: "convective adjustment + mPP base"; constants of wind_mixing/train_NDE.jl:69-73)."""
     nets = [] if net is None else [NET_SHAPES[net](Nz)]
-    d = ModelDesc(Nz=Nz, n_fields=1, variant=RHS_FREE_CONVECTION, flags=(FLAG_CA if ca else 0), nets=nets, H=100.0,
+    d = ModelDesc(Nz=Nz, n_fields=1, variant=RHS_FREE_CONVECTION, flags=(FLAG_CA if ca else 0) | (FLAG_MPP if mpp else 0), nets=nets, H=100.0,
                   tau=691200.0, mu=MU, sigma=SIGMA, K_ca=10.0, integrator=integrator, dt=1.0 / 1152.0, n_steps=n_steps,
                   save_stride=save_stride, ckpt_stride=ckpt_stride)
     for k, v in kw.items():

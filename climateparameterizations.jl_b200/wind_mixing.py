@@ -233,12 +233,25 @@ def train_NDE(uw_NN: Chain, vw_NN: Chain, wT_NN: Chain, data: ProfileData, tstep
     best_theta, best_loss = weights.copy(), np.inf
     try:
         for i, opt in enumerate(optimizers):
+            resume = opt.state  # a state the CALLER attached (checkpoint/resume); consumed by this optimizer's first epoch
             for epoch in range(1, epochs + 1):
-                if opt.state:
-                    model.set_adam_state(opt.state["m"], opt.state["v"], opt.state["beta_pow"])
+                # Every `solve(prob, opt, ...)` of the reference copies theta (GalacticOptim 1.2.0), and Flux keys the ADAM
+                # moments by array identity, so each epoch of each optimizer starts from zero moments and full bias
+                # correction (NDE_training.jl:370); the device state is therefore reset here, never carried over from the
+                # previous optimizer or epoch.
+                if resume:
+                    model.set_adam_state(resume["m"], resume["v"], resume["beta_pow"])
+                    resume = None
+                else:
+                    model.reset_adam_state()
                 for it in range(1, maxiters + 1):
                     theta_before = model.get_theta()
-                    l = model.train_step(uvT0, BCs, targets, w, opt.eta, opt.beta[0], opt.beta[1], opt.eps, Q=Q)
+                    try:
+                        l = model.train_step(uvT0, BCs, targets, w, opt.eta, opt.beta[0], opt.beta[1], opt.eps, Q=Q)
+                    except engine.CpzError as e:
+                        if e.code != engine.ERR_NONFINITE:
+                            raise
+                        raise FloatingPointError(f"non-finite loss at iteration {it}: reduce dt (n_substeps={nsub}) or the learning rate") from e
                     total = float(l[6])
                     losses = dict(zip(LOSS_KEYS, map(float, l[:6])))
                     if not np.isfinite(total):
@@ -256,8 +269,7 @@ def train_NDE(uw_NN: Chain, vw_NN: Chain, wT_NN: Chain, data: ProfileData, tstep
                     if callback is not None:
                         callback(theta_before, total, losses, loss_scalings)
                 m_, v_, bp_ = model.adam_state()
-                opt.state = {"m": m_, "v": v_, "beta_pow": bp_}
-                record.adam_state = opt.state
+                record.adam_state = {"m": m_, "v": v_, "beta_pow": bp_}  # what write_data_NDE_training checkpoints
                 # weights .= res.minimizer  (:371): continue the next epoch from the best-seen theta
                 final_theta = model.get_theta()
                 l_final, _ = model.loss_grad(uvT0, BCs, targets, w, Q=Q, want_grad=False)

@@ -59,7 +59,9 @@ typedef enum {
 } cpz_rhs_variant;
 
 /* Flags (bitmask in cpz_model_desc.flags). */
-#define CPZ_FLAG_MPP              (1u << 0) /* modified Pacanowski–Philander diffusivity (NDE_training.jl:114-139) */
+#define CPZ_FLAG_MPP              (1u << 0) /* modified Pacanowski–Philander diffusivity (NDE_training.jl:114-139); on the T-only
+                                              * variant: the same rule at u = v = 0 (shear gradients 0 + eps), added to the NN
+                                              * flux as -sigma_T/(sigma_wT H) nu/Pr dT/dz — BASELINE config 1 "CA + mPP base" */
 #define CPZ_FLAG_CA               (1u << 1) /* convective adjustment (training_postprocessing.jl:118-124; convective_adjustment_nde.jl:44-47) */
 #define CPZ_FLAG_ZERO_WEIGHTS     (1u << 2) /* conditions.zero_weights boundary handling (NDE_training.jl:104-112,129-133) */
 #define CPZ_FLAG_SMOOTH_NN        (1u << 3) /* filters.interior on NN output (NDE_training.jl:98-102) */
@@ -138,6 +140,10 @@ int cpz_ctx_destroy(cpz_ctx* ctx);
 int cpz_ctx_set_allreduce(cpz_ctx* ctx, cpz_allreduce_fn fn, void* user, int rank, int world_size);
 int cpz_ctx_synchronize(cpz_ctx* ctx);
 int cpz_ctx_stream(cpz_ctx* ctx, void** stream_out);     /* the cudaStream_t kernels are launched on */
+/* CPZ_ERR_NONFINITE reporting. The host flavours of cpz_solve / cpz_loss_grad / cpz_train_step return CPZ_ERR_NONFINITE
+ * (after writing their results as computed) when the final saved frame or the loss holds a NaN/Inf. The *_dev flavours
+ * cannot (they do not synchronise): they add to a device counter that this call reads (it synchronises the stream). */
+int cpz_ctx_nonfinite_count(cpz_ctx* ctx, uint64_t* n);
 /* Number of library kernels launched on this context since creation (for gpu_launches accounting). */
 int cpz_ctx_launch_count(cpz_ctx* ctx, uint64_t* n);
 

@@ -188,6 +188,17 @@ def rhs_free_convection(desc, theta, T, bcs, t=0.0, Q=None, dtype=np.float64):
     else:
         wT_interior = np.zeros(Nz - 1, dtype=dtype)
     wT = np.concatenate([[bottom_flux], wT_interior, [top_flux]])
+    if desc.flags & FLAG_MPP:
+        # "convective adjustment + mPP base" of BASELINE config 1: predict_flux's mPP block (NDE_training.jl:114-139,
+        # not zero_weights) with u = v = 0, so that dudz = dvdz = D_face*0
+        eps = _c(desc, "eps", dtype)
+        sig_u, sig_v = dtype(np.float32(desc.sigma[0])), dtype(np.float32(desc.sigma[1]))
+        zero = np.zeros(Nz + 1, dtype=dtype)
+        dTdz = Dzf @ T
+        Ri = local_richardson(zero + eps, zero + eps, dTdz + eps, H, _c(desc, "g", dtype), _c(desc, "alpha", dtype), sig_u, sig_v, sig_T)
+        nu = _c(desc, "nu0", dtype) + _c(desc, "nu_m", dtype) * tanh_step((Ri - _c(desc, "Ric", dtype)) / _c(desc, "dRi", dtype))
+        nu_dTdz = sig_T / sig_wT / H * nu * dTdz / _c(desc, "Pr", dtype)   # boundary rows of D_face are zero
+        wT = wT - nu_dTdz
     if desc.flags & FLAG_CA:
         dz_wT = Dzc @ wT
         dTdz = Dzf @ T

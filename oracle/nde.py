@@ -104,6 +104,15 @@ def rhs(desc, theta, x, bcs, t=0.0, Q=None):
             nn = chain_torch(thetas[0], desc.nets[0].sizes, desc.nets[0].acts, T)
         else:
             nn = torch.zeros(ncol, N - 1, dtype=dtype)
+        if desc.flags & FLAG_MPP:
+            # BASELINE config 1 ("convective adjustment + mPP base" on the T-only NDE): the mPP
+            # rule of NDE_training.jl:114-139 at u = v = 0, i.e. both shear gradients are D_face*0 + eps
+            eps = _c32(desc.eps)
+            G = N * (T[:, 1:] - T[:, :-1])
+            BzC = H * _c32(desc.g) * _c32(desc.alpha) * sg[2]
+            Ri = BzC * (G + eps) / ((sg[0] * eps) ** 2 + (sg[1] * eps) ** 2)
+            nu = _c32(desc.nu0) + _c32(desc.nu_m) * (1 - torch.tanh((Ri - _c32(desc.Ric)) / _c32(desc.dRi))) / 2
+            nn = nn - sg[2] / sg[5] / H * nu / _c32(desc.Pr) * G
         F = torch.cat([bcs[:, 0:1], nn, bcs[:, 1:2]], dim=1)
         A = sg[5] / sg[2] * tau / H
         out = -_delta_c(F, N)

@@ -132,3 +132,34 @@ def test_allreduce_hook_plumbing_on_one_gpu(ctx):
     assert calls == [d.n_params + 8]
     np.testing.assert_allclose(l2, l1, rtol=1e-6)
     np.testing.assert_allclose(g2, g1, rtol=1e-5, atol=1e-9)
+
+
+def test_nonfinite_results_are_reported_not_hidden(ctx):
+    """CPZ_ERR_NONFINITE: a NaN in the input propagates through relu (Julia's max(0, x) semantics, not fmaxf) into the
+    final frame; the host flavour returns the results as computed AND the error code; the device flavour counts."""
+    d = syn.wind_mixing_desc(variant=RHS_TRAIN, net=None, n_steps=4, save_stride=2)
+    d.nets = [syn.NET_SHAPES["uvT_test"](32, "relu") for _ in range(3)]
+    th = syn.theta_random(d, scale=0.3)
+    x0, bcs = syn.columns(d, 5)
+    m = engine.Model(ctx, d, th)
+    ok = m.solve(x0, bcs)
+    assert np.isfinite(ok).all()
+    x0[3, 40] = np.nan
+    out = np.zeros((5, d.n_saved, d.S), dtype=np.float32)
+    with pytest.raises(engine.CpzError) as ei:
+        m.solve(x0, bcs, out=out)
+    assert ei.value.code == engine.ERR_NONFINITE
+    assert np.isnan(out[3, -1]).any() and np.isfinite(out[[0, 1, 2, 4]]).all()   # IEEE semantics kept, other columns untouched
+    before = ctx.nonfinite_count
+    x0d, bcsd = torch.tensor(x0, device="cuda"), torch.tensor(bcs, device="cuda")
+    traj = torch.empty((5, d.n_saved, d.S), device="cuda")
+    m.solve_dev(x0d, bcsd, traj)
+    assert ctx.nonfinite_count > before
+    # NaN through every activation of the RHS: Julia propagates it, so must the kernels
+    for act in ("relu", "leakyrelu", "tanh", "mish", "swish"):
+        d.nets = [syn.NET_SHAPES["uvT_test"](32, act) for _ in range(3)]
+        m2 = engine.Model(ctx, d, th)
+        dx = m2.rhs(x0, bcs)
+        m2.close()
+        assert np.isnan(dx[3, 0]), act  # level 0 of u sees the NaN at level 8 of v only through the net's hidden layer
+    m.close()

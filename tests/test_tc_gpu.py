@@ -129,7 +129,10 @@ def test_host_solve_chunked_pipeline_matches_single_launch(ctx, net):
     ncol = 2048 + 7
     x0, bcs = syn.columns(d, ncol)
     m = engine.Model(ctx, d, th)
-    host = m.solve(x0, bcs)                       # 2055 x 97 x 96 floats = 76.5 MB -> chunked
+    pinned = torch.empty((ncol, d.n_saved, d.S), dtype=torch.float32).pin_memory()  # chunking needs a page-locked destination
+    host = m.solve(x0, bcs, out=pinned.numpy())   # 2055 x 97 x 96 floats = 76.5 MB -> chunked
+    pageable = m.solve(x0, bcs)                   # pageable destination: single launch + one copy
+    np.testing.assert_array_equal(host, pageable)
     x0d, bcsd = torch.tensor(x0, device="cuda"), torch.tensor(bcs, device="cuda")
     traj = torch.empty((ncol, d.n_saved, d.S), device="cuda")
     m.solve_dev(x0d, bcsd, traj)
@@ -181,10 +184,35 @@ def test_fc_host_solve_chunked_pipeline_matches_single_launch(ctx):
     ncol = 8192 + 5
     x0, bcs = syn.columns(d, ncol)
     m = engine.Model(ctx, d, th)
-    host = m.solve(x0, bcs)   # 8197 x 73 x 32 floats = 76.6 MB -> chunked
+    pinned = torch.empty((ncol, d.n_saved, d.S), dtype=torch.float32).pin_memory()
+    host = m.solve(x0, bcs, out=pinned.numpy())   # 8197 x 73 x 32 floats = 76.6 MB -> chunked
     x0d, bcsd = torch.tensor(x0, device="cuda"), torch.tensor(bcs, device="cuda")
     traj = torch.empty((ncol, d.n_saved, d.S), device="cuda")
     m.solve_dev(x0d, bcsd, traj)
     ctx.synchronize()
     m.close()
     np.testing.assert_array_equal(host, traj.cpu().numpy())
+
+
+def test_host_solve_chunked_diurnal_bitwise_and_validation(ctx):
+    """The chunked host solve passes a step offset to the kernels (stage times are not re-rounded per chunk), so a
+    time-dependent (diurnal) model gives bitwise the single-launch trajectory; a missing diurnal_Q is refused whatever
+    the trajectory size."""
+    d = syn.wind_mixing_desc(variant=RHS_TRAIN, flags=FLAG_MPP | FLAG_ZERO_WEIGHTS | FLAG_DIURNAL, n_steps=96, save_stride=1)
+    th = syn.theta_random(d, scale=0.3)
+    ncol = 2048 + 3
+    x0, bcs = syn.columns(d, ncol)
+    Q = syn.diurnal_Q(ncol)
+    m = engine.Model(ctx, d, th)
+    pinned = torch.empty((ncol, d.n_saved, d.S), dtype=torch.float32).pin_memory()
+    host = m.solve(x0, bcs, Q=Q, out=pinned.numpy())
+    x0d, bcsd, Qd = torch.tensor(x0, device="cuda"), torch.tensor(bcs, device="cuda"), torch.tensor(Q, device="cuda")
+    traj = torch.empty((ncol, d.n_saved, d.S), device="cuda")
+    m.solve_dev(x0d, bcsd, traj, Q=Qd)
+    ctx.synchronize()
+    np.testing.assert_array_equal(host, traj.cpu().numpy())
+    with pytest.raises(engine.CpzError):
+        m.solve(x0, bcs, out=pinned.numpy())   # large trajectory, no Q
+    with pytest.raises(engine.CpzError):
+        m.solve(x0[:4], bcs[:4])               # small trajectory, no Q
+    m.close()
