@@ -24,7 +24,8 @@ struct AdjArgs {
   float* kslots;         // [grid][n_stages][S][CT]
   float* segx;           // [grid][seg_len][S][CT]
   float* gpart;          // [grid][M.slab] gradient slabs in tile layout (zeroed by the host)
-  float* lpart;          // [grid][8]   (zeroed by the host)
+  float* lpart;          // [grid][LP]: six squared-error sums, then (from LP/2) the five mPP-parameter gradient sums (zeroed by the host)
+  int want_pgrad;        // accumulate d(loss)/d(nu0, nu_m, dRi, Ric, Pr)  (diffusivity_parameter_optimisation.jl:1-33)
   int ncol, n_saved, n_ckpt, n_tiles, seg_len;
   float w[6];
   float inv_prof, inv_grad;  // 1/(Nz*n_saved*ncol_global), 1/((Nz+1)*n_saved*ncol_global)
@@ -32,6 +33,8 @@ struct AdjArgs {
 };
 #define CPZ_APROF_T() ((a.prof && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0)
 #define CPZ_APROF_ADD(slot, t0) do { if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[slot] += (unsigned long long)(clock64() - (t0)); } while (0)
+
+constexpr int LP = 16;  // floats per CTA in lpart
 
 struct AdjSmem {
   int w, xs, xbar, xin, xb, arena, zarena, bcf, qs, red, model, total_floats;
@@ -62,7 +65,7 @@ inline size_t adjoint_other_smem(int S, int nbc, int CT) {
 // (zarena at M.nn_off) and the cotangent of the face gradients Gbar_q[face][c] into `gbar` (arena flux rows).
 template <int CT, int NT>
 __device__ __noinline__ void faces_vjp(const ModelD& M, const float* __restrict__ X, const float* __restrict__ kbar,
-                                          float* __restrict__ zarena, float* __restrict__ gbar) {
+                                          float* __restrict__ zarena, float* __restrict__ gbar, float* __restrict__ pg /*[5] or null*/) {
   const int N = M.Nz, nfaces = N + 1;
   const bool has_nn = M.n_nets > 0;
   if (M.variant == RHS_FC) {
@@ -88,15 +91,47 @@ __device__ __noinline__ void faces_vjp(const ModelD& M, const float* __restrict_
   }
   const bool mpp = (M.flags & F_MPP) || M.variant == RHS_INFER;
   const float eps = M.variant == RHS_TRAIN ? M.rc.eps : 0.f;
+  // smoothing filters of the training RHS (NDE_training.jl:98-102,121-123; filtering_operators.jl:1-15): both are linear
+  // width-3 running means, so their VJP is the same stencil transposed. These variants are rare, so the neighbouring
+  // faces' quantities are simply recomputed per thread instead of staged.
+  const bool smooth_nn = M.variant == RHS_TRAIN && (M.flags & F_SMOOTH_NN) && has_nn;
+  const bool smooth_ri = M.variant == RHS_TRAIN && (M.flags & F_SMOOTH_RI) && mpp;
+  constexpr float third = 1.f / 3.f;
   for (int i = threadIdx.x; i < nfaces * CT; i += NT) {
     const int f = i / CT, c = i - f * CT;
+    // cotangent of the total flux of field q at interior face k (0 at the boundary faces: their fluxes are data)
+    auto ebq = [&](int q, int k) -> float {
+      return (k > 0 && k < N) ? M.rc.A[q] * M.rc.Nf * (kbar[(q * N + k) * CT + c] - kbar[(q * N + k - 1) * CT + c]) : 0.f;
+    };
+    auto ri_used = [&](int k) -> float {  // the Richardson number the diffusivity at interior face k is evaluated at
+      if (!smooth_ri) return ri_face(M, X, k, c, CT, eps);
+      return (ri_face(M, X, k - 1, c, CT, eps) + ri_face(M, X, k, c, CT, eps) + ri_face(M, X, k + 1, c, CT, eps)) * third;
+    };
+    auto rib_used = [&](int k) -> float {  // cotangent of ri_used(k)
+      if (k < 1 || k > N - 1) return 0.f;
+      const float Gu = M.rc.Nf * (X[k * CT + c] - X[(k - 1) * CT + c]);
+      const float Gv = M.rc.Nf * (X[(N + k) * CT + c] - X[(N + k - 1) * CT + c]);
+      const float GT = M.rc.Nf * (X[(2 * N + k) * CT + c] - X[(2 * N + k - 1) * CT + c]);
+      const float y2 = 2.f * (ri_used(k) - M.rc.Ric) * M.rc.inv_dRi;
+      const float s = __fdividef(1.f, 1.f + __expf(y2));
+      const float nub = -(M.rc.c[0] * Gu * ebq(0, k) + M.rc.c[1] * Gv * ebq(1, k) + M.rc.inv_Pr * M.rc.c[2] * GT * ebq(2, k));
+      return nub * (-2.f * M.rc.inv_dRi * M.rc.nu_m * s * (1.f - s));
+    };
     float gb[3] = {0.f, 0.f, 0.f};
     if (f > 0 && f < N) {
       float eb[3];
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
-        eb[q] = M.rc.A[q] * M.rc.Nf * (kbar[(q * N + f) * CT + c] - kbar[(q * N + f - 1) * CT + c]);
-        if (has_nn) zarena[(M.nn_off[q] + f - 1) * CT + c] = eb[q];
+        eb[q] = ebq(q, f);
+        if (has_nn) {
+          float nb = eb[q];
+          if (smooth_nn) {  // transposed filter: output j = f-1 of the N-1 NN outputs collects rows j-1, j, j+1
+            const int j = f - 1, n = N - 1;
+            nb = 0.f;
+            for (int r = max(j - 1, 0); r <= min(j + 1, n - 1); ++r) nb += ((r == 0 || r == n - 1) ? 0.5f : third) * ebq(q, r + 1);
+          }
+          zarena[(M.nn_off[q] + f - 1) * CT + c] = nb;
+        }
       }
       const float Gu = M.rc.Nf * (X[f * CT + c] - X[(f - 1) * CT + c]);
       const float Gv = M.rc.Nf * (X[(N + f) * CT + c] - X[(N + f - 1) * CT + c]);
@@ -107,7 +142,7 @@ __device__ __noinline__ void faces_vjp(const ModelD& M, const float* __restrict_
         const float S2 = su * su + sv * sv;
         const float iS2 = __fdividef(1.f, S2);
         const float Ri = M.rc.BzC * gT * iS2;
-        const float y2 = 2.f * (Ri - M.rc.Ric) * M.rc.inv_dRi;
+        const float y2 = 2.f * ((smooth_ri ? ri_used(f) : Ri) - M.rc.Ric) * M.rc.inv_dRi;
         const float s = __fdividef(1.f, 1.f + __expf(y2));
         const float nu = M.rc.nu0 + M.rc.nu_m * s;
         float nuT = nu * M.rc.inv_Pr, dnuT = M.rc.inv_Pr;
@@ -121,7 +156,18 @@ __device__ __noinline__ void faces_vjp(const ModelD& M, const float* __restrict_
         gb[2] = M.rc.c[2] * nuT * DT;
         const float nub = M.rc.c[0] * Gu * Du + M.rc.c[1] * Gv * Dv + dnuT * M.rc.c[2] * GT * DT;
         // s(1-s) underflows cleanly to 0 for |y| large; inf*0 cannot occur because s is in [0,1]
-        const float Rib = nub * (-2.f * M.rc.inv_dRi * M.rc.nu_m * s * (1.f - s));
+        float Rib = nub * (-2.f * M.rc.inv_dRi * M.rc.nu_m * s * (1.f - s));
+        if (smooth_ri) Rib = (rib_used(f - 1) + Rib + rib_used(f + 1)) * third;  // transposed face filter (interior rows only)
+        if (pg != nullptr && !smooth_ri) {
+          // gradient wrt p = (nu0, nu_m, dRi, Ric, Pr) of `DE` (diffusivity_parameter_optimisation.jl:2,20): nu = nu0 + nu_m s(y),
+          // s = 1/(1+e^y), y = 2 (Ri - Ric)/dRi; nu_T = nu/Pr. nub is the cotangent of nu at this face and stage.
+          const float ss = s * (1.f - s);
+          pg[0] += nub;
+          pg[1] += nub * s;
+          pg[2] += nub * M.rc.nu_m * ss * y2 * M.rc.inv_dRi;
+          pg[3] += nub * M.rc.nu_m * ss * 2.f * M.rc.inv_dRi;
+          if (dnuT != 0.f) pg[4] += eb[2] * M.rc.c[2] * nu * GT * M.rc.inv_Pr * M.rc.inv_Pr;
+        }
         gb[2] += Rib * M.rc.BzC * iS2;
         const float t = -Rib * Ri * iS2 * 2.f;
         gb[0] += t * M.rc.sig_u * su;
@@ -482,6 +528,7 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, 
   float* gflux = arena + M.flux_off * CT;
   uint32_t parity = 0;
   float lsum[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float pgs[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   const int Lmax = M.n_gemm > 0 ? last_layer_of<CT, NT>(M) : -1;
   PhaseCache pc;
   build_phase_cache<WS, CT, NT>(M, pc);
@@ -628,7 +675,7 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, 
           }
           CPZ_APROF_ADD(2, pb1);
           const long long pb2 = CPZ_APROF_T();
-          faces_vjp<CT, NT>(M, in, xb, zarena, gflux);
+          faces_vjp<CT, NT>(M, in, xb, zarena, gflux, a.want_pgrad ? pgs : nullptr);
           __syncthreads();
           centres_vjp<CT, NT>(M, xb, gflux);
           __syncthreads();
@@ -666,16 +713,16 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, 
       }
     }
   }
-  // block reduction of the six loss sums
-  for (int q = 0; q < 6; ++q) {
-    float v = lsum[q];
+  // block reduction of the six loss sums and the five mPP-parameter gradient sums
+  for (int q = 0; q < 11; ++q) {
+    float v = q < 6 ? lsum[q] : pgs[q - 6];
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
     if (threadIdx.x == 0) {
       float s = 0.f;
       for (int wdx = 0; wdx < NT / 32; ++wdx) s += red[wdx];
-      a.lpart[(size_t)blockIdx.x * 8 + q] = s;
+      a.lpart[(size_t)blockIdx.x * LP + (q < 6 ? q : LP / 2 + q - 6)] = s;
     }
     __syncthreads();
   }

@@ -83,20 +83,20 @@ static int rebuild_plans(cpz_model* m) {
   bo.smem_budget = m->ctx->smem_optin;
   bo.other_smem_bytes = adjoint_other_smem(m->desc.n_fields * m->desc.Nz, m->desc.n_fields == 3 ? 6 : 2, m->CT);
   m->has_bwd = build_plan(m->desc, bo, m->bwd, m->bwd_err);
-  {
-    const int cs = cpz_model::CT_SMALL;
+  for (int i = 0; i < cpz_model::N_SMALL; ++i) {
+    const int cs = cpz_model::small_ct(i);
     PlanOptions fs = fo, bs = bo;
     std::string es;
     fs.CT = cs; fs.other_smem_bytes = solve_other_smem(m->desc, cs, m->tab.n_stages);
     bs.CT = cs; bs.other_smem_bytes = adjoint_other_smem(m->desc.n_fields * m->desc.Nz, m->desc.n_fields == 3 ? 6 : 2, cs);
-    m->has_small = m->has_bwd && build_plan(m->desc, fs, m->fwd_s, es) && build_plan(m->desc, bs, m->bwd_s, es);
-    // both adjoint plans must describe the same gradient slab (one index map, one reduction kernel)
-    if (m->has_small) {
-      const ModelD &A = m->bwd.M, &B = m->bwd_s.M;
+    m->has_small[i] = m->has_bwd && build_plan(m->desc, fs, m->fwd_s[i], es) && build_plan(m->desc, bs, m->bwd_s[i], es);
+    // every adjoint plan must describe the same gradient slab (one index map, one reduction kernel)
+    if (m->has_small[i]) {
+      const ModelD &A = m->bwd.M, &B = m->bwd_s[i].M;
       bool same = A.slab == B.slab && A.n_gemm == B.n_gemm;
       for (int gi = 0; same && gi < A.n_gemm; ++gi)
         same = A.gemm[gi].gw_off == B.gemm[gi].gw_off && A.gemm[gi].gb_off == B.gemm[gi].gb_off && A.gemm[gi].w_off == B.gemm[gi].w_off;
-      m->has_small = same;
+      m->has_small[i] = same;
     }
   }
   if (m->has_bwd && m->P > 0) {
@@ -293,9 +293,10 @@ int cpz_model_describe(const cpz_model* m, char* buf, size_t buf_len) {
   dump("forward", m->fwd, solve_other_smem(m->desc, m->CT, m->tab.n_stages));
   if (m->has_bwd) dump("adjoint", m->bwd, adjoint_other_smem(m->desc.n_fields * m->desc.Nz, m->desc.n_fields == 3 ? 6 : 2, m->CT));
   else s += "adjoint plan: unavailable (" + m->bwd_err + ")\n";
-  if (m->has_small) {
-    snprintf(line, sizeof(line), "small-batch training pass: %d-column tiles (FP32 forward + adjoint) up to %d columns\n", cpz_model::CT_SMALL,
-             cpz_model::CT_SMALL * (m->ctx->sm_count > 0 ? m->ctx->sm_count : 148));
+  if (m->has_small[0]) {
+    const int sms = m->ctx->sm_count > 0 ? m->ctx->sm_count : 148;
+    snprintf(line, sizeof(line), "small-batch training pass: 4- / 8- / 16-column adjoint tiles while the batch fits one wave (up to %d / %d / %d columns)\n",
+             4 * sms, 8 * sms, 16 * sms);
     s += line;
   }
   snprintf(buf, buf_len, "%s", s.c_str());
@@ -417,6 +418,7 @@ int cpz_solve(cpz_model* m, const float* x0, const float* bcs, const float* diur
   if ((m->desc.flags & CPZ_FLAG_DIURNAL) && !diurnal_Q) return fail(CPZ_ERR_INVALID, "diurnal model needs diurnal_Q");
   if (ncol > (size_t)INT32_MAX / 512) return fail(CPZ_ERR_INVALID, "ncol too large");
   if ((rc = bind_device(m->ctx))) return rc;
+  if ((rc = begin_host_call(m->ctx))) return rc;
   if ((rc = upload_inputs(m, x0, bcs, diurnal_Q, ncol))) return rc;
   const size_t S = (size_t)m->fwd.M.S;
   const int n_saved = n_saved_of(m->tm);

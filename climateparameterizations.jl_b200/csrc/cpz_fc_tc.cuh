@@ -16,7 +16,9 @@ namespace cpz {
 // stage input X sits in the first 32 columns of the activation planes, the layer-3 accumulator in the first 32
 // accumulator columns), the other set does its column work in registers (flux divergence, Runge-Kutta combination
 // against the global stage slots, frame stores). Phases are separated by CTA barriers; TMEM is owned by one set per phase.
-template <int ACT>
+// MPP: the mPP base diffusivity term (BASELINE config 1) is compiled only into its own instantiation, so that the plain
+// FreeConvectionNDE / ConvectiveAdjustmentNDE kernel (config 4) carries none of its registers or instructions.
+template <int ACT, bool MPP>
 __global__ void __launch_bounds__(CTC_NT, 1) solve_fc_tc_kernel(const __grid_constant__ ClosureTcD C, const __grid_constant__ ModelD M,
                                                                 const __grid_constant__ TableauD tab, const TimeD tm, const SolveArgs a,
                                                                 const float* __restrict__ img, float* __restrict__ kscr, const int n_pair_ctas) {
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(CTC_NT, 1) solve_fc_tc_kernel(const __grid_con
   const float bc_b = __ldg(a.bcs + (size_t)colc * 2), bc_t = __ldg(a.bcs + (size_t)colc * 2 + 1);
 #pragma unroll
   for (int k = 0; k < N; ++k) { X[k] = x[k]; nn[k] = 0.f; }
-  const bool ca = (M.flags & F_CA) != 0, mpp1 = (M.flags & F_MPP) != 0;
+  const bool ca = (M.flags & F_CA) != 0;
   const float ANf = M.rc.A[2] * M.rc.Nf, Nf = M.rc.Nf, Kca = M.rc.K_ca;
   const float h = tm.dt / (float)tm.n_substeps;
   const int ns = tab.n_stages;
@@ -158,9 +160,11 @@ __global__ void __launch_bounds__(CTC_NT, 1) solve_fc_tc_kernel(const __grid_con
         if (k == N - 1) Ehi = bc_t;
         else {
           Ehi = nn[k] + b3[k];
-          const float G = Nf * (X[k + 1] - X[k]);
-          if (mpp1) Ehi -= fc_mpp_cnu(M, G) * G;   // mPP base at u = v = 0 (BASELINE config 1)
-          if (ca) Ehi -= fminf(0.f, Kca * G);
+          if constexpr (MPP) {
+            const float G = Nf * (X[k + 1] - X[k]);
+            Ehi -= fc_mpp_cnu(M, G) * G;   // mPP base at u = v = 0 (BASELINE config 1)
+          }
+          if (ca) Ehi -= fminf(0.f, Kca * (Nf * (X[k + 1] - X[k])));
         }
         dx[k] = -ANf * (Ehi - Elo);
         Elo = Ehi;

@@ -21,8 +21,9 @@ struct cpz_ctx {
   cudaStream_t copy_stream = nullptr;  // D2H of finished trajectory chunks, overlapped with the next chunk's kernel
   cudaEvent_t chunk_ev[2] = {nullptr, nullptr};
   size_t smem_optin = 0;
-  unsigned int* d_nonfinite = nullptr;  // device counter of non-finite values seen in results (CPZ_ERR_NONFINITE)
-  unsigned int nonfinite_seen = 0;      // value of the counter at the last host read
+  // device counters of non-finite values seen in results (CPZ_ERR_NONFINITE): [0] cumulative since the context was
+  // created (what the *_dev flavours report through cpz_ctx_nonfinite_count), [1] of the current host-flavour call
+  unsigned int* d_nonfinite = nullptr;
 };
 
 struct DevBuf {
@@ -39,13 +40,14 @@ struct cpz_model {
   bool has_bwd = false;
   // the same two plans for CT_SMALL-column tiles: small batches (BASELINE config 1: one column; the reference's 9-18
   // simulations) and shards too small to give every SM a 32-column tile run on these
-  cpz::Plan fwd_s, bwd_s;
-  bool has_small = false;
+  static constexpr int N_SMALL = 3;
+  static constexpr int small_ct(int i) { return 4 << i; }  // 4, 8, 16
+  cpz::Plan fwd_s[N_SMALL], bwd_s[N_SMALL];
+  bool has_small[N_SMALL] = {false, false, false};
   std::string bwd_err;
   TableauD tab;
   TimeD tm;
   int CT = 32, NT = 256;
-  static constexpr int CT_SMALL = 4;
   // parameters and optimiser state (device)
   float* d_theta = nullptr;
   float* d_m = nullptr;

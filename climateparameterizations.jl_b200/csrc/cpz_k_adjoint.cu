@@ -3,7 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 
-#include "cpz_launch.h"
+#include "cpz_adjoint_launch.h"
 
 namespace cpz {
 
@@ -21,17 +21,18 @@ __global__ void reduce_slabs_kernel(const float* __restrict__ part, int n_slabs,
 }
 
 // pack[0..P) = grad (unnormalised here: normalisation is folded into the loss cotangent), pack[P..P+6) = raw squared-error
-// sums, pack[P+6] = column count, pack[P+7] = 0.
-__global__ void pack_loss_kernel(const float* __restrict__ lpart, int n_slabs, float ncol, float* __restrict__ pack_tail) {
+// sums, pack[P+6] = column count, pack[P+7] = 0, pack[P+8..P+13) = gradient sums wrt the five mPP parameters, rest 0.
+// `stride` floats per partial row (LP from the adjoint kernel, 8 from the loss-only path).
+__global__ void pack_loss_kernel(const float* __restrict__ lpart, int n_slabs, int stride, float ncol, float* __restrict__ pack_tail) {
   const int q = threadIdx.x;
-  if (q < 6) {
+  if (q < 6 || (q >= 8 && q < 13 && stride >= 16)) {
     float s = 0.f;
-    for (int t = 0; t < n_slabs; ++t) s += lpart[(size_t)t * 8 + q];
+    for (int t = 0; t < n_slabs; ++t) s += lpart[(size_t)t * stride + q];
     pack_tail[q] = s;
   } else if (q == 6) {
     pack_tail[6] = ncol;
-  } else if (q == 7) {
-    pack_tail[7] = 0.f;
+  } else if (q < 16) {
+    pack_tail[q] = 0.f;
   }
 }
 
@@ -47,7 +48,7 @@ __global__ void finalize_loss_kernel(const float* __restrict__ pack_tail, const 
       tot += v;
     }
     loss_out[6] = tot;
-    if (tot - tot != 0.f) atomicAdd(nonfinite, 1u);  // NaN / Inf loss: reported as CPZ_ERR_NONFINITE by the host flavours
+    if (tot - tot != 0.f) { atomicAdd(nonfinite, 1u); atomicAdd(nonfinite + 1, 1u); }  // NaN / Inf loss: reported as CPZ_ERR_NONFINITE by the host flavours
   }
 }
 
@@ -90,13 +91,13 @@ __global__ void check_finite_kernel(const float* __restrict__ p, size_t stride, 
       bad += (v - v != 0.f) ? 1u : 0u;  // NaN or +-Inf
     }
   bad = __reduce_add_sync(0xffffffffu, bad);
-  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(counter, bad);
+  if ((threadIdx.x & 31) == 0 && bad) { atomicAdd(counter, bad); atomicAdd(counter + 1, bad); }
 }
 
-// grad[p] *= scale
+// grad[p] *= 1/ncol_global, for the theta gradient [0, P) and the mPP-parameter gradient at [P+8, P+13)
 __global__ void scale_kernel(float* __restrict__ g, int P, const float* __restrict__ pack_tail) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < P) g[p] *= 1.f / pack_tail[6];
+  if (p < P || (p >= P + 8 && p < P + 13)) g[p] *= 1.f / pack_tail[6];
 }
 
 // Flux 0.11 ADAM: m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; theta -= lr * m/(1-bp1) / (sqrt(v/(1-bp2)) + eps)
@@ -113,41 +114,11 @@ __global__ void adam_kernel(float* __restrict__ theta, float* __restrict__ m, fl
 }
 
 
-template <int CT, int NT, bool WS>
-static int launch_adjoint_t(cpz_model* m, const AdjArgs& a, int grid) {
-  const AdjSmem L = adjoint_smem_layout(m->bwd.M, CT);
-  const size_t smem = (size_t)L.total_floats * sizeof(float);
-  if (smem > m->ctx->smem_optin) return fail(CPZ_ERR_INVALID, "adjoint kernel needs %zu B shared memory, device allows %zu", smem, m->ctx->smem_optin);
-  auto kern = adjoint_kernel<CT, NT, WS>;
-  CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  static const bool prof = getenv("CPZ_PROF") != nullptr;
-  if (prof) {
-    AdjArgs ap = a;
-    unsigned long long* d = nullptr;
-    CPZ_CUDA(cudaMalloc(&d, 8 * sizeof(unsigned long long)));
-    CPZ_CUDA(cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), m->ctx->stream));
-    ap.prof = d;
-    kern<<<grid, NT, smem, m->ctx->stream>>>(m->bwd.M, m->tab, m->tm, ap);
-    unsigned long long hc[8];
-    CPZ_CUDA(cudaMemcpyAsync(hc, d, sizeof(hc), cudaMemcpyDeviceToHost, m->ctx->stream));
-    CPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));
-    cudaFree(d);
-    const int tiles0 = (a.n_tiles + grid - 1) / grid;  // tiles processed by CTA 0
-    const double nrk = (double)m->tm.n_steps * m->tm.n_substeps * tiles0, nst = nrk * m->tab.n_stages;
-    fprintf(stderr, "[cpz prof adjoint] cycles per RK step: fwd-recompute(5 stages) %.0f | per reverse stage: combine+store %.0f mlp-fwd %.0f stencil-vjp %.0f bwd-L0 %.0f bwd-L1 %.0f bwd-L2+ %.0f\n",
-            hc[0] / nrk, hc[1] / nst, hc[2] / nst, hc[3] / nst, hc[4] / nst, hc[5] / nst, hc[6] / nst);
-    m->ctx->launches++;
-    return CPZ_OK;
-  }
-  kern<<<grid, NT, smem, m->ctx->stream>>>(m->bwd.M, m->tab, m->tm, a);
-  CPZ_CUDA(cudaGetLastError());
-  m->ctx->launches++;
-  return CPZ_OK;
-}
+static int ensure_counters(cpz_ctx* c);
 
 int launch_adjoint(cpz_model* m, const AdjArgs& a, int grid) {
-  if (m->bwd.M.w_in_smem) return launch_adjoint_t<32, 256, true>(m, a, grid);
-  return launch_adjoint_t<32, 256, false>(m, a, grid);
+  if (m->bwd.M.w_in_smem) return launch_adjoint_t<32, 256, true>(m, m->bwd, a, grid);
+  return launch_adjoint_t<32, 256, false>(m, m->bwd, a, grid);
 }
 
 #define CPZ_LAUNCHED(m)            \
@@ -159,17 +130,14 @@ int launch_reduce_slabs(cpz_model* m, const float* part, int n_slabs, int P, flo
   reduce_slabs_kernel<<<(P + 255) / 256, 256, 0, m->ctx->stream>>>(part, n_slabs, m->bwd.M.slab, m->d_gmap, P, out);
   CPZ_LAUNCHED(m);
 }
-int launch_pack_loss(cpz_model* m, const float* lpart, int n_slabs, float ncol, float* pack_tail) {
-  pack_loss_kernel<<<1, 32, 0, m->ctx->stream>>>(lpart, n_slabs, ncol, pack_tail);
+int launch_pack_loss(cpz_model* m, const float* lpart, int n_slabs, int stride, float ncol, float* pack_tail) {
+  pack_loss_kernel<<<1, 32, 0, m->ctx->stream>>>(lpart, n_slabs, stride, ncol, pack_tail);
   CPZ_LAUNCHED(m);
 }
 int launch_finalize_loss(cpz_model* m, const float* pack_tail, const float* w6, float inv_prof, float inv_grad, float* loss_out) {
   W6 w;
   for (int q = 0; q < 6; ++q) w.w[q] = w6[q];
-  if (!m->ctx->d_nonfinite) {
-    CPZ_CUDA(cudaMalloc(&m->ctx->d_nonfinite, sizeof(unsigned int)));
-    CPZ_CUDA(cudaMemsetAsync(m->ctx->d_nonfinite, 0, sizeof(unsigned int), m->ctx->stream));
-  }
+  { int rc = ensure_counters(m->ctx); if (rc) return rc; }
   finalize_loss_kernel<<<1, 32, 0, m->ctx->stream>>>(pack_tail, w, inv_prof, inv_grad, loss_out, m->ctx->d_nonfinite);
   CPZ_LAUNCHED(m);
 }
@@ -177,11 +145,22 @@ int launch_loss_traj(cpz_model* m, const float* traj, const float* tgt, int ncol
   loss_traj_kernel<<<(unsigned)ncol, 256, 0, m->ctx->stream>>>(traj, tgt, n_saved, S, Nz, nf, (float)Nz, lpart);
   CPZ_LAUNCHED(m);
 }
-int launch_check_finite(cpz_ctx* c, const float* p, size_t stride, int ncol, int S) {
+static int ensure_counters(cpz_ctx* c) {
   if (!c->d_nonfinite) {
-    CPZ_CUDA(cudaMalloc(&c->d_nonfinite, sizeof(unsigned int)));
-    CPZ_CUDA(cudaMemsetAsync(c->d_nonfinite, 0, sizeof(unsigned int), c->stream));
+    CPZ_CUDA(cudaMalloc(&c->d_nonfinite, 2 * sizeof(unsigned int)));
+    CPZ_CUDA(cudaMemsetAsync(c->d_nonfinite, 0, 2 * sizeof(unsigned int), c->stream));
   }
+  return CPZ_OK;
+}
+int begin_host_call(cpz_ctx* c) {
+  int rc = ensure_counters(c);
+  if (rc) return rc;
+  CPZ_CUDA(cudaMemsetAsync(c->d_nonfinite + 1, 0, sizeof(unsigned int), c->stream));
+  return CPZ_OK;
+}
+int launch_check_finite(cpz_ctx* c, const float* p, size_t stride, int ncol, int S) {
+  int rc = ensure_counters(c);
+  if (rc) return rc;
   check_finite_kernel<<<std::min(ncol, 592), 128, 0, c->stream>>>(p, stride, ncol, S, c->d_nonfinite);
   CPZ_CUDA(cudaGetLastError());
   c->launches++;
@@ -189,16 +168,14 @@ int launch_check_finite(cpz_ctx* c, const float* p, size_t stride, int ncol, int
 }
 int report_nonfinite(cpz_ctx* c, const char* what) {
   if (!c->d_nonfinite) return CPZ_OK;
-  unsigned int n = 0;
-  CPZ_CUDA(cudaMemcpyAsync(&n, c->d_nonfinite, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
+  unsigned int fresh = 0;
+  CPZ_CUDA(cudaMemcpyAsync(&fresh, c->d_nonfinite + 1, sizeof(fresh), cudaMemcpyDeviceToHost, c->stream));
   CPZ_CUDA(cudaStreamSynchronize(c->stream));
-  const unsigned int fresh = n - c->nonfinite_seen;
-  c->nonfinite_seen = n;
   if (fresh) return fail(CPZ_ERR_NONFINITE, "%u non-finite value(s) in %s (results are returned as computed)", fresh, what);
   return CPZ_OK;
 }
 int launch_scale(cpz_model* m, float* g, int P, const float* pack_tail) {
-  scale_kernel<<<(P + 255) / 256, 256, 0, m->ctx->stream>>>(g, P, pack_tail);
+  scale_kernel<<<(P + 16 + 255) / 256, 256, 0, m->ctx->stream>>>(g, P, pack_tail);
   CPZ_LAUNCHED(m);
 }
 int launch_adam(cpz_model* m, const float* g, float lr, float b1, float b2, float eps) {

@@ -89,9 +89,9 @@ static int ensure_image(cpz_model* m, const ClosureTcD& C, const float* theta) {
   return CPZ_OK;
 }
 
-template <int ACT>
+template <int ACT, bool MPP>
 static int launch_fc_tc_t(cpz_model* m, const ClosureTcD& C, const SolveArgs& a) {
-  auto kern = solve_fc_tc_kernel<ACT>;
+  auto kern = solve_fc_tc_kernel<ACT, MPP>;
   CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C.img_bytes));
   const int n_tiles = (a.ncol + CTC_TILE - 1) / CTC_TILE;
   // full waves of two-tile CTAs; a remainder that fits one wave of single-tile CTAs runs as such (a single tile per CTA
@@ -121,9 +121,13 @@ int launch_solve_fc_tc(cpz_model* m, const SolveArgs& a) {
     m->b_fcscr.cap = need;
   }
   const bool same = C.act1 == C.act2;
-  if (same && C.act1 == ACT_RELU) return launch_fc_tc_t<ACT_RELU>(m, C, a);
-  if (same && C.act1 == ACT_MISH) return launch_fc_tc_t<ACT_MISH>(m, C, a);
-  return launch_fc_tc_t<-1>(m, C, a);
+  if (m->desc.flags & CPZ_FLAG_MPP) {  // T-only model with the mPP base (BASELINE config 1)
+    if (same && C.act1 == ACT_RELU) return launch_fc_tc_t<ACT_RELU, true>(m, C, a);
+    return launch_fc_tc_t<-1, true>(m, C, a);
+  }
+  if (same && C.act1 == ACT_RELU) return launch_fc_tc_t<ACT_RELU, false>(m, C, a);
+  if (same && C.act1 == ACT_MISH) return launch_fc_tc_t<ACT_MISH, false>(m, C, a);
+  return launch_fc_tc_t<-1, false>(m, C, a);
 }
 
 int launch_closure(cpz_model* m, const ClosureD& cd, const ClosureArgs& a) {

@@ -1,44 +1,27 @@
-// CT_SMALL-column-tile instantiations of the FP32 forward-solve and adjoint kernels (see train_tile in cpz_k_solve.cu).
-#include <cstdlib>
-
-#include "cpz_launch.h"
+// Small-column-tile instantiations of the FP32 forward-solve and adjoint kernels (see train_tile in cpz_k_solve.cu).
+// One translation unit per tile width (cpz_k_small.cu: 4, cpz_k_small8.cu: 8, cpz_k_small16.cu: 16) so that they compile
+// in parallel; this file also holds the dispatch.
+#include "cpz_small_impl.h"
 
 namespace cpz {
 
-template <bool WS>
-static int solve_small_t(cpz_model* m, const SolveArgs& a) {
-  constexpr int CT = cpz_model::CT_SMALL, NT = 256;
-  const SolveSmem L = solve_smem_layout(m->fwd_s.M, CT, m->tab.n_stages);
-  const size_t smem = (size_t)L.total_floats * sizeof(float);
-  if (smem > m->ctx->smem_optin) return fail(CPZ_ERR_INVALID, "small-tile forward kernel needs %zu B shared memory, device allows %zu", smem, m->ctx->smem_optin);
-  auto kern = solve_kernel<CT, NT, WS>;
-  CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(a.ncol + CT - 1) / CT, NT, smem, m->ctx->stream>>>(m->fwd_s.M, m->tab, m->tm, a);
-  CPZ_CUDA(cudaGetLastError());
-  m->ctx->launches++;
-  return CPZ_OK;
-}
+CPZ_SMALL_DEFINE(4)
 
-int launch_solve_small(cpz_model* m, const SolveArgs& a) {
-  return m->fwd_s.M.w_in_smem ? solve_small_t<true>(m, a) : solve_small_t<false>(m, a);
+int launch_solve_small(cpz_model* m, const SolveArgs& a, int CT) {
+  switch (CT) {
+    case 4: return solve_small_4(m, a);
+    case 8: return solve_small_8(m, a);
+    case 16: return solve_small_16(m, a);
+    default: return fail(CPZ_ERR_INVALID, "no forward kernel for %d-column tiles", CT);
+  }
 }
-
-template <bool WS>
-static int adjoint_small_t(cpz_model* m, const AdjArgs& a, int grid) {
-  constexpr int CT = cpz_model::CT_SMALL, NT = 256;
-  const AdjSmem L = adjoint_smem_layout(m->bwd_s.M, CT);
-  const size_t smem = (size_t)L.total_floats * sizeof(float);
-  if (smem > m->ctx->smem_optin) return fail(CPZ_ERR_INVALID, "small-tile adjoint kernel needs %zu B shared memory, device allows %zu", smem, m->ctx->smem_optin);
-  auto kern = adjoint_kernel<CT, NT, WS>;
-  CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, NT, smem, m->ctx->stream>>>(m->bwd_s.M, m->tab, m->tm, a);
-  CPZ_CUDA(cudaGetLastError());
-  m->ctx->launches++;
-  return CPZ_OK;
-}
-
-int launch_adjoint_small(cpz_model* m, const AdjArgs& a, int grid) {
-  return m->bwd_s.M.w_in_smem ? adjoint_small_t<true>(m, a, grid) : adjoint_small_t<false>(m, a, grid);
+int launch_adjoint_small(cpz_model* m, const AdjArgs& a, int grid, int CT) {
+  switch (CT) {
+    case 4: return adjoint_small_4(m, a, grid);
+    case 8: return adjoint_small_8(m, a, grid);
+    case 16: return adjoint_small_16(m, a, grid);
+    default: return fail(CPZ_ERR_INVALID, "no adjoint kernel for %d-column tiles", CT);
+  }
 }
 
 }  // namespace cpz

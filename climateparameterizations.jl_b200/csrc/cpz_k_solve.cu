@@ -38,15 +38,20 @@ static int launch_solve_t(cpz_model* m, const SolveArgs& a) {
   return CPZ_OK;
 }
 
-// Column tile of the training pass. 32 columns per CTA is the efficient shape; CT_SMALL-column tiles take over while
-// they still fit one wave of the device (ncol <= CT_SMALL * SMs): a 4-column tile runs several times faster than a
-// 32-column one, so small batches (one column in BASELINE config 1, the reference's 9-18 simulations) and small shards
-// (1 152 columns per GPU in config 3 on eight GPUs = 36 tiles of 32 on 148 SMs) finish sooner. CPZ_SMALL_NCOL overrides.
+// Column tile of the training pass. The adjoint kernel is latency-bound per Runge–Kutta stage (measured: a 4-column tile
+// takes 0.59 of the time of a 32-column one), so the smallest tile that still fits ONE wave of the device is the fastest:
+// 4-, 8- or 16-column tiles for batches up to 4, 8 or 16 x SMs columns (one column in BASELINE config 1, the reference's
+// 9-18 simulations, 1 152 / 2 304 columns per GPU of config 3 on eight / four GPUs), 32-column tiles beyond.
+// CPZ_SMALL_NCOL overrides.
 int train_tile(const cpz_model* m, size_t ncol) {
-  if (!m->has_small) return m->CT;
-  const char* ov = getenv("CPZ_SMALL_NCOL");
-  const size_t lim = ov ? (size_t)atol(ov) : (size_t)cpz_model::CT_SMALL * (size_t)(m->ctx->sm_count > 0 ? m->ctx->sm_count : 148);
-  return ncol <= lim ? cpz_model::CT_SMALL : m->CT;
+  const char* ov = getenv("CPZ_SMALL_NCOL");  // "0": always 32-column tiles; n > 0: 4-column tiles up to n columns
+  const size_t sms = (size_t)(m->ctx->sm_count > 0 ? m->ctx->sm_count : 148);
+  if (ov) return (m->has_small[0] && ncol <= (size_t)atol(ov)) ? 4 : m->CT;
+  for (int i = 0; i < cpz_model::N_SMALL; ++i) {
+    const int ct = cpz_model::small_ct(i);
+    if (m->has_small[i] && (ncol + ct - 1) / ct <= sms) return ct;
+  }
+  return m->CT;
 }
 
 int launch_solve(cpz_model* m, const SolveArgs& a) {
@@ -63,7 +68,7 @@ int launch_solve(cpz_model* m, const SolveArgs& a) {
       if (rc <= 0) return rc;
     }
   }
-  if (a.small_tiles && a.ckpt != nullptr && m->has_small) return launch_solve_small(m, a);
+  if (a.small_tiles && a.ckpt != nullptr) return launch_solve_small(m, a, a.small_tiles);
   if (m->fwd.M.w_in_smem) return launch_solve_t<32, 256, true>(m, a);
   return launch_solve_t<32, 256, false>(m, a);
 }

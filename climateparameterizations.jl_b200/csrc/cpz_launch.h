@@ -15,19 +15,21 @@ bool closure_uses_tc(const cpz_model* m);  // NN-free u/v/T model; 1 = not eligi
 // one line for cpz_model_describe: which forward kernel this model runs on and why
 std::string tc_describe(const cpz_model* m);  // 1 = not eligible, use the SIMT kernel
 int launch_adjoint(cpz_model* m, const AdjArgs& a, int grid);
-// CT_SMALL-column-tile instantiations (cpz_k_small.cu)
-int launch_solve_small(cpz_model* m, const SolveArgs& a);
-int launch_adjoint_small(cpz_model* m, const AdjArgs& a, int grid);
+// 4-, 8- and 16-column-tile instantiations (cpz_k_small.cu, cpz_k_small8.cu, cpz_k_small16.cu); CT selects the plan
+int launch_solve_small(cpz_model* m, const SolveArgs& a, int CT);
+int launch_adjoint_small(cpz_model* m, const AdjArgs& a, int grid, int CT);
 // column tile the training pass (checkpointing forward + adjoint) uses for `ncol` columns
 int train_tile(const cpz_model* m, size_t ncol);
 int launch_closure(cpz_model* m, const ClosureD& cd, const ClosureArgs& a);
 int launch_reduce_slabs(cpz_model* m, const float* part, int n_slabs, int P, float* out);
-int launch_pack_loss(cpz_model* m, const float* lpart, int n_slabs, float ncol, float* pack_tail);
+int launch_pack_loss(cpz_model* m, const float* lpart, int n_slabs, int stride, float ncol, float* pack_tail);
 int launch_finalize_loss(cpz_model* m, const float* pack_tail, const float* w6, float inv_prof, float inv_grad, float* loss_out);
 int launch_loss_traj(cpz_model* m, const float* traj, const float* tgt, int ncol, int n_saved, int S, int Nz, int nf, float* lpart);
 // counts non-finite values of rows [ncol] x [S] (row stride `stride` floats) into the context's device counter
 int launch_check_finite(cpz_ctx* c, const float* p, size_t stride, int ncol, int S);
-// host flavours: read the counter (after a stream synchronise); returns CPZ_ERR_NONFINITE if it grew since the last read
+// host flavours: begin_host_call zeroes the per-call counter; report_nonfinite reads it (synchronises the stream) and
+// returns CPZ_ERR_NONFINITE when the call produced non-finite values
+int begin_host_call(cpz_ctx* c);
 int report_nonfinite(cpz_ctx* c, const char* what);
 int launch_scale(cpz_model* m, float* g, int P, const float* pack_tail);
 int launch_adam(cpz_model* m, const float* g, float lr, float b1, float b2, float eps);

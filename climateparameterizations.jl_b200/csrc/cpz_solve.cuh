@@ -21,7 +21,7 @@ struct SolveArgs {
   unsigned long long* prof;  // optional [8] cycle counters (CTA 0, thread 0): set CPZ_PROF=1 in the environment
   size_t x0_stride;          // floats between consecutive columns of x0 (0 = S); a trajectory frame can be the start state
   int skip_frame0;           // continuation of a chunked solve: the start state is already in the trajectory, do not store it
-  int small_tiles;           // host hint: a checkpointing solve whose adjoint runs on CT_SMALL-column tiles
+  int small_tiles;           // host hint: a checkpointing solve whose adjoint runs on tiles of this many (4, 8, 16) columns; 0 = 32
   float* kstore;             // optional [n_tiles][n_rk_steps][n_stages][S][32]: every stage tendency k_i, for the adjoint (tcgen05 solve only)
 };
 

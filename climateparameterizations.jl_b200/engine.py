@@ -19,7 +19,7 @@ EXPORTS = [
     "cpz_ctx_synchronize", "cpz_ctx_stream", "cpz_ctx_launch_count", "cpz_ctx_nonfinite_count", "cpz_model_create", "cpz_model_destroy",
     "cpz_model_n_params", "cpz_model_n_saved", "cpz_model_describe", "cpz_set_theta", "cpz_get_theta", "cpz_model_set_time", "cpz_rhs",
     "cpz_rhs_dev", "cpz_solve", "cpz_solve_dev", "cpz_loss_grad", "cpz_loss_grad_dev", "cpz_train_step",
-    "cpz_train_step_dev", "cpz_adam_get_state", "cpz_adam_set_state", "cpz_closure_step", "cpz_closure_step_dev",
+    "cpz_train_step_dev", "cpz_set_mpp_params", "cpz_get_mpp_params", "cpz_loss_grad_mpp", "cpz_loss_grad_mpp_dev", "cpz_adam_get_state", "cpz_adam_set_state", "cpz_closure_step", "cpz_closure_step_dev",
 ]
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
@@ -71,6 +71,10 @@ def lib() -> C.CDLL:
         getattr(L, name).argtypes = [vp, vp, vp, vp, vp, sz]
     for name in ("cpz_loss_grad", "cpz_loss_grad_dev"):
         getattr(L, name).argtypes = [vp, vp, vp, vp, vp, sz, vp, vp, vp]
+    for name in ("cpz_loss_grad_mpp", "cpz_loss_grad_mpp_dev"):
+        getattr(L, name).argtypes = [vp, vp, vp, vp, vp, sz, vp, vp, vp, vp]
+    L.cpz_set_mpp_params.argtypes = [vp, vp]
+    L.cpz_get_mpp_params.argtypes = [vp, vp]
     for name in ("cpz_train_step", "cpz_train_step_dev"):
         getattr(L, name).argtypes = [vp, vp, vp, vp, vp, sz, vp, f32, f32, f32, f32, vp]
     L.cpz_adam_get_state.argtypes = [vp, vp, vp, vp, sz]
@@ -259,6 +263,32 @@ class Model:
         _check(lib().cpz_loss_grad(self._h, _ptr(x0), _ptr(bcs), _ptr(Q), _ptr(targets), ncol, _ptr(w), _ptr(loss),
                                    _ptr(grad)))
         return loss, grad
+
+    def loss_grad_mpp(self, x0, bcs, targets, loss_w, Q=None, want_theta_grad: bool = False):
+        """(loss[7], d loss/d(nu0, nu_m, dRi, Ric, Pr) [5], theta gradient or None) — cpz_loss_grad_mpp."""
+        x0 = _np(x0)
+        ncol = x0.shape[0]
+        bcs = _np(bcs, (ncol, self.desc.n_bc))
+        targets = _np(targets, (ncol, self.n_saved, self.desc.S))
+        Q = None if Q is None else _np(Q, (ncol,))
+        w = _np(loss_w, (6,))
+        loss = np.zeros(7, dtype=np.float32)
+        gp = np.zeros(5, dtype=np.float32)
+        gt = np.zeros(self.P, dtype=np.float32) if (want_theta_grad and self.P > 0) else None
+        _check(lib().cpz_loss_grad_mpp(self._h, _ptr(x0), _ptr(bcs), _ptr(Q), _ptr(targets), ncol, _ptr(w), _ptr(loss),
+                                       _ptr(gt), _ptr(gp)))
+        return loss, gp, gt
+
+    def set_mpp_params(self, nu0, nu_m, dRi, Ric, Pr) -> None:
+        p = np.array([nu0, nu_m, dRi, Ric, Pr], dtype=np.float32)
+        _check(lib().cpz_set_mpp_params(self._h, _ptr(p)))
+        d = self.desc
+        d.nu0, d.nu_m, d.dRi, d.Ric, d.Pr = (float(v) for v in p)
+
+    def mpp_params(self) -> np.ndarray:
+        p = np.zeros(5, dtype=np.float32)
+        _check(lib().cpz_get_mpp_params(self._h, _ptr(p)))
+        return p
 
     def train_step(self, x0, bcs, targets, loss_w, lr, beta1=0.9, beta2=0.999, eps=1e-8, Q=None) -> np.ndarray:
         x0 = _np(x0)

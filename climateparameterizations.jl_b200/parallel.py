@@ -1,7 +1,8 @@
 """Column sharding across ranks (one process per GPU) and the single gradient allreduce.
 
 Forward / inference needs no communication: every rank integrates its contiguous block of columns.
-Training sums one packed buffer [grad (P); six squared-error sums; column count; pad] over ranks — the engine calls the
+Training sums one packed buffer [grad (P); six squared-error sums; column count; pad; five mPP-parameter gradient sums; pad]
+(P + 16 floats) over ranks — the engine calls the
 hook between the adjoint kernel and the fused ADAM update, on its own stream.
 """
 from __future__ import annotations
@@ -21,12 +22,12 @@ def shard_columns(ncol: int, rank: int, world: int) -> Tuple[int, int]:
 def pack_local(grad_unnormalised: np.ndarray, sq_sums: np.ndarray, ncol_local: int) -> np.ndarray:
     """Host-side statement of what the device packs before the allreduce (cpz_capi_train.inc: loss_grad_core)."""
     return np.concatenate([np.asarray(grad_unnormalised, dtype=np.float64), np.asarray(sq_sums, dtype=np.float64)[:6],
-                           [float(ncol_local), 0.0]])
+                           [float(ncol_local), 0.0], np.zeros(8)])  # [P+8, P+13): mPP-parameter gradient sums (cpz_loss_grad_mpp)
 
 
 def finalize(packed_sum: np.ndarray, loss_w: np.ndarray, Nz: int, n_saved: int):
     """Host-side statement of scale_kernel + finalize_loss_kernel: (grad, [6 weighted losses, total])."""
-    P = len(packed_sum) - 8
+    P = len(packed_sum) - 16
     ncol = packed_sum[P + 6]
     grad = packed_sum[:P] / ncol
     inv = np.array([1.0 / (Nz * n_saved)] * 3 + [1.0 / ((Nz + 1) * n_saved)] * 3)

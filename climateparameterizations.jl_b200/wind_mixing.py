@@ -318,3 +318,92 @@ def solve_NDE_mutating(uw_NN: Chain, vw_NN: Chain, wT_NN: Chain, scalings, const
         m.close()
         if own_ctx:
             ctx.close()
+
+
+# ---- diffusivity_parameter_optimisation.jl ----------------------------------------------------------------------------------
+MPP_KEYS = ("nu0", "nu_m", "dRi", "Ric", "Pr")
+
+
+def DE(x, p, t, scalings, constants, BCs, ctx: engine.Context, conditions: Optional[dict] = None):
+    """RHS of the NN-free base closure, p = (nu0, nu_m, dRi, Ric, Pr) (wind_mixing/src/diffusivity_parameter_optimisation.jl:1-33),
+    batched: x [ncol, 3Nz], BCs [ncol, 6] -> [ncol, 3Nz]."""
+    cond = dict(modified_pacanowski_philander=True, zero_weights=True)
+    cond.update(conditions or {})
+    c = dict(constants)
+    c.update(dict(zip(MPP_KEYS, map(float, p))))
+    d = _model_desc((), c, scalings, cond, RHS_TRAIN, constants["Nz"], "tsit5", 1.0, 0.0, 1, 1, 1, 1)
+    m = engine.Model(ctx, d, np.zeros(0, dtype=np.float32))
+    try:
+        return m.rhs(np.atleast_2d(x), np.atleast_2d(BCs), t=float(t))
+    finally:
+        m.close()
+
+
+def optimise_modified_pacanowski_philander(data: ProfileData, tsteps, timestepper, maxiters: int, *, nu0=1e-4, nu_m=1e-1, dRi=0.1,
+                                           Ric=0.25, Pr=1.0, f=1e-4, alpha=2e-4, g=9.80665, train_gradient=True,
+                                           gradient_scaling=5e-3, training_fractions=None, ctx: Optional[engine.Context] = None,
+                                           n_substeps: Optional[int] = None, callback: Optional[Callable] = None,
+                                           record: Optional[TrainingRecord] = None):
+    """wind_mixing/src/diffusivity_parameter_optimisation.jl:35-235: fit the five mPP parameters of the NN-free column model
+    to the profiles. As in the reference the optimiser works on p .* (1 ./ p_initial) inside the box [0, 10]^5
+    (`OptimizationProblem(..., lb=0, ub=10)` with `LBFGS()`, optimise_modified_pacanowski_philander.jl:40); the box-constrained
+    quasi-Newton iteration itself stays on the host (scipy L-BFGS-B), loss and gradient come from cpz_loss_grad_mpp.
+    Returns (dict of fitted parameters, TrainingRecord). dRi and Pr are kept >= 1e-6 (they divide)."""
+    from scipy.optimize import minimize
+
+    own_ctx = ctx is None
+    ctx = ctx or engine.Context(0)
+    Nz = data.Nz
+    H = abs(float(data.zF[-1] - data.zF[0]))
+    tau = abs(float(data.t[-1] - data.t[0]))
+    constants = dict(H=H, tau=tau, f=f, Nz=Nz, g=g, alpha=alpha, nu0=nu0, nu_m=nu_m, dRi=dRi, Ric=Ric, Pr=Pr)
+    scalings = {k: data.scalings[k] for k in ("u", "v", "T", "uw", "vw", "wT")}
+    conditions = dict(modified_pacanowski_philander=True, zero_weights=True)
+    integrator = _integrator(timestepper)
+    dt_hat, t0, n_steps, stride = _time_grid(data.t, tsteps, tau)
+    p_init = np.array([nu0, nu_m, dRi, Ric, Pr], dtype=np.float64)
+    if n_substeps is None:  # stable for diffusivities up to twice the initial nu0 + nu_m
+        c2 = dict(constants); c2["nu_m"] = 2 * nu_m; c2["nu0"] = 2 * nu0
+        n_substeps = default_substeps(c2, conditions, dt_hat, Nz, integrator)
+    tsteps = np.asarray(tsteps)
+    uvT0 = np.ascontiguousarray(data.uvT_scaled[:, tsteps[0]], dtype=np.float32)
+    targets = np.ascontiguousarray(data.uvT_scaled[:, tsteps], dtype=np.float32)
+    BCs = np.ascontiguousarray(data.bcs_scaled, dtype=np.float32)
+    d = _model_desc((), constants, scalings, conditions, RHS_TRAIN, Nz, integrator, dt_hat, t0, n_steps, n_substeps, stride, stride)
+    model = engine.Model(ctx, d, np.zeros(0, dtype=np.float32))
+    record = record if record is not None else TrainingRecord()
+    try:
+        if training_fractions is None:
+            gs = gradient_scaling if train_gradient else 0.0
+            loss_scalings = {"u": 1.0, "v": 1.0, "T": 1.0, "∂u∂z": gs, "∂v∂z": gs, "∂T∂z": gs}
+        else:
+            wu = np.array([1, 1, 1, 1, 1, 1] if train_gradient else [1, 1, 1, 0, 0, 0], dtype=np.float32)
+            l, _ = model.loss_grad(uvT0, BCs, targets, wu, want_grad=False)
+            loss_scalings = calculate_loss_scalings(dict(zip(LOSS_KEYS, map(float, l[:6]))), training_fractions, train_gradient)
+            if not train_gradient:
+                loss_scalings.update({"∂u∂z": 0.0, "∂v∂z": 0.0, "∂T∂z": 0.0})
+        record.loss_scalings = loss_scalings
+        w = np.array([loss_scalings[k] for k in LOSS_KEYS], dtype=np.float32)
+        best = {"loss": np.inf, "p": p_init.copy()}
+
+        def fun(scaled):
+            p = np.asarray(scaled, dtype=np.float64) * p_init  # unscale_parameter (:50-52)
+            p[2] = max(p[2], 1e-6); p[4] = max(p[4], 1e-6)
+            model.set_mpp_params(*p)
+            l, gp, _ = model.loss_grad_mpp(uvT0, BCs, targets, w)
+            total = float(l[6])
+            losses = dict(zip(LOSS_KEYS, map(float, l[:6])))
+            record.losses.append(losses); record.totals.append(total)
+            if total < best["loss"]:
+                best["loss"], best["p"] = total, p.copy()
+            log.info("nu0 = %g, nu_m = %g, dRi = %g, Ric = %g, Pr = %g, loss = %g", *p, total)
+            if callback is not None:
+                callback(p, total, losses, loss_scalings)
+            return total, gp.astype(np.float64) * p_init  # chain rule to the scaled parameters
+
+        minimize(fun, np.ones(5), jac=True, method="L-BFGS-B", bounds=[(0.0, 10.0)] * 5, options={"maxiter": int(maxiters)})
+        return dict(zip(MPP_KEYS, map(float, best["p"]))), record
+    finally:
+        model.close()
+        if own_ctx:
+            ctx.close()

@@ -192,6 +192,19 @@ int cpz_loss_grad(cpz_model* m, const float* x0, const float* bcs, const float* 
 int cpz_loss_grad_dev(cpz_model* m, const float* x0, const float* bcs, const float* diurnal_Q, const float* targets,
                       size_t ncol, const float* loss_w, float* loss_out_dev, float* grad_out_dev);
 
+/* ---- S3 for the NN-free base closure: gradient wrt the five mPP parameters ---------------------------------- */
+/* replaces loss_mpp / loss_gradient_mpp + Zygote gradient of optimise_modified_pacanowski_philander
+ * (wind_mixing/src/diffusivity_parameter_optimisation.jl:1-33,150-197): p = (nu0, nu_m, dRi, Ric, Pr) in the order `DE`
+ * destructures it (:2). The parameters live in the model description; set/get below. The loss is cpz_loss_grad's;
+ * grad_mpp_out[5] = d(total loss)/dp (unscaled parameters — the reference optimises p .* (1 ./ p_initial), so the host
+ * multiplies by p_initial); grad_theta_out[P] may be NULL (and must be for a model without nets). */
+int cpz_set_mpp_params(cpz_model* m, const float* p5);
+int cpz_get_mpp_params(const cpz_model* m, float* p5);
+int cpz_loss_grad_mpp(cpz_model* m, const float* x0, const float* bcs, const float* diurnal_Q, const float* targets,
+                      size_t ncol, const float* loss_w, float* loss_out, float* grad_theta_out, float* grad_mpp_out);
+int cpz_loss_grad_mpp_dev(cpz_model* m, const float* x0, const float* bcs, const float* diurnal_Q, const float* targets,
+                          size_t ncol, const float* loss_w, float* loss_out_dev, float* grad_theta_out_dev, float* grad_mpp_out_dev);
+
 /* ---- S3+S4: fused training iteration -------------------------------------------------------- */
 /* forward + discrete adjoint + (allreduce) + ADAM update of the model's theta; replaces one GalacticOptim iteration
  * (NDE_training.jl:340-372) with Flux.ADAM(lr,(beta1,beta2)), eps=1e-8 semantics. loss_out[7] is the loss at the

@@ -88,8 +88,10 @@ def diurnal_top(desc, Q, t, dtype):
     return (flux - _c32(desc.mu[5])) / _c32(desc.sigma[5])
 
 
-def rhs(desc, theta, x, bcs, t=0.0, Q=None):
-    """dx/dt for a batch of columns. x [ncol, S] torch tensor; theta torch 1-D (may require grad)."""
+def rhs(desc, theta, x, bcs, t=0.0, Q=None, p_mpp=None):
+    """dx/dt for a batch of columns. x [ncol, S] torch tensor; theta torch 1-D (may require grad).
+    p_mpp: optional tensor (nu0, nu_m, dRi, Ric, Pr) overriding the description's constants — the differentiable
+    parameter vector p of `DE` (diffusivity_parameter_optimisation.jl:2)."""
     N = desc.Nz
     dtype = x.dtype
     H, tau = _c32(desc.H), _c32(desc.tau)
@@ -154,8 +156,11 @@ def rhs(desc, theta, x, bcs, t=0.0, Q=None):
             Ri = _filter3(Ri)[:, 1:-1]
         else:
             Ri = BzC * (Gi[2] + eps) / ((sg[0] * (Gi[0] + eps)) ** 2 + (sg[1] * (Gi[1] + eps)) ** 2)
-        nu = _c32(desc.nu0) + _c32(desc.nu_m) * (1 - torch.tanh((Ri - _c32(desc.Ric)) / _c32(desc.dRi))) / 2
-        Pr = _c32(desc.Pr)
+        if p_mpp is not None:
+            nu0_, num_, dRi_, Ric_, Pr = p_mpp[0], p_mpp[1], p_mpp[2], p_mpp[3], p_mpp[4]
+        else:
+            nu0_, num_, dRi_, Ric_, Pr = _c32(desc.nu0), _c32(desc.nu_m), _c32(desc.dRi), _c32(desc.Ric), _c32(desc.Pr)
+        nu = nu0_ + num_ * (1 - torch.tanh((Ri - Ric_) / dRi_)) / 2
         if desc.variant == 1 and (desc.flags & FLAG_CA):
             test = Gi[0] if (desc.flags & FLAG_CA_LITERAL_U) else Gi[2]
             nu_T = torch.where(test > 0, nu / Pr, torch.full_like(nu, _c32(desc.kappa)))
@@ -186,7 +191,7 @@ def rhs(desc, theta, x, bcs, t=0.0, Q=None):
     return torch.cat([dudt, dvdt, dTdt], dim=1)
 
 
-def rk_step(desc, theta, x, bcs, t, h, Q=None):
+def rk_step(desc, theta, x, bcs, t, h, Q=None, mpp=None):
     a, b, c = TABLEAUS[desc.integrator]
     ks = []
     for i in range(len(b)):
@@ -194,14 +199,14 @@ def rk_step(desc, theta, x, bcs, t, h, Q=None):
         for j, aij in enumerate(a[i]):
             if aij != 0.0:
                 xi = xi + (h * aij) * ks[j]
-        ks.append(rhs(desc, theta, xi, bcs, t + c[i] * h, Q))
+        ks.append(rhs(desc, theta, xi, bcs, t + c[i] * h, Q, mpp))
     xn = x
     for i, bi in enumerate(b):
         xn = xn + (h * bi) * ks[i]
     return xn
 
 
-def solve(desc, theta, x0, bcs, Q=None):
+def solve(desc, theta, x0, bcs, Q=None, mpp=None):
     """Fixed-step solve; returns traj [ncol, n_saved, S]. Frame 0 is the initial condition (save_stride > 0)."""
     x = x0
     frames = [x0] if desc.save_stride > 0 else []
@@ -209,7 +214,7 @@ def solve(desc, theta, x0, bcs, Q=None):
     for n in range(desc.n_steps):
         t_n = _c32(desc.t0) + n * _c32(desc.dt)
         for s in range(desc.n_substeps):
-            x = rk_step(desc, theta, x, bcs, t_n + s * h, h, Q)
+            x = rk_step(desc, theta, x, bcs, t_n + s * h, h, Q, mpp)
         if desc.save_stride > 0 and (n + 1) % desc.save_stride == 0:
             frames.append(x)
     if desc.save_stride <= 0:
@@ -237,8 +242,8 @@ def loss_components(desc, traj, targets):
     return out
 
 
-def loss_total(desc, theta, x0, bcs, Q, targets, w):
-    traj = solve(desc, theta, x0, bcs, Q)
+def loss_total(desc, theta, x0, bcs, Q, targets, w, mpp=None):
+    traj = solve(desc, theta, x0, bcs, Q, mpp)
     comps = loss_components(desc, traj, targets)
     scaled = [float(w[i]) * comps[i] for i in range(6)]
     return sum(scaled), scaled
@@ -250,6 +255,16 @@ def loss_grad(desc, theta, x0, bcs, Q, targets, w):
     total, scaled = loss_total(desc, th, x0, bcs, Q, targets, w)
     (g,) = torch.autograd.grad(total, th)
     return total.detach(), [s.detach() for s in scaled], g
+
+
+def loss_grad_mpp(desc, theta, x0, bcs, Q, targets, w):
+    """(total, grad wrt p = (nu0, nu_m, dRi, Ric, Pr)) — loss_mpp / loss_gradient_mpp of
+    diffusivity_parameter_optimisation.jl:150-197 in UNSCALED parameters, exact discrete adjoint via autograd."""
+    p = torch.tensor([_c32(desc.nu0), _c32(desc.nu_m), _c32(desc.dRi), _c32(desc.Ric), _c32(desc.Pr)], dtype=x0.dtype,
+                     requires_grad=True)
+    total, scaled = loss_total(desc, theta, x0, bcs, Q, targets, w, mpp=p)
+    (g,) = torch.autograd.grad(total, p)
+    return total.detach(), g
 
 
 def adam_step(theta, g, m, v, beta_pow, lr, b1=0.9, b2=0.999, eps=1e-8):
