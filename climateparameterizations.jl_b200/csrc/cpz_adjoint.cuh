@@ -37,8 +37,12 @@ struct AdjArgs {
 constexpr int LP = 16;  // floats per CTA in lpart
 
 struct AdjSmem {
-  int w, xs, xbar, xin, xb, arena, zarena, bcf, qs, red, model, total_floats;
+  int w, xs, xbar, xin, xb, arena, zarena, imp, bcf, qs, red, model, total_floats;
 };
+// Scratch of the implicit-diffusion step and its VJP (2 S CT floats: r and the Thomas forward-sweep coefficients): the layer-
+// output rows of the activation arena are dead at the step boundaries where these run, so they are used when there are
+// enough of them; models with no or very small nets get a dedicated region.
+__host__ __device__ inline bool adjoint_imp_in_arena(const ModelD& M) { return M.flux_off >= 2 * M.S; }
 __host__ __device__ inline AdjSmem adjoint_smem_layout(const ModelD& M, int CT) {
   AdjSmem L;
   int o = 0;
@@ -49,6 +53,7 @@ __host__ __device__ inline AdjSmem adjoint_smem_layout(const ModelD& M, int CT) 
   L.xb = o; o += M.S * CT;         // kbar_i, then Xbar_i; target frame at step boundaries
   L.arena = o; o += M.arena_floats * CT;
   L.zarena = o; o += M.flux_off * CT;  // pre-activations / deltas of every layer output row
+  L.imp = o; o += ((M.flags & F_IMPLICIT) && !adjoint_imp_in_arena(M)) ? 2 * M.S * CT : 0;
   L.bcf = o; o += M.nbc * CT;
   L.qs = o; o += CT;
   L.red = o; o += 64;
@@ -65,7 +70,7 @@ inline size_t adjoint_other_smem(int S, int nbc, int CT) {
 // (zarena at M.nn_off) and the cotangent of the face gradients Gbar_q[face][c] into `gbar` (arena flux rows).
 template <int CT, int NT>
 __device__ __noinline__ void faces_vjp(const ModelD& M, const float* __restrict__ X, const float* __restrict__ kbar,
-                                          float* __restrict__ zarena, float* __restrict__ gbar, float* __restrict__ pg /*[5] or null*/) {
+                                          float* __restrict__ zarena, float* __restrict__ gbar, double* __restrict__ pg /*[5] or null*/) {
   const int N = M.Nz, nfaces = N + 1;
   const bool has_nn = M.n_nets > 0;
   if (M.variant == RHS_FC) {
@@ -505,6 +510,113 @@ __device__ __noinline__ void stage_input(const TableauD& tab, int i, float h, co
   }
 }
 
+// VJP of y = L(D(x)) \ x (implicit_diffusion_tile): on entry `xbar` holds ybar, on exit xbar_x.
+//   lambda = L^{-1} ybar (L is symmetric);  rbar_k = -(lambda_k - lambda_{k-1}) (y_k - y_{k-1});  Dbar = h A Nz^2 rbar;
+//   xbar = lambda + (dD/dx)^T Dbar through the same Richardson-number chain as faces_vjp.
+// x: the incoming state (diffusivities are evaluated there), y: the outgoing state, scr: 2 S CT floats, gbar: 3 (Nz+1) CT floats.
+template <int CT, int NT>
+__device__ __noinline__ void implicit_vjp_tile(const ModelD& M, const float* __restrict__ x, const float* __restrict__ y,
+                                                 float* __restrict__ xbar, float* __restrict__ scr, float* __restrict__ gbar,
+                                                 float h, double* __restrict__ pg) {
+  const int N = M.Nz, nf = M.nf, nfaces = N + 1;
+  float* r = scr;
+  float* cp = scr + nf * N * CT;
+  for (int i = threadIdx.x; i < nf * N * CT; i += NT) {
+    const int c = i % CT, k = (i / CT) % N, q = i / (CT * N);
+    r[i] = k == 0 ? 0.f : h * M.rc.A[nf == 1 ? 2 : q] * M.rc.Nf * M.rc.Nf * face_diffusivity(M, x, q, k, c, CT);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < nf * CT; t += NT) {  // lambda = L \ ybar, in place
+    const int c = t % CT, q = t / CT;
+    float* xq = xbar + q * N * CT + c;
+    const float* rq = r + q * N * CT + c;
+    float* cq = cp + q * N * CT + c;
+    float cprev = 0.f, dprev = 0.f;
+    for (int k = 0; k < N; ++k) {
+      const float rlo = rq[k * CT], rhi = k + 1 < N ? rq[(k + 1) * CT] : 0.f;
+      const float inv = 1.f / (1.f + rlo + rhi + rlo * cprev);
+      cprev = -rhi * inv;
+      dprev = (xq[k * CT] + rlo * dprev) * inv;
+      cq[k * CT] = cprev;
+      xq[k * CT] = dprev;
+    }
+    float v = xq[(N - 1) * CT];
+    for (int k = N - 2; k >= 0; --k) {
+      v = xq[k * CT] - cq[k * CT] * v;
+      xq[k * CT] = v;
+    }
+  }
+  __syncthreads();
+  // cotangents of the face gradients
+  for (int i = threadIdx.x; i < nfaces * CT; i += NT) {
+    const int f = i / CT, c = i - f * CT;
+    float gb[3] = {0.f, 0.f, 0.f};
+    if (f > 0 && f < N) {
+      float Db[3];  // cotangent of D_q at this face
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        Db[q] = 0.f;
+        if (q < nf) {
+          const int e = (q * N + f) * CT + c;
+          const float rb = -(xbar[e] - xbar[e - CT]) * (y[e] - y[e - CT]);
+          Db[q] = h * M.rc.A[nf == 1 ? 2 : q] * M.rc.Nf * M.rc.Nf * rb;
+        }
+      }
+      if (M.variant == RHS_FC) {
+        if (M.flags & F_MPP) {
+          const float G = M.rc.Nf * (x[f * CT + c] - x[(f - 1) * CT + c]);
+          float dcnu;
+          fc_mpp_cnu(M, G, &dcnu);
+          gb[0] = Db[0] * dcnu;  // the convective-adjustment part K [G < 0] is piecewise constant
+        }
+      } else {
+        const bool mpp = (M.flags & F_MPP) || M.variant == RHS_INFER;
+        if (mpp) {
+          const float eps = M.variant == RHS_TRAIN ? M.rc.eps : 0.f;
+          const float Gu = M.rc.Nf * (x[f * CT + c] - x[(f - 1) * CT + c]);
+          const float Gv = M.rc.Nf * (x[(N + f) * CT + c] - x[(N + f - 1) * CT + c]);
+          const float GT = M.rc.Nf * (x[(2 * N + f) * CT + c] - x[(2 * N + f - 1) * CT + c]);
+          const float su = M.rc.sig_u * (Gu + eps), sv = M.rc.sig_v * (Gv + eps);
+          const float iS2 = __fdividef(1.f, su * su + sv * sv);
+          const float Ri = M.rc.BzC * (GT + eps) * iS2;
+          const float y2 = 2.f * (Ri - M.rc.Ric) * M.rc.inv_dRi;
+          const float s = __fdividef(1.f, 1.f + __expf(y2));
+          const float nu = M.rc.nu0 + M.rc.nu_m * s;
+          float dnuT = M.rc.inv_Pr;
+          if (M.variant == RHS_INFER && (M.flags & F_CA)) {
+            const float test = (M.flags & F_CA_LITERAL_U) ? Gu : GT;
+            if (!(test > 0.f)) dnuT = 0.f;
+          }
+          const float nub = M.rc.c[0] * Db[0] + M.rc.c[1] * Db[1] + M.rc.c[2] * dnuT * Db[2];
+          const float ss = s * (1.f - s);
+          if (pg != nullptr) {
+            pg[0] += nub;
+            pg[1] += nub * s;
+            pg[2] += nub * M.rc.nu_m * ss * y2 * M.rc.inv_dRi;
+            pg[3] += nub * M.rc.nu_m * ss * 2.f * M.rc.inv_dRi;
+            if (dnuT != 0.f) pg[4] -= Db[2] * M.rc.c[2] * nu * M.rc.inv_Pr * M.rc.inv_Pr;
+          }
+          const float Rib = nub * (-2.f * M.rc.inv_dRi * M.rc.nu_m * ss);
+          gb[2] = Rib * M.rc.BzC * iS2;
+          const float t = -Rib * Ri * iS2 * 2.f;
+          gb[0] = t * M.rc.sig_u * su;
+          gb[1] = t * M.rc.sig_v * sv;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      if (q < nf) gbar[(q * nfaces + f) * CT + c] = gb[q];
+  }
+  __syncthreads();
+  for (int it = threadIdx.x; it < nf * N * CT; it += NT) {
+    const int c = it % CT, k = (it / CT) % N, q = it / (CT * N);
+    const float g0 = (k >= 1) ? gbar[(q * nfaces + k) * CT + c] : 0.f;
+    const float g1 = (k + 1 <= N - 1) ? gbar[(q * nfaces + k + 1) * CT + c] : 0.f;
+    xbar[it] += M.rc.Nf * (g0 - g1);
+  }
+}
+
 template <int CT, int NT, bool WS, int NF>
 __device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, const TableauD& tab, const TimeD& tm,
                                              const AdjArgs& a, float* smem) {
@@ -526,9 +638,11 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, 
   float* segx = a.segx + (size_t)blockIdx.x * a.seg_len * SC;
   float* gpart = a.gpart + (size_t)blockIdx.x * M.slab;
   float* gflux = arena + M.flux_off * CT;
+  const bool implicit = (M.flags & F_IMPLICIT) != 0;
+  float* imp = adjoint_imp_in_arena(M) ? arena : smem + L.imp;  // scratch of the implicit-diffusion step (2 S CT floats)
   uint32_t parity = 0;
   float lsum[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  float pgs[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  double pgs[5] = {0., 0., 0., 0., 0.};  // FP64 accumulators: sums of ~1e8 small terms of both signs (rare path, 5 adds per face)
   const int Lmax = M.n_gemm > 0 ? last_layer_of<CT, NT>(M) : -1;
   PhaseCache pc;
   build_phase_cache<WS, CT, NT>(M, pc);
@@ -593,6 +707,7 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, 
       for (int r = 0; r + 1 < R; ++r) {
         const float tb = tm.t0 + (float)(n0 + r / tm.n_substeps) * tm.dt + (float)(r % tm.n_substeps) * h;
         const KSrc kfw = kst != nullptr ? KSrc{kst + (size_t)r * ns * SL, LT, SL} : own;  // stored k_i, or recomputed below
+        if (implicit) { implicit_diffusion_tile<CT, NT>(M, xs, imp, h); __syncthreads(); }  // xs: x_r -> y_r
         for (int i = 0; i < ns && kst == nullptr; ++i) {
           const float* in = xs;
           if (i > 0) { stage_input<CT, NT>(tab, i, h, xs, own, SC, xin); __syncthreads(); in = xin; }
@@ -622,7 +737,8 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, 
       }
       // ---- reverse sweep over the segment
       for (int r = R - 1; r >= 0; --r) {
-        if (R > 1) { load_state(xs, segx + (size_t)r * SC, CT); __syncthreads(); }
+        if (R > 1 || implicit) { load_state(xs, segx + (size_t)r * SC, CT); __syncthreads(); }
+        if (implicit) { implicit_diffusion_tile<CT, NT>(M, xs, imp, h); __syncthreads(); }  // the explicit stages start from y_r
         const int nstep = n0 + r / tm.n_substeps, sub = r % tm.n_substeps;
         const float tb = tm.t0 + (float)nstep * tm.dt + (float)sub * h;
         // (a) forward stages 0..ns-2 -> k_i into the slots
@@ -701,6 +817,17 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, 
           reinterpret_cast<float4*>(xbar)[e4] = acc;
         }
         __syncthreads();
+        if (implicit) {
+          // xbar is the cotangent of y_r; pull it back through y_r = L(D(x_r)) \ x_r. x_r is re-read from the segment scratch.
+          load_state(xin, segx + (size_t)r * SC, CT);
+          __syncthreads();
+          implicit_vjp_tile<CT, NT>(M, xin, xs, xbar, imp, gflux, h, a.want_pgrad ? pgs : nullptr);
+          __syncthreads();
+          if (sub == 0 && frame_of(nstep) >= 0) {  // the saved frame is x_r, not y_r
+            load_state(xs, segx + (size_t)r * SC, CT);
+            __syncthreads();
+          }
+        }
         if (sub == 0) {
           const int fr = frame_of(nstep);
           if (fr >= 0) {
@@ -715,8 +842,9 @@ __device__ __forceinline__ void adjoint_body(const ModelD& M, const ModelD& Mp, 
   }
   // block reduction of the six loss sums and the five mPP-parameter gradient sums
   for (int q = 0; q < 11; ++q) {
-    float v = q < 6 ? lsum[q] : pgs[q - 6];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    double vd = q < 6 ? (double)lsum[q] : pgs[q - 6];
+    for (int o = 16; o > 0; o >>= 1) vd += __shfl_xor_sync(0xffffffffu, vd, o);
+    float v = (float)vd;
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -65,6 +65,7 @@ static int bind_device(const cpz_ctx* c) {
 
 static size_t solve_other_smem(const cpz_model_desc& d, int CT, int n_stages) {
   const int S = d.n_fields * d.Nz, nbc = d.n_fields == 3 ? 6 : 2;
+  if ((d.flags & CPZ_FLAG_IMPLICIT_DIFFUSION) && n_stages < 2) n_stages = 2;  // scratch of the implicit-diffusion step
   return ((size_t)3 * CT * (S + 4) + (size_t)n_stages * S * CT + (size_t)nbc * CT + CT + 4) * sizeof(float) + ((sizeof(ModelD) + 15) / 16) * 16;
 }
 
@@ -83,6 +84,7 @@ static int rebuild_plans(cpz_model* m) {
   bo.smem_budget = m->ctx->smem_optin;
   bo.other_smem_bytes = adjoint_other_smem(m->desc.n_fields * m->desc.Nz, m->desc.n_fields == 3 ? 6 : 2, m->CT);
   m->has_bwd = build_plan(m->desc, bo, m->bwd, m->bwd_err);
+  m->implicit_adjoint_ok = true;  // adjoint_kernel carries implicit_vjp_tile
   for (int i = 0; i < cpz_model::N_SMALL; ++i) {
     const int cs = cpz_model::small_ct(i);
     PlanOptions fs = fo, bs = bo;
@@ -387,6 +389,36 @@ int cpz_rhs(cpz_model* m, const float* x, const float* bcs, const float* diurnal
   if ((rc = ensure(m->b_traj, ncol * S))) return rc;
   if ((rc = cpz_rhs_dev(m, m->b_x0.p, m->b_bcs.p, diurnal_Q ? m->b_q.p : nullptr, t, m->b_traj.p, ncol))) return rc;
   CPZ_CUDA(cudaMemcpyAsync(dxdt, m->b_traj.p, ncol * S * sizeof(float), cudaMemcpyDeviceToHost, m->ctx->stream));
+  CPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  return CPZ_OK;
+}
+
+// ---- predict_flux ---------------------------------------------------------------------------------------------------
+int cpz_predict_flux_dev(cpz_model* m, const float* x, const float* bcs, const float* diurnal_Q, float t, float* flux, size_t ncol) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (ncol == 0) return CPZ_OK;
+  if (!x || !bcs || !flux) return fail(CPZ_ERR_INVALID, "null array");
+  if ((m->desc.flags & CPZ_FLAG_DIURNAL) && !diurnal_Q) return fail(CPZ_ERR_INVALID, "diurnal model needs diurnal_Q");
+  if (ncol > (size_t)INT32_MAX / 512) return fail(CPZ_ERR_INVALID, "ncol too large");
+  if ((rc = bind_device(m->ctx))) return rc;
+  SolveArgs a{};
+  a.theta = m->d_theta; a.x0 = x; a.bcs = bcs; a.Q = diurnal_Q; a.dxdt = flux; a.ncol = (int)ncol;
+  a.rhs_only = 2; a.t_rhs = t; a.n_saved = 1; a.n_ckpt = 0;
+  return launch_flux(m, a);
+}
+
+int cpz_predict_flux(cpz_model* m, const float* x, const float* bcs, const float* diurnal_Q, float t, float* flux, size_t ncol) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (ncol == 0) return CPZ_OK;
+  if (!x || !bcs || !flux) return fail(CPZ_ERR_INVALID, "null array");
+  if ((rc = bind_device(m->ctx))) return rc;
+  if ((rc = upload_inputs(m, x, bcs, diurnal_Q, ncol))) return rc;
+  const size_t rows = (size_t)m->fwd.M.nf * (m->fwd.M.Nz + 1);
+  if ((rc = ensure(m->b_traj, ncol * rows))) return rc;
+  if ((rc = cpz_predict_flux_dev(m, m->b_x0.p, m->b_bcs.p, diurnal_Q ? m->b_q.p : nullptr, t, m->b_traj.p, ncol))) return rc;
+  CPZ_CUDA(cudaMemcpyAsync(flux, m->b_traj.p, ncol * rows * sizeof(float), cudaMemcpyDeviceToHost, m->ctx->stream));
   CPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));
   return CPZ_OK;
 }

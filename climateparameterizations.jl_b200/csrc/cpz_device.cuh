@@ -18,7 +18,7 @@ namespace cpz {
 enum { RHS_TRAIN = 0, RHS_INFER = 1, RHS_FC = 2 };
 enum {
   F_MPP = 1, F_CA = 2, F_ZERO_WEIGHTS = 4, F_SMOOTH_NN = 8, F_SMOOTH_RI = 16, F_DIURNAL = 32, F_CA_LITERAL_U = 64,
-  F_DIURNAL_UNSHIFTED = 128
+  F_DIURNAL_UNSHIFTED = 128, F_IMPLICIT = 256
 };
 enum { ACT_ID = 0, ACT_RELU = 1, ACT_MISH = 2, ACT_SWISH = 3, ACT_LEAKY = 4, ACT_TANH = 5 };
 
@@ -210,7 +210,8 @@ __device__ __noinline__ void faces_phase(const ModelD& M, const float* __restric
   const bool has_nn = M.n_nets > 0;
   if (M.variant == RHS_FC) {
     const float* nn = has_nn ? arena + M.nn_off[0] * CT : nullptr;
-    const bool ca = M.flags & F_CA, mpp1 = M.flags & F_MPP;
+    const bool expl = !(M.flags & F_IMPLICIT);  // implicit diffusion: the RHS carries the NN and boundary fluxes only
+    const bool ca = (M.flags & F_CA) && expl, mpp1 = (M.flags & F_MPP) && expl;
     for (int i = threadIdx.x; i < nfaces * CT; i += NT) {
       const int k = i / CT, c = i - k * CT;
       float e;
@@ -226,7 +227,8 @@ __device__ __noinline__ void faces_phase(const ModelD& M, const float* __restric
     }
     return;
   }
-  const bool mpp = (M.flags & F_MPP) || M.variant == RHS_INFER;
+  const bool expl = !(M.flags & F_IMPLICIT);
+  const bool mpp = ((M.flags & F_MPP) || M.variant == RHS_INFER) && expl;
   const bool smooth_nn = M.variant == RHS_TRAIN && (M.flags & F_SMOOTH_NN);
   const bool smooth_ri = M.variant == RHS_TRAIN && (M.flags & F_SMOOTH_RI);
   const float eps = M.variant == RHS_TRAIN ? M.rc.eps : 0.f;
@@ -269,7 +271,7 @@ __device__ __noinline__ void faces_phase(const ModelD& M, const float* __restric
         e[0] = nn[0] - M.rc.c[0] * nu * Gu;
         e[1] = nn[1] - M.rc.c[1] * nu * Gv;
         e[2] = nn[2] - M.rc.c[2] * nuT * GT;
-      } else if (M.flags & F_CA) {
+      } else if ((M.flags & F_CA) && expl) {
         e[0] = nn[0]; e[1] = nn[1];
         e[2] = nn[2] - M.rc.c[2] * M.rc.kappa * fminf(0.f, GT);
       } else {
@@ -304,8 +306,9 @@ __device__ __forceinline__ void stencil_fused(const ModelD& M, const float* __re
                                            const float* __restrict__ bcf, Sink sink) {
   const int N = M.Nz;
   const bool has_nn = M.n_nets > 0;
-  const bool mpp = NF == 3 && ((M.flags & F_MPP) || M.variant == RHS_INFER);
-  const bool ca = (M.flags & F_CA) != 0;
+  const bool expl = !(M.flags & F_IMPLICIT);  // implicit diffusion: the RHS carries the NN and boundary fluxes only
+  const bool mpp = NF == 3 && ((M.flags & F_MPP) || M.variant == RHS_INFER) && expl;
+  const bool ca = (M.flags & F_CA) != 0 && expl;
   const float eps = M.variant == RHS_TRAIN ? M.rc.eps : 0.f;
   const float Nf = M.rc.Nf;
   const int n_items = (N / 4) * CT;
@@ -339,7 +342,7 @@ __device__ __forceinline__ void stencil_fused(const ModelD& M, const float* __re
       for (int q = 0; q < NF; ++q) G[q] = Nf * (xl[q][fi + 1] - xl[q][fi]);
       if constexpr (NF == 1) {
         float e = nn[0];
-        if (M.flags & F_MPP) e -= fc_mpp_cnu(M, G[0]) * G[0];
+        if ((M.flags & F_MPP) && expl) e -= fc_mpp_cnu(M, G[0]) * G[0];
         if (ca) e -= fminf(0.f, M.rc.K_ca * G[0]);
         E[0][fi] = e;
       } else {
@@ -374,6 +377,74 @@ __device__ __forceinline__ void stencil_fused(const ModelD& M, const float* __re
       }
     }
     sink(k0, c, dx);
+  }
+}
+
+// ---- implicit vertical diffusion (CPZ_FLAG_IMPLICIT_DIFFUSION) ---------------------------------------------------------------
+// Diffusivity D_q at interior face k of column c such that the diffusive flux is -D_q G_q (the terms stencil_fused leaves out
+// when the flag is set): u, v: c_q nu; T: c_T nu_T with the variant's convective-adjustment rule; T-only: [mPP] c_T nu/Pr +
+// [CA] K [G < 0].
+__device__ __forceinline__ float face_diffusivity(const ModelD& M, const float* __restrict__ X, int q, int k, int c, int CT_) {
+  const int N = M.Nz;
+  const float Nf = M.rc.Nf;
+  if (M.variant == RHS_FC) {
+    const float G = Nf * (X[k * CT_ + c] - X[(k - 1) * CT_ + c]);
+    float D = 0.f;
+    if (M.flags & F_MPP) D += fc_mpp_cnu(M, G);
+    if ((M.flags & F_CA) && M.rc.K_ca * G < 0.f) D += M.rc.K_ca;
+    return D;
+  }
+  const bool mpp = (M.flags & F_MPP) || M.variant == RHS_INFER;
+  const float Gu = Nf * (X[k * CT_ + c] - X[(k - 1) * CT_ + c]);
+  const float GT = Nf * (X[(2 * N + k) * CT_ + c] - X[(2 * N + k - 1) * CT_ + c]);
+  if (!mpp) return (q == 2 && (M.flags & F_CA) && GT < 0.f) ? M.rc.c[2] * M.rc.kappa : 0.f;
+  const float eps = M.variant == RHS_TRAIN ? M.rc.eps : 0.f;
+  const float nu = nu_of_ri(M, ri_face(M, X, k, c, CT_, eps));
+  if (q < 2) return M.rc.c[q] * nu;
+  float nuT = nu * M.rc.inv_Pr;
+  if (M.variant == RHS_INFER && (M.flags & F_CA)) {
+    const float test = (M.flags & F_CA_LITERAL_U) ? Gu : GT;
+    nuT = test > 0.f ? nuT : M.rc.kappa;
+  }
+  return M.rc.c[2] * nuT;
+}
+
+// x_q <- L_q \ x_q for every field of the tile, L_q = tridiag(-r_k, 1 + r_k + r_{k+1}, -r_{k+1}), r_k = h A_q Nz^2 D_q,k on the
+// interior faces (0 on the boundary faces), diffusivities of the incoming state (NDE_oceananigans.jl:61-101,
+// oceananigans_nn.jl:13-40). One thread per (field, column) runs the Thomas recurrence over the levels; `scr` holds 2 S CT
+// floats (r, then the forward-sweep coefficients) — the dead Runge–Kutta stage slots at the start of a step.
+// Smoothed-Ri models are not supported (refused by the host). Block barriers inside; the caller syncs afterwards.
+template <int CT, int NT>
+__device__ __noinline__ void implicit_diffusion_tile(const ModelD& M, float* __restrict__ x, float* __restrict__ scr, float h) {
+  const int N = M.Nz, nf = M.nf;
+  float* r = scr;                 // [nf][N][CT]: r at face k (below level k), k = 1..N-1; index 0 unused (= 0)
+  float* cp = scr + nf * N * CT;  // [nf][N][CT]
+  for (int i = threadIdx.x; i < nf * N * CT; i += NT) {
+    const int c = i % CT, k = (i / CT) % N, q = i / (CT * N);
+    const float A = M.rc.A[nf == 1 ? 2 : q];
+    r[i] = k == 0 ? 0.f : h * A * M.rc.Nf * M.rc.Nf * face_diffusivity(M, x, q, k, c, CT);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < nf * CT; t += NT) {
+    const int c = t % CT, q = t / CT;
+    float* xq = x + q * N * CT + c;
+    const float* rq = r + q * N * CT + c;
+    float* cq = cp + q * N * CT + c;
+    float cprev = 0.f, dprev = 0.f;
+    for (int k = 0; k < N; ++k) {
+      const float rlo = rq[k * CT], rhi = k + 1 < N ? rq[(k + 1) * CT] : 0.f;
+      const float den = 1.f + rlo + rhi + rlo * cprev;  // diag - lower * cp_{k-1}, lower = -rlo
+      const float inv = 1.f / den;
+      cprev = -rhi * inv;
+      dprev = (xq[k * CT] + rlo * dprev) * inv;
+      cq[k * CT] = cprev;
+      xq[k * CT] = dprev;
+    }
+    float y = xq[(N - 1) * CT];
+    for (int k = N - 2; k >= 0; --k) {
+      y = xq[k * CT] - cq[k * CT] * y;
+      xq[k * CT] = y;
+    }
   }
 }
 

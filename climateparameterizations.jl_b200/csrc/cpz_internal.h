@@ -38,6 +38,7 @@ struct cpz_model {
   cpz::Plan fwd;  // forward plan (aliasing arena, free TO)
   cpz::Plan bwd;  // adjoint plan (all activations kept)
   bool has_bwd = false;
+  bool implicit_adjoint_ok = false;  // set once the adjoint kernels carry the VJP of the implicit-diffusion step
   // the same two plans for CT_SMALL-column tiles: small batches (BASELINE config 1: one column; the reference's 9-18
   // simulations) and shards too small to give every SM a 32-column tile run on these
   static constexpr int N_SMALL = 3;

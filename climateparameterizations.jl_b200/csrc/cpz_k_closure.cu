@@ -110,6 +110,7 @@ static int launch_fc_tc_t(cpz_model* m, const ClosureTcD& C, const SolveArgs& a)
 int launch_solve_fc_tc(cpz_model* m, const SolveArgs& a) {
   ClosureTcD C;
   if (m->desc.variant != CPZ_RHS_FREE_CONVECTION || !closure_tc_plan(m, C)) return 1;
+  if (m->desc.flags & CPZ_FLAG_IMPLICIT_DIFFUSION) return 1;  // the implicit-diffusion step lives in the FP32 tile kernels
   int rc = ensure_image(m, C, a.theta);
   if (rc) return rc;
   const size_t n_tiles = 2 * (((size_t)(a.ncol + CTC_TILE - 1) / CTC_TILE + 1) / 2);  // tile pairs

@@ -54,6 +54,27 @@ int train_tile(const cpz_model* m, size_t ncol) {
   return m->CT;
 }
 
+template <bool WS>
+static int launch_flux_t(cpz_model* m, const SolveArgs& a) {
+  constexpr int CT = 32, NT = 256;
+  const ModelD& M = m->bwd.M;  // keeps the 3 (Nz+1) face-flux scratch rows
+  TableauD tab1 = m->tab;
+  tab1.n_stages = 1;  // a single evaluation needs no Runge–Kutta stage slots (the adjoint plan's arena is the larger one)
+  const SolveSmem L = solve_smem_layout(M, CT, tab1.n_stages);
+  const size_t smem = (size_t)L.total_floats * sizeof(float);
+  if (smem > m->ctx->smem_optin) return fail(CPZ_ERR_INVALID, "flux kernel needs %zu B shared memory, device allows %zu", smem, m->ctx->smem_optin);
+  auto kern = solve_kernel<CT, NT, WS>;
+  CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(a.ncol + CT - 1) / CT, NT, smem, m->ctx->stream>>>(M, tab1, m->tm, a);
+  CPZ_CUDA(cudaGetLastError());
+  m->ctx->launches++;
+  return CPZ_OK;
+}
+int launch_flux(cpz_model* m, const SolveArgs& a) {
+  if (!m->has_bwd) return fail(CPZ_ERR_INVALID, "predict_flux needs the adjoint plan: %s", m->bwd_err.c_str());
+  return m->bwd.M.w_in_smem ? launch_flux_t<true>(m, a) : launch_flux_t<false>(m, a);
+}
+
 int launch_solve(cpz_model* m, const SolveArgs& a) {
   static const bool prof = getenv("CPZ_PROF") != nullptr;
   if (!prof) {

@@ -89,7 +89,7 @@ std::string tc_describe(const cpz_model* m) {
   if (m->desc.n_nets == 0 && m->desc.n_fields == 3 && m->desc.Nz == 32 && m->desc.variant != CPZ_RHS_FREE_CONVECTION &&
       !(m->desc.flags & (CPZ_FLAG_SMOOTH_NN | CPZ_FLAG_SMOOTH_RI)))
     return "forward kernel: nn-free warp-per-columns (2 columns per warp, no block barriers)\n";
-  if (m->desc.variant == CPZ_RHS_FREE_CONVECTION && closure_uses_tc(m))
+  if (m->desc.variant == CPZ_RHS_FREE_CONVECTION && closure_uses_tc(m) && !(m->desc.flags & CPZ_FLAG_IMPLICIT_DIFFUSION))
     return "forward kernel: tcgen05 3xTF32, columns on the M side (128-column tiles, activations in TMEM, weights in shared memory)\n";
   if (!tc_plan(m, T, why)) return "forward kernel: fp32-simt (tcgen05 path not eligible: " + why + ")\n";
   const TcSmem L = tc_smem_layout(T, m->tab.n_stages);

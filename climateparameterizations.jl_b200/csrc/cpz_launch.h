@@ -7,6 +7,7 @@
 
 namespace cpz {
 int launch_solve(cpz_model* m, const SolveArgs& a);
+int launch_flux(cpz_model* m, const SolveArgs& a);  // rhs_only == 2 on the FP32 kernel with the adjoint plan's face-flux rows
 int launch_solve_tc(cpz_model* m, const SolveArgs& a);
 bool solve_tc_eligible(cpz_model* m);
 int launch_solve_nnfree(cpz_model* m, const SolveArgs& a);

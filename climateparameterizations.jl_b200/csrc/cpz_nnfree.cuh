@@ -45,6 +45,39 @@ __global__ void __launch_bounds__(NF_WARPS * 32) solve_nnfree_kernel(const __gri
     Qd[c] = (diurnal && a.Q != nullptr) ? __ldg(a.Q + col) : 0.f;
   }
   const float Au = M.rc.A[0] * M.rc.Nf, Av = M.rc.A[1] * M.rc.Nf, AT = M.rc.A[2] * M.rc.Nf;
+  // CPZ_FLAG_IMPLICIT_DIFFUSION: the stages see no diffusive flux; the diffusivities act in a backward-Euler solve per sub-step
+  const bool implicit = (M.flags & F_IMPLICIT) != 0;
+  const int rhs_mode = implicit ? (int)SIDE_NONE : side_mode;
+  auto diffusivity = [&](int mode, float du, float dv, float dT, float& Du, float& Dv, float& DT) {
+    switch (mode) {
+      case SIDE_MPP: side_column<SIDE_MPP>(SC, du, dv, dT, Du, Dv, DT); break;
+      case SIDE_MPP_CA_T: side_column<SIDE_MPP_CA_T>(SC, du, dv, dT, Du, Dv, DT); break;
+      case SIDE_MPP_CA_U: side_column<SIDE_MPP_CA_U>(SC, du, dv, dT, Du, Dv, DT); break;
+      case SIDE_CA_ONLY: side_column<SIDE_CA_ONLY>(SC, du, dv, dT, Du, Dv, DT); break;
+      default: side_column<SIDE_NONE>(SC, du, dv, dT, Du, Dv, DT); break;
+    }
+  };
+  // x <- L(nu(x)) \ x per field: lane <-> level, parallel cyclic reduction across the warp (see pcr32)
+  auto implicit_step = [&](float hsub) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float u = x[0][c], v = x[1][c], T = x[2][c];
+      const float du = __shfl_down_sync(0xffffffffu, u, 1) - u;
+      const float dv = __shfl_down_sync(0xffffffffu, v, 1) - v;
+      const float dT = __shfl_down_sync(0xffffffffu, T, 1) - T;
+      float D[3];
+      diffusivity(side_mode, du, dv, dT, D[0], D[1], D[2]);
+      const float Aq[3] = {Au, Av, AT};
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float rup = lane == 31 ? 0.f : hsub * Aq[q] * D[q];
+        float rdn = __shfl_up_sync(0xffffffffu, rup, 1);
+        if (lane == 0) rdn = 0.f;
+        x[q][c] = pcr32(-rdn, 1.f + rdn + rup, -rup, x[q][c]);
+        X[q][c] = x[q][c];
+      }
+    }
+  };
 
   auto rhs = [&](float t_stage, float (&dx)[3][NC]) {
 #pragma unroll
@@ -54,13 +87,7 @@ __global__ void __launch_bounds__(NF_WARPS * 32) solve_nnfree_kernel(const __gri
       const float dv = __shfl_down_sync(0xffffffffu, v, 1) - v;
       const float dT = __shfl_down_sync(0xffffffffu, T, 1) - T;
       float Du, Dv, DT;
-      switch (side_mode) {
-        case SIDE_MPP: side_column<SIDE_MPP>(SC, du, dv, dT, Du, Dv, DT); break;
-        case SIDE_MPP_CA_T: side_column<SIDE_MPP_CA_T>(SC, du, dv, dT, Du, Dv, DT); break;
-        case SIDE_MPP_CA_U: side_column<SIDE_MPP_CA_U>(SC, du, dv, dT, Du, Dv, DT); break;
-        case SIDE_CA_ONLY: side_column<SIDE_CA_ONLY>(SC, du, dv, dT, Du, Dv, DT); break;
-        default: side_column<SIDE_NONE>(SC, du, dv, dT, Du, Dv, DT); break;
-      }
+      diffusivity(rhs_mode, du, dv, dT, Du, Dv, DT);
       float bT = bnd[2][c];
       if (diurnal && lane == 31) bT = diurnal_top_eff(M, Qd[c], t_stage);
       // flux at face lane+1 (top boundary flux for lane 31), flux at face lane from the lane below (bottom flux for lane 0)
@@ -109,6 +136,7 @@ __global__ void __launch_bounds__(NF_WARPS * 32) solve_nnfree_kernel(const __gri
   for (int n = 0; n < tm.n_steps; ++n) {
     for (int sub = 0; sub < tm.n_substeps; ++sub) {
       const float tb = tm.t0 + (float)(tm.step0 + n) * tm.dt + (float)sub * h;
+      if (implicit) implicit_step(h);
 #pragma unroll 1
       for (int i = 0; i < ns; ++i) {
         float dx[3][NC];

@@ -33,6 +33,10 @@ bool validate_desc(const cpz_model_desc& d, std::string& err) {
       return false;
     }
   }
+  if ((d.flags & CPZ_FLAG_IMPLICIT_DIFFUSION) && (d.flags & CPZ_FLAG_SMOOTH_RI)) {
+    err = "implicit diffusion is not available with smooth_Ri";
+    return false;
+  }
   const int S = d.n_fields * d.Nz;
   for (int n = 0; n < d.n_nets; ++n) {
     const cpz_net_desc& nd = d.nets[n];

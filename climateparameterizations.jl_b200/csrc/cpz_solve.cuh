@@ -12,7 +12,7 @@ struct SolveArgs {
   const float* Q;      // [ncol] diurnal amplitudes or null
   float* traj;         // [ncol][n_saved][S] or null
   float* ckpt;         // [n_tiles32][n_ckpt][S][32] (32-column-tile layout whatever the kernel's tile width) or null
-  float* dxdt;         // rhs_only: [ncol][S]
+  float* dxdt;         // rhs_only == 1: [ncol][S] tendencies; rhs_only == 2: [ncol][nf][Nz+1] total face fluxes (predict_flux)
   int ncol;
   int n_saved;
   int n_ckpt;
@@ -43,7 +43,8 @@ __host__ __device__ inline SolveSmem solve_smem_layout(const ModelD& M, int CT, 
   // [CT][S+4] transpose staging buffer of the bulk copies
   L.bufsz = CT * (M.S + 4);
   L.buf = o; o += 3 * L.bufsz;
-  L.ks = o; o += n_stages * M.S * CT;
+  // Runge–Kutta stage slots; the implicit-diffusion step borrows two of them as scratch at the start of a sub-step
+  L.ks = o; o += (((M.flags & F_IMPLICIT) && n_stages < 2) ? 2 : n_stages) * M.S * CT;
   L.arena = o; o += M.arena_floats * CT;
   L.bcf = o; o += M.nbc * CT;
   L.qs = o; o += CT;
@@ -154,6 +155,20 @@ __device__ __forceinline__ void solve_body(const ModelD& M, const ModelD& Mp, co
   PhaseCache pc;
   build_phase_cache<WS, CT, NT>(M, pc);
 
+  if (a.rhs_only == 2) {
+    // predict_flux (NDE_training.jl:83-147; the wT reconstruction of free_convection/src/solve.jl:35-48): the total face
+    // fluxes E_q[0..Nz] whose cell difference gives the tendency. Needs a plan with the face-flux scratch rows (the adjoint plan).
+    rhs_mlp<CT, NT, WS>(M, pc, xs, arena, wsm, a.theta, bcf, qs, a.t_rhs);
+    float* E = arena + M.flux_off * CT;
+    faces_phase<CT, NT>(M, xs, arena, E, bcf);
+    __syncthreads();
+    const int rows = M.nf * (N + 1);
+    for (int i = threadIdx.x; i < rows * CT; i += NT) {
+      const int c = i % CT, r = i / CT;
+      if (col0 + c < a.ncol) a.dxdt[(size_t)(col0 + c) * rows + r] = E[r * CT + c];
+    }
+    return;
+  }
   if (a.rhs_only) {
     rhs_mlp<CT, NT, WS>(M, pc, xs, arena, wsm, a.theta, bcf, qs, a.t_rhs);
     rhs_tendencies<CT, NT, NF>(Mp, xs, arena, bcf, [=](int k0, int c, const float (&dx)[NF][4]) {
@@ -191,6 +206,10 @@ __device__ __forceinline__ void solve_body(const ModelD& M, const ModelD& Mp, co
   for (int n = 0; n < tm.n_steps; ++n) {
     for (int sub = 0; sub < tm.n_substeps; ++sub) {
       const float tb = tm.t0 + (float)(tm.step0 + n) * tm.dt + (float)sub * h;
+      if (M.flags & F_IMPLICIT) {  // backward-Euler diffusion with the incoming state's diffusivities, then the explicit step
+        implicit_diffusion_tile<CT, NT>(M, xs, ks, h);
+        __syncthreads();
+      }
       const float* in = xs;
       for (int i = 0; i < ns; ++i) {
         if (a.prof) {

@@ -240,6 +240,26 @@ __device__ __forceinline__ void side_column(const SideC& C, float du, float dv, 
   }
 }
 
+// Tridiagonal solve across the 32 lanes of a warp (lane = level): a_k x_{k-1} + b_k x_k + c_k x_{k+1} = d_k with a = 0 on lane 0
+// and c = 0 on lane 31, by parallel cyclic reduction — five shuffle steps, no shared memory, no serial sweep. After the step
+// with stride s every equation couples level k to k-2s and k+2s only; a coefficient that would point outside the column is
+// zero by induction, so out-of-range shuffles (which return the lane's own value) are multiplied by zero.
+__device__ __forceinline__ float pcr32(float a, float b, float c, float d) {
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) {
+    const float am = __shfl_up_sync(0xffffffffu, a, s), bm = __shfl_up_sync(0xffffffffu, b, s);
+    const float cm = __shfl_up_sync(0xffffffffu, c, s), dm = __shfl_up_sync(0xffffffffu, d, s);
+    const float ap = __shfl_down_sync(0xffffffffu, a, s), bp = __shfl_down_sync(0xffffffffu, b, s);
+    const float cp = __shfl_down_sync(0xffffffffu, c, s), dp = __shfl_down_sync(0xffffffffu, d, s);
+    const float al = -__fdividef(a, bm), ga = -__fdividef(c, bp);
+    b = fmaf(al, cm, fmaf(ga, ap, b));
+    d = fmaf(al, dm, fmaf(ga, dp, d));
+    a = al * am;
+    c = ga * cp;
+  }
+  return d / b;  // IEEE division: at kappa = 10 the off-diagonals are ~100 and MUFU.RCP's error shows up in the profiles
+}
+
 // ---- the solve kernel ---------------------------------------------------------------------------------------------
 // out of line: the full-range sinf keeps its slow path (and local-memory table) away from the hot loop
 static __device__ __noinline__ float tc_diurnal_top(const ModelD& M, float Q, float t) { return diurnal_top_eff(M, Q, t); }
@@ -341,7 +361,10 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
   const float Aq = qd < 3 ? M.rc.A[qd] * M.rc.Nf : 0.f;
   const float cs = qd == 0 ? M.rc.cor_u_s : (qd == 1 ? -M.rc.cor_v_s : 0.f);
   const float cm = qd == 0 ? M.rc.cor_u_m : (qd == 1 ? -M.rc.cor_v_m : 0.f);
-  const int side_mode = T.side_mode;
+  // CPZ_FLAG_IMPLICIT_DIFFUSION: the Runge–Kutta stages see no diffusive flux (mode NONE); the diffusivities act in the
+  // backward-Euler solve at the start of every sub-step instead
+  const bool implicit = (M.flags & F_IMPLICIT) != 0;
+  const int side_mode = implicit ? (int)SIDE_NONE : T.side_mode;
 
   auto write_X = [&]() {  // stage input -> B operand (hi/lo) + full-precision copy
     if (qd < 3) {
@@ -535,6 +558,51 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
     tick(6);
   };
 
+  // Backward-Euler vertical diffusion over one sub-step with the diffusivities of the incoming state (NDE_oceananigans.jl:
+  // 61-101): lane <-> level, so the tridiagonal system of each of the thread's columns is solved across the warp by parallel
+  // cyclic reduction. The other two fields' profiles come from the full-precision stage-input copies in shared memory.
+  auto implicit_step = [&](float hsub) {
+    bar_sync_named(bar_id, 256);  // every field's X (= x) of this group is in shared memory
+    if (qd < 3) {
+      float Xq[3][8];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        if (q == qd) {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) Xq[q][r] = x[r];
+        } else {
+          lds8(side_addr(3 + q, 2 * h), side_addr(3 + q, 2 * h + 1), Xq[q]);
+        }
+      }
+      float rup[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float du = __shfl_down_sync(0xffffffffu, Xq[0][r], 1) - Xq[0][r];
+        const float dv = __shfl_down_sync(0xffffffffu, Xq[1][r], 1) - Xq[1][r];
+        const float dT = __shfl_down_sync(0xffffffffu, Xq[2][r], 1) - Xq[2][r];
+        float Du = 0.f, Dv = 0.f, DT = 0.f;
+        switch (T.side_mode) {
+          case SIDE_MPP: side_column<SIDE_MPP>(T.sc, du, dv, dT, Du, Dv, DT); break;
+          case SIDE_MPP_CA_T: side_column<SIDE_MPP_CA_T>(T.sc, du, dv, dT, Du, Dv, DT); break;
+          case SIDE_MPP_CA_U: side_column<SIDE_MPP_CA_U>(T.sc, du, dv, dT, Du, Dv, DT); break;
+          case SIDE_CA_ONLY: side_column<SIDE_CA_ONLY>(T.sc, du, dv, dT, Du, Dv, DT); break;
+          default: break;
+        }
+        const float D = qd == 0 ? Du : (qd == 1 ? Dv : DT);   // Nz c_q nu_q at face lane+1
+        rup[r] = lane == 31 ? 0.f : hsub * Aq * D;
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        float rdn = __shfl_up_sync(0xffffffffu, rup[r], 1);
+        if (lane == 0) rdn = 0.f;
+        x[r] = pcr32(-rdn, 1.f + rdn + rup[r], -rup[r], x[r]);
+        X[r] = x[r];
+      }
+    }
+    bar_sync_named(bar_id, 256);  // nobody still reads the old X when it is overwritten
+    write_X();
+  };
+
   if constexpr (RHS_ONLY) {
     write_X();
     float dx[8];
@@ -577,6 +645,7 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
     for (int n = 0; n < tm.n_steps; ++n) {
       for (int sub = 0; sub < tm.n_substeps; ++sub) {
         const float tbase = tm.t0 + (float)(tm.step0 + n) * tm.dt + (float)sub * hstep;
+        if (implicit) implicit_step(hstep);
 #pragma unroll 1
         for (int i = 0; i < ns; ++i) {
           float dx[8];

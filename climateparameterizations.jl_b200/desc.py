@@ -23,6 +23,7 @@ FLAG_SMOOTH_RI = 1 << 4
 FLAG_DIURNAL = 1 << 5
 FLAG_CA_LITERAL_U = 1 << 6
 FLAG_DIURNAL_UNSHIFTED = 1 << 7
+FLAG_IMPLICIT_DIFFUSION = 1 << 8
 # activations
 ACT = {"identity": 0, "relu": 1, "mish": 2, "swish": 3, "leakyrelu": 4, "tanh": 5}
 ACT_NAMES = {v: k for k, v in ACT.items()}

@@ -18,7 +18,7 @@ EXPORTS = [
     "cpz_version", "cpz_last_error", "cpz_device_count", "cpz_sizeof_model_desc", "cpz_sizeof_closure_desc", "cpz_ctx_create", "cpz_ctx_destroy", "cpz_ctx_set_allreduce",
     "cpz_ctx_synchronize", "cpz_ctx_stream", "cpz_ctx_launch_count", "cpz_ctx_nonfinite_count", "cpz_model_create", "cpz_model_destroy",
     "cpz_model_n_params", "cpz_model_n_saved", "cpz_model_describe", "cpz_set_theta", "cpz_get_theta", "cpz_model_set_time", "cpz_rhs",
-    "cpz_rhs_dev", "cpz_solve", "cpz_solve_dev", "cpz_loss_grad", "cpz_loss_grad_dev", "cpz_train_step",
+    "cpz_rhs_dev", "cpz_predict_flux", "cpz_predict_flux_dev", "cpz_solve", "cpz_solve_dev", "cpz_loss_grad", "cpz_loss_grad_dev", "cpz_train_step",
     "cpz_train_step_dev", "cpz_set_mpp_params", "cpz_get_mpp_params", "cpz_loss_grad_mpp", "cpz_loss_grad_mpp_dev", "cpz_adam_get_state", "cpz_adam_set_state", "cpz_closure_step", "cpz_closure_step_dev",
 ]
 
@@ -65,7 +65,7 @@ def lib() -> C.CDLL:
     L.cpz_set_theta.argtypes = [vp, vp, sz]
     L.cpz_get_theta.argtypes = [vp, vp, sz]
     L.cpz_model_set_time.argtypes = [vp, i32, f32, f32, i32, i32, i32, i32]
-    for name in ("cpz_rhs", "cpz_rhs_dev"):
+    for name in ("cpz_rhs", "cpz_rhs_dev", "cpz_predict_flux", "cpz_predict_flux_dev"):
         getattr(L, name).argtypes = [vp, vp, vp, vp, f32, vp, sz]
     for name in ("cpz_solve", "cpz_solve_dev"):
         getattr(L, name).argtypes = [vp, vp, vp, vp, vp, sz]
@@ -239,6 +239,16 @@ class Model:
         Q = None if Q is None else _np(Q, (ncol,))
         out = np.empty_like(x)
         _check(lib().cpz_rhs(self._h, _ptr(x), _ptr(bcs), _ptr(Q), float(t), _ptr(out), ncol))
+        return out
+
+    def predict_flux(self, x, bcs, t: float = 0.0, Q=None) -> np.ndarray:
+        """Total face fluxes [ncol, n_fields, Nz+1] (scaled) of one RHS evaluation — cpz_predict_flux."""
+        x = _np(x)
+        ncol = x.shape[0]
+        bcs = _np(bcs, (ncol, self.desc.n_bc))
+        Q = None if Q is None else _np(Q, (ncol,))
+        out = np.empty((ncol, self.desc.n_fields, self.desc.Nz + 1), dtype=np.float32)
+        _check(lib().cpz_predict_flux(self._h, _ptr(x), _ptr(bcs), _ptr(Q), float(t), _ptr(out), ncol))
         return out
 
     def solve(self, x0, bcs, Q=None, out: Optional[np.ndarray] = None) -> np.ndarray:

@@ -99,11 +99,61 @@ def solve_nde(ndes: Sequence[NDEProblem], NN: Chain, T0: np.ndarray, alg, nde_pa
             ctx.close()
 
 
+def solve_nde_dataset(ds: FreeConvectionDataset, NN: Chain, NDEType, algorithm, T_scaling, wT_scaling, T0: Optional[np.ndarray] = None,
+                      ctx: Optional[engine.Context] = None, n_substeps: Optional[int] = None) -> Dict[str, np.ndarray]:
+    """The six-argument solve_nde (free_convection/src/solve.jl:8-51): integrate one dataset's NDE, reconstruct the total
+    temperature flux wT = [bottom; NN(T_n); top] (minus min(0, 10 dT/dz) for ConvectiveAdjustmentNDE) at every saved frame
+    and unscale both. Returns {"T": [Nt, Nz] deg C, "wT": [Nt, Nz+1]}. The per-frame NN evaluations run on the device in
+    one batched cpz_predict_flux call over all frames."""
+    own = ctx is None
+    ctx = ctx or engine.Context(0)
+    nde = NDEType(NN, ds)
+    params = FreeConvectionNDEParameters(ds, T_scaling, wT_scaling)
+    if T0 is None:
+        T0 = T_scaling(ds.T[0])  # :28-30
+    d = _desc(nde, T_scaling, wT_scaling, _integrator(algorithm), n_substeps)
+    m = engine.Model(ctx, d, destructure(NN)[0])
+    try:
+        bcs = np.ascontiguousarray(params[None, :2], dtype=np.float32)
+        T = m.solve(np.atleast_2d(np.asarray(T0, dtype=np.float32)), bcs)[0]          # [Nt, Nz] scaled
+        wT = m.predict_flux(T, np.repeat(bcs, T.shape[0], axis=0))[:, 0, :]            # [Nt, Nz+1] scaled
+        return {"T": T_scaling.unscale(T), "wT": wT_scaling.unscale(wT)}  # inv(T_scaling).(T), :50
+    finally:
+        m.close()
+        if own:
+            ctx.close()
+
+
+def masked_weight_penalty(NN: Chain, layer: int, mask: np.ndarray):
+    """causal_penalty() = sum(abs2, NN[layer].W[mask]) of train_free_convection_nde.jl:190-195 with its gradient, as a
+    function of the destructured parameter vector."""
+    off = 0
+    for i, l in enumerate(NN.layers):
+        if i == layer:
+            break
+        off += l.n_in * l.n_out + l.n_out
+    L = NN.layers[layer]
+    mflat = np.asarray(mask, dtype=bool).reshape(L.n_out, L.n_in).flatten(order="F")  # vec(W) is column-major (out x in)
+    idx = off + np.nonzero(mflat)[0]
+
+    def penalty(theta):
+        g = np.zeros_like(theta, dtype=np.float64)
+        g[idx] = 2.0 * theta[idx]
+        return float(np.sum(theta[idx].astype(np.float64) ** 2)), g
+
+    return penalty
+
+
 def train_neural_differential_equation(NN: Chain, NDEType, algorithm, datasets: Dict[int, FreeConvectionDataset], T_scaling,
                                        wT_scaling, iterations, opt: ADAM, epochs: int, history: Optional[List[float]] = None,
-                                       ctx: Optional[engine.Context] = None, n_substeps: Optional[int] = None) -> Chain:
-    """training.jl:44-74: loss = Flux.mse over all simulations' saved frames; one ADAM step per epoch
-    (Flux.train! over Iterators.repeated((), epochs)). Returns the trained Chain (the reference mutates NN in place)."""
+                                       ctx: Optional[engine.Context] = None, n_substeps: Optional[int] = None,
+                                       causal_penalty=None) -> Chain:
+    """training.jl:44-74: loss = Flux.mse over all simulations' saved frames (+ causal_penalty(NN) when given, :57-58);
+    one ADAM step per epoch (Flux.train! over Iterators.repeated((), epochs)). Returns the trained Chain (the reference
+    mutates NN in place).
+    causal_penalty: callable(theta) -> (value, d value / d theta) on the destructured parameter vector — the reference
+    passes a closure over NN and lets Zygote differentiate it (train_free_convection_nde.jl:195:
+    `sum(abs2, NN[i].W[mask])`); without an AD system the caller supplies the gradient, see `masked_weight_penalty`."""
     own = ctx is None
     ctx = ctx or engine.Context(0)
     ids = sorted(datasets.keys())
@@ -121,10 +171,28 @@ def train_neural_differential_equation(NN: Chain, NDEType, algorithm, datasets: 
         if opt.state:
             m.set_adam_state(opt.state["m"], opt.state["v"], opt.state["beta_pow"])
         for e in range(epochs):
-            l = m.train_step(T0, bcs, true_sols, w, opt.eta, opt.beta[0], opt.beta[1], opt.eps)
-            log.info("Training free convection NDE... MSE loss: %.12e", float(l[6]))
+            if causal_penalty is None:
+                l = m.train_step(T0, bcs, true_sols, w, opt.eta, opt.beta[0], opt.beta[1], opt.eps)
+                total = float(l[6])
+            else:
+                # gradient of the data term from the device, penalty term and its gradient from the caller, then the same
+                # Flux-0.11 ADAM arithmetic as cpz_train_step on the combined gradient (a P-vector update per epoch)
+                th = m.get_theta()
+                l, g = m.loss_grad(T0, bcs, true_sols, w)
+                pv, pg = causal_penalty(th)
+                total = float(l[6]) + float(pv)
+                mt, vt, bp = m.adam_state()
+                if bp[0] == 0 and bp[1] == 0:
+                    bp = np.array(opt.beta, dtype=np.float32)
+                gg = g.astype(np.float64) + np.asarray(pg, dtype=np.float64)
+                mt = opt.beta[0] * mt + (1 - opt.beta[0]) * gg
+                vt = opt.beta[1] * vt + (1 - opt.beta[1]) * gg * gg
+                th = th - mt / (1 - bp[0]) / (np.sqrt(vt / (1 - bp[1])) + opt.eps) * opt.eta
+                m.set_theta(th.astype(np.float32))
+                m.set_adam_state(mt.astype(np.float32), vt.astype(np.float32), np.array([bp[0] * opt.beta[0], bp[1] * opt.beta[1]], dtype=np.float32))
+            log.info("Training free convection NDE... MSE loss: %.12e", total)
             if history is not None:
-                history.append(float(l[6]))
+                history.append(total)
         mm, vv, bp = m.adam_state()
         opt.state = {"m": mm, "v": vv, "beta_pow": bp}
         return re(m.get_theta())

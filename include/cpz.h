@@ -68,6 +68,12 @@ typedef enum {
 #define CPZ_FLAG_SMOOTH_RI        (1u << 4) /* filters.face on Ri (NDE_training.jl:121-123) */
 #define CPZ_FLAG_DIURNAL          (1u << 5) /* time-dependent wT_top (NDE_training.jl:68-81, data_containers.jl:135) */
 #define CPZ_FLAG_CA_LITERAL_U     (1u << 6) /* CA switch tests du/dz>0 exactly as training_postprocessing.jl:120 (default tests dT/dz>0) */
+#define CPZ_FLAG_IMPLICIT_DIFFUSION (1u << 8) /* the diffusive / convective-adjustment part of the flux is left out of the RHS and
+                                               * applied by a backward-Euler tridiagonal solve (diffusivities of the incoming state)
+                                               * at the start of every (sub-)step, the way the reference integrates inside Oceananigans
+                                               * (modified_pacanowski_philander!, NDE_oceananigans.jl:61-101; convective_adjustment!,
+                                               * oceananigans_nn.jl:13-40); the NN flux, Coriolis and boundary fluxes stay explicit.
+                                               * Removes the stability sub-steps of explicit diffusion. */
 #define CPZ_FLAG_DIURNAL_UNSHIFTED (1u << 7) /* infer variant: diurnal top flux without the -s_wT(0) shift, as training_postprocessing.jl:142-144 */
 
 /* Activations (Flux 0.11.6 / NNlib 0.7.20 definitions). */
@@ -170,6 +176,13 @@ int cpz_model_set_time(cpz_model* m, int32_t integrator, float dt, float t0, int
  * diurnal_Q: [ncol] buoyancy-flux amplitudes or NULL. */
 int cpz_rhs(cpz_model* m, const float* x, const float* bcs, const float* diurnal_Q, float t, float* dxdt, size_t ncol);
 int cpz_rhs_dev(cpz_model* m, const float* x, const float* bcs, const float* diurnal_Q, float t, float* dxdt, size_t ncol);
+
+/* total face fluxes of one RHS evaluation; replaces predict_flux (NDE_training.jl:83-147), predict_flux! (training_postprocessing.jl:
+ * 105-128) and the per-frame wT reconstruction of solve_nde (free_convection/src/solve.jl:35-48).
+ * flux: [ncol][n_fields][Nz+1] (scaled): faces 0 and Nz are the effective boundary fluxes, interior faces NN flux minus the
+ * diffusive / convective-adjustment flux; D_c of it, times -tau/H sigma_flux/sigma_q (+ Coriolis), is cpz_rhs's result. */
+int cpz_predict_flux(cpz_model* m, const float* x, const float* bcs, const float* diurnal_Q, float t, float* flux, size_t ncol);
+int cpz_predict_flux_dev(cpz_model* m, const float* x, const float* bcs, const float* diurnal_Q, float t, float* flux, size_t ncol);
 
 /* ---- S2/S6: forward solve ------------------------------------------------------------------- */
 /* replaces Array(solve(prob, alg; p=[theta;BCs[i]], saveat)) (NDE_training.jl:291),

@@ -26,6 +26,7 @@ from .flux_nn import chain_torch
 
 FLAG_MPP, FLAG_CA, FLAG_ZERO_WEIGHTS, FLAG_SMOOTH_NN, FLAG_SMOOTH_RI = 1, 2, 4, 8, 16
 FLAG_DIURNAL, FLAG_CA_LITERAL_U, FLAG_DIURNAL_UNSHIFTED = 32, 64, 128
+FLAG_IMPLICIT = 256  # diffusive / convective-adjustment fluxes are left out of the RHS and applied by implicit_diffusion()
 
 # ---- tableaus ---------------------------------------------------------------------------------------------------
 TSIT5_C = (0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0)
@@ -88,6 +89,97 @@ def diurnal_top(desc, Q, t, dtype):
     return (flux - _c32(desc.mu[5])) / _c32(desc.sigma[5])
 
 
+def diffusivities(desc, x, p_mpp=None):
+    """Face diffusivities D_q [ncol, N-1] on the interior faces (None where a field has none) such that the diffusive part of
+    the flux is -D_q G_q, G_q = N (q_k - q_{k-1}):  u, v: c_q nu;  T: c_T nu_T (mPP, with the inference RHS's convective-
+    adjustment rule), c_T kappa [G_T < 0] (CA-only training branch);  T-only: [mPP] c_T nu/Pr + [CA] K [G < 0].
+    Same statements as in the reference RHS functions cited at the top of this file."""
+    N = desc.Nz
+    dtype = x.dtype
+    H = _c32(desc.H)
+    sg = [_c32(v) for v in desc.sigma]
+    c = [sg[0] / sg[3] / H, sg[1] / sg[4] / H, sg[2] / sg[5] / H]
+    if p_mpp is not None:
+        nu0_, num_, dRi_, Ric_, Pr = p_mpp[0], p_mpp[1], p_mpp[2], p_mpp[3], p_mpp[4]
+    else:
+        nu0_, num_, dRi_, Ric_, Pr = _c32(desc.nu0), _c32(desc.nu_m), _c32(desc.dRi), _c32(desc.Ric), _c32(desc.Pr)
+    BzC = H * _c32(desc.g) * _c32(desc.alpha) * sg[2]
+    if desc.variant == 2:  # T-only
+        G = N * (x[:, 1:] - x[:, :-1])
+        D = None
+        if desc.flags & FLAG_MPP:
+            # BASELINE config 1 ("convective adjustment + mPP base" on the T-only NDE; SURVEY 8d config 1, Q5): the mPP
+            # rule of NDE_training.jl:114-139 at u = v = 0, i.e. both shear gradients are D_face*0 + eps
+            eps = _c32(desc.eps)
+            Ri = BzC * (G + eps) / ((sg[0] * eps) ** 2 + (sg[1] * eps) ** 2)
+            nu = nu0_ + num_ * (1 - torch.tanh((Ri - Ric_) / dRi_)) / 2
+            D = c[2] * nu / Pr
+        if desc.flags & FLAG_CA:
+            Dca = torch.where(G < 0, torch.full_like(G, _c32(desc.K_ca)), torch.zeros_like(G))
+            D = Dca if D is None else D + Dca
+        return [D]
+    u, v, T = x[:, :N], x[:, N:2 * N], x[:, 2 * N:]
+    Gi = [N * (q[:, 1:] - q[:, :-1]) for q in (u, v, T)]
+    mpp = bool(desc.flags & FLAG_MPP) or desc.variant == 1  # the inference RHS always applies mPP
+    if mpp:
+        eps = _c32(desc.eps) if desc.variant == 0 else 0.0
+        if desc.variant == 0 and (desc.flags & FLAG_SMOOTH_RI):
+            # filters.face acts on all N+1 faces, so the boundary-face Ri (gradients = 0 + eps) takes part
+            Gf = [_delta_f(q, N) for q in (u, v, T)]
+            Ri = BzC * (Gf[2] + eps) / ((sg[0] * (Gf[0] + eps)) ** 2 + (sg[1] * (Gf[1] + eps)) ** 2)
+            Ri = _filter3(Ri)[:, 1:-1]
+        else:
+            Ri = BzC * (Gi[2] + eps) / ((sg[0] * (Gi[0] + eps)) ** 2 + (sg[1] * (Gi[1] + eps)) ** 2)
+        nu = nu0_ + num_ * (1 - torch.tanh((Ri - Ric_) / dRi_)) / 2
+        if desc.variant == 1 and (desc.flags & FLAG_CA):
+            test = Gi[0] if (desc.flags & FLAG_CA_LITERAL_U) else Gi[2]
+            nu_T = torch.where(test > 0, nu / Pr, torch.full_like(nu, _c32(desc.kappa)))
+        else:
+            nu_T = nu / Pr
+        return [c[0] * nu, c[1] * nu, c[2] * nu_T]
+    if desc.flags & FLAG_CA:
+        return [None, None, c[2] * _c32(desc.kappa) * (Gi[2] < 0).to(dtype)]
+    return [None, None, None]
+
+
+def implicit_diffusion(desc, x, h, p_mpp=None):
+    r"""Backward-Euler step of the vertical-diffusion part of the RHS over a non-dimensional interval h, with the
+    diffusivities frozen at the incoming state — the treatment the reference uses when the NDE runs inside Oceananigans
+    (modified_pacanowski_philander!, wind_mixing/src/NDE_oceananigans.jl:61-101; convective_adjustment!,
+    free_convection/src/oceananigans_nn.jl:13-40):  lower_k = -r_k, upper_k = -r_{k+1}, diag_k = 1 + r_k + r_{k+1},
+    r_k = h A_q N^2 D_q,k on the interior faces and r = 0 on the two boundary faces (their fluxes are prescribed and stay in
+    the explicit part); x_q <- L_q \ x_q by the Thomas algorithm. Here in the NDE's scaled, non-dimensional variables."""
+    N = desc.Nz
+    tau, H = _c32(desc.tau), _c32(desc.H)
+    sg = [_c32(v) for v in desc.sigma]
+    Ds = diffusivities(desc, x, p_mpp)
+    nf = desc.n_fields
+    out = []
+    for q in range(nf):
+        xq = x[:, q * N:(q + 1) * N]
+        if Ds[q] is None:
+            out.append(xq)
+            continue
+        qq = q if nf == 3 else 2
+        A = tau / H * sg[3 + qq] / sg[qq]
+        z = torch.zeros_like(xq[:, :1])
+        r = torch.cat([z, (h * A * N * N) * Ds[q], z], dim=1)  # faces 0..N
+        lower, upper, diag = -r[:, :-1], -r[:, 1:], 1 + r[:, :-1] + r[:, 1:]  # per level k: faces k (below) and k+1 (above)
+        cp, dp = [None] * N, [None] * N
+        cp[0] = upper[:, 0] / diag[:, 0]
+        dp[0] = xq[:, 0] / diag[:, 0]
+        for k in range(1, N):
+            den = diag[:, k] - lower[:, k] * cp[k - 1]
+            cp[k] = upper[:, k] / den
+            dp[k] = (xq[:, k] - lower[:, k] * dp[k - 1]) / den
+        y = [None] * N
+        y[N - 1] = dp[N - 1]
+        for k in range(N - 2, -1, -1):
+            y[k] = dp[k] - cp[k] * y[k + 1]
+        out.append(torch.stack(y, dim=1))
+    return torch.cat(out, dim=1)
+
+
 def rhs(desc, theta, x, bcs, t=0.0, Q=None, p_mpp=None):
     """dx/dt for a batch of columns. x [ncol, S] torch tensor; theta torch 1-D (may require grad).
     p_mpp: optional tensor (nu0, nu_m, dRi, Ric, Pr) overriding the description's constants — the differentiable
@@ -99,6 +191,7 @@ def rhs(desc, theta, x, bcs, t=0.0, Q=None, p_mpp=None):
     sg = [_c32(s) for s in desc.sigma]
     thetas = split_thetas(desc, theta) if desc.nets else []
 
+    implicit = bool(desc.flags & FLAG_IMPLICIT)
     if desc.variant == 2:  # T-only
         T = x
         ncol = T.shape[0]
@@ -106,21 +199,14 @@ def rhs(desc, theta, x, bcs, t=0.0, Q=None, p_mpp=None):
             nn = chain_torch(thetas[0], desc.nets[0].sizes, desc.nets[0].acts, T)
         else:
             nn = torch.zeros(ncol, N - 1, dtype=dtype)
-        if desc.flags & FLAG_MPP:
-            # BASELINE config 1 ("convective adjustment + mPP base" on the T-only NDE): the mPP
-            # rule of NDE_training.jl:114-139 at u = v = 0, i.e. both shear gradients are D_face*0 + eps
-            eps = _c32(desc.eps)
-            G = N * (T[:, 1:] - T[:, :-1])
-            BzC = H * _c32(desc.g) * _c32(desc.alpha) * sg[2]
-            Ri = BzC * (G + eps) / ((sg[0] * eps) ** 2 + (sg[1] * eps) ** 2)
-            nu = _c32(desc.nu0) + _c32(desc.nu_m) * (1 - torch.tanh((Ri - _c32(desc.Ric)) / _c32(desc.dRi))) / 2
-            nn = nn - sg[2] / sg[5] / H * nu / _c32(desc.Pr) * G
+        if not implicit:
+            D = diffusivities(desc, x, p_mpp)[0]
+            if D is not None:
+                # D G = [mPP] sigma_T/(sigma_wT H) nu/Pr dT/dz + [CA] min(0, K dT/dz)   (convective_adjustment_nde.jl:44-47)
+                nn = nn - D * (N * (T[:, 1:] - T[:, :-1]))
         F = torch.cat([bcs[:, 0:1], nn, bcs[:, 1:2]], dim=1)
         A = sg[5] / sg[2] * tau / H
-        out = -_delta_c(F, N)
-        if desc.flags & FLAG_CA:
-            out = out + _delta_c(torch.clamp_max(_c32(desc.K_ca) * _delta_f(T, N), 0.0), N)
-        return A * out
+        return -A * _delta_c(F, N)
 
     f = _c32(desc.f)
     u, v, T = x[:, :N], x[:, N:2 * N], x[:, 2 * N:]
@@ -146,31 +232,8 @@ def rhs(desc, theta, x, bcs, t=0.0, Q=None, p_mpp=None):
     mpp = bool(desc.flags & FLAG_MPP) or desc.variant == 1  # the inference RHS always applies mPP
     shift = desc.variant == 1 or bool(desc.flags & FLAG_ZERO_WEIGHTS)
 
-    if mpp:
-        eps = _c32(desc.eps) if desc.variant == 0 else 0.0
-        BzC = H * _c32(desc.g) * _c32(desc.alpha) * sg[2]
-        if desc.variant == 0 and (desc.flags & FLAG_SMOOTH_RI):
-            # filters.face acts on all N+1 faces, so the boundary-face Ri (gradients = 0 + eps) takes part
-            Gf = [_delta_f(q, N) for q in (u, v, T)]
-            Ri = BzC * (Gf[2] + eps) / ((sg[0] * (Gf[0] + eps)) ** 2 + (sg[1] * (Gf[1] + eps)) ** 2)
-            Ri = _filter3(Ri)[:, 1:-1]
-        else:
-            Ri = BzC * (Gi[2] + eps) / ((sg[0] * (Gi[0] + eps)) ** 2 + (sg[1] * (Gi[1] + eps)) ** 2)
-        if p_mpp is not None:
-            nu0_, num_, dRi_, Ric_, Pr = p_mpp[0], p_mpp[1], p_mpp[2], p_mpp[3], p_mpp[4]
-        else:
-            nu0_, num_, dRi_, Ric_, Pr = _c32(desc.nu0), _c32(desc.nu_m), _c32(desc.dRi), _c32(desc.Ric), _c32(desc.Pr)
-        nu = nu0_ + num_ * (1 - torch.tanh((Ri - Ric_) / dRi_)) / 2
-        if desc.variant == 1 and (desc.flags & FLAG_CA):
-            test = Gi[0] if (desc.flags & FLAG_CA_LITERAL_U) else Gi[2]
-            nu_T = torch.where(test > 0, nu / Pr, torch.full_like(nu, _c32(desc.kappa)))
-        else:
-            nu_T = nu / Pr
-        interior = [nn[0] - c[0] * nu * Gi[0], nn[1] - c[1] * nu * Gi[1], nn[2] - c[2] * nu_T * Gi[2]]
-    elif desc.flags & FLAG_CA:
-        interior = [nn[0], nn[1], nn[2] - c[2] * _c32(desc.kappa) * torch.clamp_max(Gi[2], 0.0)]
-    else:
-        interior = nn
+    D = [None, None, None] if implicit else diffusivities(desc, x, p_mpp)
+    interior = [nn[i] if D[i] is None else nn[i] - D[i] * Gi[i] for i in range(3)]
 
     F = []
     for i in range(3):
@@ -214,6 +277,8 @@ def solve(desc, theta, x0, bcs, Q=None, mpp=None):
     for n in range(desc.n_steps):
         t_n = _c32(desc.t0) + n * _c32(desc.dt)
         for s in range(desc.n_substeps):
+            if desc.flags & FLAG_IMPLICIT:  # Lie splitting in the order of the Oceananigans embedding: implicit diffusion with
+                x = implicit_diffusion(desc, x, h, mpp)  # the diffusivities of the incoming state, then the explicit step
             x = rk_step(desc, theta, x, bcs, t_n + s * h, h, Q, mpp)
         if desc.save_stride > 0 and (n + 1) % desc.save_stride == 0:
             frames.append(x)

@@ -129,7 +129,7 @@ def test_allreduce_hook_plumbing_on_one_gpu(ctx):
     m2 = engine.Model(c2, d, th)
     l2, g2 = m2.loss_grad(x0, bcs, tgt, w)
     m2.close(); c2.close()
-    assert calls == [d.n_params + 8]
+    assert calls == [d.n_params + 16]  # [grad; 6 sums; ncol; pad; 5 mPP-parameter sums; pad]
     np.testing.assert_allclose(l2, l1, rtol=1e-6)
     np.testing.assert_allclose(g2, g1, rtol=1e-5, atol=1e-9)
 
@@ -163,3 +163,79 @@ def test_nonfinite_results_are_reported_not_hidden(ctx):
         m2.close()
         assert np.isnan(dx[3, 0]), act  # level 0 of u sees the NaN at level 8 of v only through the net's hidden layer
     m.close()
+
+
+@pytest.mark.parametrize("case", ["uvT_train", "uvT_infer_ca", "T_only", "T_only_ca_mpp"])
+def test_predict_flux_matches_the_oracle_and_the_rhs(ctx, case):
+    """cpz_predict_flux = predict_flux (NDE_training.jl:83-147) / the wT reconstruction of solve_nde (solve.jl:35-48):
+    D_c of the returned face fluxes, times -tau/H sigma_flux/sigma_q (plus Coriolis), must be cpz_rhs's tendency, and the
+    T-only fluxes must equal [bottom; NN(T); top] - min(0, 10 dT/dz) evaluated with the oracle's Chain."""
+    from cpz_b200.desc import FLAG_CA
+    if case == "uvT_train":
+        d = syn.wind_mixing_desc(variant=RHS_TRAIN)
+    elif case == "uvT_infer_ca":
+        d = syn.wind_mixing_desc(variant=RHS_INFER, flags=FLAG_MPP | FLAG_CA)
+    else:
+        d = syn.free_convection_desc(ca=True, mpp=(case == "T_only_ca_mpp"))
+    th = syn.theta_random(d, scale=1.0)
+    x, bcs = syn.columns(d, 45)
+    if d.n_fields == 1:
+        x[:, 8:16] = x[:, 15:7:-1].copy()
+    m = engine.Model(ctx, d, th)
+    F = m.predict_flux(x, bcs, t=0.1)
+    dx = m.rhs(x, bcs, t=0.1)
+    m.close()
+    N = d.Nz
+    assert F.shape == (45, d.n_fields, N + 1)
+    ref = oracle_rhs(d, th, x, bcs, 0.1)
+    for q in range(d.n_fields):
+        qq = q if d.n_fields == 3 else 2
+        A = d.tau / d.H * d.sigma[3 + qq] / d.sigma[qq]
+        tend = -A * N * (F[:, q, 1:].astype(np.float64) - F[:, q, :-1])
+        if d.n_fields == 3 and q == 0:
+            tend += d.f * d.tau / d.sigma[0] * (d.sigma[1] * x[:, N:2 * N] + d.mu[1])
+        if d.n_fields == 3 and q == 1:
+            tend -= d.f * d.tau / d.sigma[1] * (d.sigma[0] * x[:, :N] + d.mu[0])
+        scale = np.abs(ref).max()
+        assert np.abs(tend - ref[:, q * N:(q + 1) * N]).max() / scale <= 2e-5, (case, q)
+        assert np.abs(tend - dx[:, q * N:(q + 1) * N]).max() / scale <= 2e-5
+    if case == "T_only":
+        from oracle.flux_nn import chain_numpy
+        nn = np.stack([chain_numpy(th.astype(np.float64), d.nets[0].sizes, d.nets[0].acts, x[i].astype(np.float64)) for i in range(45)])
+        G = N * (x[:, 1:].astype(np.float64) - x[:, :-1])
+        wT = np.concatenate([bcs[:, :1], nn - np.minimum(0, d.K_ca * G), bcs[:, 1:]], axis=1)
+        assert rel_inf(F[:, 0], wT) <= 1e-5
+
+
+def test_solve_nde_six_argument_method_and_causal_penalty(ctx):
+    """solve_nde(ds, NN, NDEType, alg, T_scaling, wT_scaling) (solve.jl:8-51) returns unscaled T and the reconstructed wT;
+    train_neural_differential_equation! accepts a causal penalty (training.jl:57-58, train_free_convection_nde.jl:190-195)."""
+    rng = np.random.default_rng(3)
+    T_scaling = ZeroMeanUnitVarianceScaling(mu=19.8, sigma=0.15)
+    wT_scaling = ZeroMeanUnitVarianceScaling(mu=5e-6, sigma=6e-6)
+    Nt, z = 19, -100 + (np.arange(32) + 0.5) * 100 / 32
+    T = (20 + 0.01 * np.minimum(z, -30.0))[None, :] - 0.002 * np.linspace(0, 1, Nt)[:, None] * np.exp(z / 30)[None, :]
+    ds = fc.FreeConvectionDataset(T=T, wT_bottom=0.0, temperature_flux=1e-5, H=100.0, times=np.arange(Nt) * 600.0)
+    NN = flux.Chain(flux.Dense(32, 128, "relu", rng=rng), flux.Dense(128, 128, "relu", rng=rng), flux.Dense(128, 31, rng=rng)).scale(1e-2)
+    out = fc.solve_nde_dataset(ds, NN, fc.ConvectiveAdjustmentNDE, "Tsit5", T_scaling, wT_scaling, ctx=ctx)
+    assert out["T"].shape == (Nt, 32) and out["wT"].shape == (Nt, 33) and np.isfinite(out["wT"]).all()
+    np.testing.assert_allclose(out["T"][0], T[0], rtol=1e-6)
+    np.testing.assert_allclose(out["wT"][:, 0], 0.0, atol=1e-12)      # bottom flux
+    np.testing.assert_allclose(out["wT"][:, -1], 1e-5, rtol=1e-5)     # imposed surface flux
+    # causal penalty on the upper triangle of the first layer: the penalised weights shrink relative to plain training
+    mask = np.triu(np.ones((128, 32), dtype=bool), k=1)
+    pen = fc.masked_weight_penalty(NN, 0, mask)
+    th0 = flux.destructure(NN)[0]
+    v0, g0 = pen(th0)
+    assert v0 > 0 and np.count_nonzero(g0) == mask.sum()
+    datasets = {1: ds}
+    hist = []
+    lam = 1e3
+    NNp = fc.train_neural_differential_equation(NN, fc.ConvectiveAdjustmentNDE, "Tsit5", datasets, T_scaling, wT_scaling, range(0, 19, 9),
+                                                flux.ADAM(1e-3), 8, history=hist, ctx=ctx,
+                                                causal_penalty=lambda th: tuple(lam * np.asarray(v) for v in pen(th)))
+    NNu = fc.train_neural_differential_equation(NN, fc.ConvectiveAdjustmentNDE, "Tsit5", datasets, T_scaling, wT_scaling, range(0, 19, 9),
+                                                flux.ADAM(1e-3), 8, ctx=ctx)
+    vp, vu = pen(flux.destructure(NNp)[0])[0], pen(flux.destructure(NNu)[0])[0]
+    print(f"causal penalty: initial {v0:.4e}, after 8 epochs with penalty {vp:.4e}, without {vu:.4e}; losses {hist[0]:.3e} -> {hist[-1]:.3e}")
+    assert len(hist) == 8 and np.all(np.isfinite(hist)) and vp < vu and vp < v0

@@ -18,13 +18,16 @@ for ncol in sizes:
         x, b = syn.columns(d, ncol, seed=1000)
         xd, bd = torch.tensor(x, device="cuda"), torch.tensor(b, device="cuda")
         tg = xd[:, None, :].repeat(1, d.n_saved, 1).contiguous()
-        for small in ("0", "100000"):
-            os.environ["CPZ_SMALL_NCOL"] = small
+        for small in ("0", "100000", "auto"):
+            if small == "auto":
+                os.environ.pop("CPZ_SMALL_NCOL", None)
+            else:
+                os.environ["CPZ_SMALL_NCOL"] = small
             m = engine.Model(ctx, d, syn.theta_init(d, seed=42, scale=1e-5))
             m.train_step_dev(xd, bd, tg, w, 3e-4)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); m.train_step_dev(xd, bd, tg, w, 3e-4); e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
-            print(f"ncol {ncol:5d} ckpt_stride {ck} tiles {'4-col ' if small != '0' else '32-col'}: {ms:8.1f} ms  {ncol*1152/ms*1e3:.3e} col-steps/s", flush=True)
+            print(f"ncol {ncol:5d} ckpt_stride {ck} tiles {dict([('0', '32-col'), ('100000', '4-col '), ('auto', 'auto  ')])[small]}: {ms:8.1f} ms  {ncol*1152/ms*1e3:.3e} col-steps/s", flush=True)
             m.close()
