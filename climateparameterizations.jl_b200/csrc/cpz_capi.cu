@@ -252,7 +252,7 @@ int cpz_model_destroy(cpz_model* m) {
   if (m->d_m) cudaFree(m->d_m);
   if (m->d_v) cudaFree(m->d_v);
   if (m->d_gmap) cudaFree(m->d_gmap);
-  DevBuf* bufs[] = {&m->b_x0, &m->b_bcs, &m->b_q, &m->b_traj, &m->b_tgt, &m->b_ckpt, &m->b_scr, &m->b_part, &m->b_red, &m->b_out, &m->b_w, &m->b_wimg, &m->b_cimg, &m->b_fcscr, &m->b_kstore};
+  DevBuf* bufs[] = {&m->b_x0, &m->b_bcs, &m->b_q, &m->b_traj, &m->b_tgt, &m->b_ckpt, &m->b_scr, &m->b_part, &m->b_red, &m->b_out, &m->b_w, &m->b_wimg, &m->b_cimg, &m->b_fcscr, &m->b_kstore, &m->b_aux, &m->b_bwimg, &m->b_tcadj};
   for (DevBuf* b : bufs) release(*b);
   delete m;
   return CPZ_OK;

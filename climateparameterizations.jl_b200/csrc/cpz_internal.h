@@ -57,6 +57,7 @@ struct cpz_model {
   float beta_pow[2] = {0.f, 0.f};  // 0 = uninitialised (set to (beta1,beta2) on the first step)
   // grow-only device scratch
   DevBuf b_x0, b_bcs, b_q, b_traj, b_tgt, b_ckpt, b_scr, b_part, b_red, b_out, b_w, b_wimg, b_cimg, b_fcscr, b_kstore;
+  DevBuf b_aux, b_bwimg, b_tcadj;  // tensor-core adjoint: per-stage records, transposed weight image, xbar + loss sums + accumulator images
   uint64_t theta_ver = 1;   // bumped whenever d_theta changes (set_theta, ADAM step)
   uint64_t cimg_ver = 0;    // theta_ver the closure weight image was built from
 };

@@ -1,0 +1,163 @@
+// Tensor-core adjoint (cpz_adjoint_tc.cuh): eligibility, buffers, and the per-segment launch sequence
+//   segment forward pass (solve_tc_kernel<AUX>) -> adjoint_tc_kernel -> wgrad_tc_kernel,   last segment first.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+#include "cpz_launch.h"
+#include "cpz_adjoint_tc.cuh"
+
+namespace cpz {
+
+bool tc_plan(const cpz_model* m, TcD& T, std::string& why);  // cpz_k_tc.cu
+
+static int ensure_buf(DevBuf& b, size_t floats) {
+  if (floats <= b.cap) return CPZ_OK;
+  if (b.p) CPZ_CUDA(cudaFree(b.p));
+  b.p = nullptr; b.cap = 0;
+  CPZ_CUDA(cudaMalloc(&b.p, std::max<size_t>(floats, 4) * sizeof(float)));
+  b.cap = floats;
+  return CPZ_OK;
+}
+
+// The tensor-core adjoint covers what the tcgen05 forward solve covers, minus the implicit-diffusion step (its VJP lives
+// in the FP32 adjoint) and the mPP-parameter gradient. CPZ_NO_TC_ADJ=1 forces the FP32 SIMT adjoint for A/B runs.
+bool adjoint_tc_eligible(cpz_model* m, std::string* why_out) {
+  std::string why;
+  TcD T;
+  TcB B;
+  bool ok = true;
+  if (getenv("CPZ_NO_TC") != nullptr || getenv("CPZ_NO_TC_ADJ") != nullptr) { why = "disabled by CPZ_NO_TC / CPZ_NO_TC_ADJ"; ok = false; }
+  else if (getenv("CPZ_PROF") != nullptr) { why = "CPZ_PROF profiles the FP32 kernels"; ok = false; }
+  else if (!tc_plan(m, T, why)) ok = false;
+  else if (m->desc.flags & CPZ_FLAG_IMPLICIT_DIFFUSION) { why = "implicit diffusion step"; ok = false; }
+  else if (!tc_bwd_plan(T, B)) { why = "transposed weight images exceed tensor memory"; ok = false; }
+  else {
+    const TcBSmem L = tc_bwd_smem_layout(B, m->tab.n_stages);
+    AuxD A{};
+    tc_aux_rows(T, A);
+    const size_t wg_smem = (size_t)2 * 8 * (A.rx + 2 * A.r1 + 2 * A.r2 + A.r3) * 16 + 64;
+    if ((size_t)L.total > m->ctx->smem_optin || wg_smem > m->ctx->smem_optin) { why = "shared memory"; ok = false; }
+  }
+  if (why_out) *why_out = why;
+  return ok;
+}
+
+template <int ACT>
+static int launch_segment_t(cpz_model* m, const TcD& T, const TcB& B, const AdjTcArgs& aa, const TimeD& tm, int n_tiles, const WgradArgs& wa,
+                            int wg_grid, size_t wg_smem, bool ref) {
+  const TcBSmem L = tc_bwd_smem_layout(B, m->tab.n_stages);
+  auto kern = adjoint_tc_kernel<ACT>;
+  CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  kern<<<n_tiles, TC_NT, L.total, m->ctx->stream>>>(m->fwd.M, T, B, m->tab, tm, aa);
+  CPZ_CUDA(cudaGetLastError());
+  m->ctx->launches++;
+  if (ref) {
+    const int n = (B.N1 + 2 * B.N2 + 96) * 128;
+    wgrad_ref_kernel<ACT><<<(n + 127) / 128, 128, 0, m->ctx->stream>>>(T, B, wa);
+  } else {
+    auto wk = wgrad_tc_kernel<ACT>;
+    CPZ_CUDA(cudaFuncSetAttribute(wk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem));
+    wk<<<wg_grid, WG_NT, wg_smem, m->ctx->stream>>>(T, B, wa);
+  }
+  CPZ_CUDA(cudaGetLastError());
+  m->ctx->launches++;
+  return CPZ_OK;
+}
+
+// Forward solve with checkpoints, then the reverse sweep segment by segment. On return m->b_red[0,P) holds the sum over
+// the local columns of d(unnormalised loss)/dtheta and *lpart_out / *n_lpart the per-tile squared-error sums (stride 8).
+int loss_grad_tc(cpz_model* m, const float* x0, const float* bcs, const float* Q, const float* targets, size_t ncol,
+                 const float* loss_w, float inv_prof, float inv_grad, int n_saved, int n_ckpt, const float** lpart_out, int* n_lpart) {
+  TcD T;
+  TcB B;
+  std::string why;
+  if (!tc_plan(m, T, why) || !tc_bwd_plan(T, B)) return fail(CPZ_ERR_INVALID, "tensor-core adjoint not eligible: %s", why.c_str());
+  cudaStream_t st = m->ctx->stream;
+  const int P = (int)m->P, S = 96;
+  const int n_tiles = ((int)ncol + 31) / 32;
+  const TimeD tm_full = m->tm;
+  const int cs = tm_full.ckpt_stride, ns = m->tab.n_stages;
+  const int nseg = (tm_full.n_steps + cs - 1) / cs;
+  const int max_eval = std::min(cs, tm_full.n_steps) * tm_full.n_substeps * ns;
+  AuxD A{};
+  tc_aux_rows(T, A);
+  const size_t rec_rows = (size_t)A.rx + 2 * A.r1 + 2 * A.r2 + A.r3;
+  const size_t n_rec_max = (size_t)n_tiles * max_eval;
+  int rc;
+  if ((rc = ensure_buf(m->b_ckpt, (size_t)n_tiles * n_ckpt * S * 32))) return rc;
+  if ((rc = ensure_buf(m->b_aux, n_rec_max * rec_rows * 32))) return rc;
+  if ((rc = ensure_buf(m->b_bwimg, (size_t)B.n_wcols * 128))) return rc;
+  const bool ref = getenv("CPZ_WGRAD_REF") != nullptr;
+  const int sms = m->ctx->sm_count > 0 ? m->ctx->sm_count : 148;
+  const int wg_grid = ref ? 1 : (int)std::min<size_t>((size_t)sms, (size_t)n_tiles * ns);
+  // [xbar: n_tiles*96*32][lpart: n_tiles*8][accumulator images: wg_grid*WG_COLS*128]
+  const size_t f_xbar = (size_t)n_tiles * S * 32, f_lp = (size_t)n_tiles * 8, f_img = (size_t)wg_grid * WG_COLS * 128;
+  if ((rc = ensure_buf(m->b_tcadj, f_xbar + f_lp + f_img))) return rc;
+  float* xbar = m->b_tcadj.p;
+  float* lpart = xbar + f_xbar;
+  float* img = lpart + f_lp;
+  CPZ_CUDA(cudaMemsetAsync(lpart, 0, (f_lp + f_img) * sizeof(float), st));
+  float* p = m->b_aux.p;
+  A.x = p; p += n_rec_max * A.rx * 32;
+  A.z1 = p; p += n_rec_max * A.r1 * 32;
+  A.z2 = p; p += n_rec_max * A.r2 * 32;
+  A.d1 = p; p += n_rec_max * A.r1 * 32;
+  A.d2 = p; p += n_rec_max * A.r2 * 32;
+  A.d3 = p;
+
+  // (1) forward with checkpoints
+  SolveArgs fa{};
+  fa.theta = m->d_theta; fa.x0 = x0; fa.bcs = bcs; fa.Q = Q; fa.traj = nullptr; fa.ckpt = m->b_ckpt.p;
+  fa.ncol = (int)ncol; fa.n_saved = n_saved; fa.n_ckpt = n_ckpt; fa.rhs_only = 0;
+  if ((rc = launch_solve_tc(m, fa))) return rc > 0 ? fail(CPZ_ERR_INVALID, "tcgen05 forward solve not eligible") : rc;
+
+  tc_bwd_image_kernel<<<(B.n_wcols * 128 + 255) / 256, 256, 0, st>>>(T, B, m->d_theta, m->b_bwimg.p);
+  CPZ_CUDA(cudaGetLastError());
+  m->ctx->launches++;
+
+  // (2) segments, last first
+  const size_t SL = (size_t)S * 32;
+  for (int seg = nseg - 1; seg >= 0; --seg) {
+    const int n0 = seg * cs, n1 = std::min(n0 + cs, tm_full.n_steps);
+    A.n_eval = (n1 - n0) * tm_full.n_substeps * ns;
+    SolveArgs sa{};
+    sa.theta = m->d_theta; sa.x0 = x0; sa.bcs = bcs; sa.Q = Q; sa.traj = nullptr; sa.ckpt = nullptr;
+    sa.ncol = (int)ncol; sa.n_saved = n_saved; sa.n_ckpt = 0; sa.rhs_only = 0;
+    sa.x0_tile = m->b_ckpt.p + (size_t)seg * SL; sa.x0_tile_stride = (size_t)n_ckpt * SL;
+    sa.aux = A;
+    m->tm = tm_full;
+    m->tm.step0 = tm_full.step0 + n0;
+    m->tm.n_steps = n1 - n0;
+    m->tm.save_stride = 0;
+    rc = launch_solve_tc(m, sa);
+    m->tm = tm_full;
+    if (rc) return rc > 0 ? fail(CPZ_ERR_INVALID, "tcgen05 forward solve not eligible") : rc;
+
+    AdjTcArgs aa{};
+    aa.wimg = m->b_bwimg.p; aa.theta = m->d_theta; aa.targets = targets;
+    aa.xN = m->b_ckpt.p + (size_t)(n_ckpt - 1) * SL; aa.xN_stride = (size_t)n_ckpt * SL;
+    aa.xbar = xbar; aa.lpart = lpart; aa.aux = A;
+    aa.ncol = (int)ncol; aa.n_saved = n_saved; aa.first = seg == nseg - 1 ? 1 : 0;
+    aa.seg_step0 = n0; aa.seg_steps = n1 - n0;
+    for (int q = 0; q < 6; ++q) aa.w[q] = loss_w[q];
+    aa.inv_prof = inv_prof; aa.inv_grad = inv_grad;
+    WgradArgs wa{};
+    wa.aux = A; wa.n_rec = n_tiles * A.n_eval; wa.part = img;
+    const size_t wg_smem = (size_t)2 * 8 * rec_rows * 16 + 64;
+    const bool mish = T.act1 == T.act2 && T.act1 == ACT_MISH, relu = T.act1 == T.act2 && T.act1 == ACT_RELU;
+    if (mish) rc = launch_segment_t<ACT_MISH>(m, T, B, aa, tm_full, n_tiles, wa, wg_grid, wg_smem, ref);
+    else if (relu) rc = launch_segment_t<ACT_RELU>(m, T, B, aa, tm_full, n_tiles, wa, wg_grid, wg_smem, ref);
+    else rc = launch_segment_t<-1>(m, T, B, aa, tm_full, n_tiles, wa, wg_grid, wg_smem, ref);
+    if (rc) return rc;
+  }
+  // (3) gradient in destructure order
+  wgrad_finish_kernel<<<(P + 255) / 256, 256, 0, st>>>(T, B, img, wg_grid, P, m->b_red.p);
+  CPZ_CUDA(cudaGetLastError());
+  m->ctx->launches++;
+  *lpart_out = lpart;
+  *n_lpart = n_tiles;
+  return CPZ_OK;
+}
+
+}  // namespace cpz

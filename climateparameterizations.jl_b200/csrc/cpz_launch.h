@@ -16,6 +16,11 @@ bool closure_uses_tc(const cpz_model* m);  // NN-free u/v/T model; 1 = not eligi
 // one line for cpz_model_describe: which forward kernel this model runs on and why
 std::string tc_describe(const cpz_model* m);  // 1 = not eligible, use the SIMT kernel
 int launch_adjoint(cpz_model* m, const AdjArgs& a, int grid);
+// tensor-core adjoint (cpz_k_adjoint_tc.cu): checkpointing forward solve + reverse sweep; leaves the summed gradient in
+// m->b_red[0,P) and returns the per-tile squared-error sums (stride 8)
+bool adjoint_tc_eligible(cpz_model* m, std::string* why);
+int loss_grad_tc(cpz_model* m, const float* x0, const float* bcs, const float* Q, const float* targets, size_t ncol,
+                 const float* loss_w, float inv_prof, float inv_grad, int n_saved, int n_ckpt, const float** lpart_out, int* n_lpart);
 // 4-, 8- and 16-column-tile instantiations (cpz_k_small.cu, cpz_k_small8.cu, cpz_k_small16.cu); CT selects the plan
 int launch_solve_small(cpz_model* m, const SolveArgs& a, int CT);
 int launch_adjoint_small(cpz_model* m, const AdjArgs& a, int grid, int CT);

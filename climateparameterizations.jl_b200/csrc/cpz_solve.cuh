@@ -5,6 +5,20 @@
 
 namespace cpz {
 
+// Per-stage records the tensor-core adjoint exchanges through HBM (cpz_adjoint_tc.cuh). One record per (32-column tile,
+// stage evaluation e of the launch): `rows` x 32 columns stored as [column quad 0..8)[row][4] floats — the canonical
+// un-swizzled K-major operand image of tcgen05.mma with K = column (LBO = 16*rows bytes, SBO = 128), so the weight-gradient
+// contraction reads a record as an MMA operand without any re-layout.
+//   x : stage input X_i (row = 32*field + level)           rx rows   written by the forward (segment) pass
+//   z1: layer-1 pre-activations (row = net*h1 + o)          r1 rows     "
+//   z2: layer-2 pre-activations (row = net*h2 + o)          r2 rows     "
+//   d1, d2: cotangents of z1, z2; d3: cotangent of the NN fluxes (row = 32*net + j, r3 = 96)   written by the reverse sweep
+struct AuxD {
+  float *x, *z1, *z2, *d1, *d2, *d3;
+  int rx, r1, r2, r3;
+  int n_eval;  // stage evaluations per tile in the buffers (segment Runge–Kutta steps x stages)
+};
+
 struct SolveArgs {
   const float* theta;  // [P] destructure order
   const float* x0;     // [ncol][S]
@@ -23,6 +37,9 @@ struct SolveArgs {
   int skip_frame0;           // continuation of a chunked solve: the start state is already in the trajectory, do not store it
   int small_tiles;           // host hint: a checkpointing solve whose adjoint runs on tiles of this many (4, 8, 16) columns; 0 = 32
   float* kstore;             // optional [n_tiles][n_rk_steps][n_stages][S][32]: every stage tendency k_i, for the adjoint (tcgen05 solve only)
+  const float* x0_tile;      // tcgen05 solve only: start state in the checkpoint layout, tile t at x0_tile + t*x0_tile_stride ([S][32]); overrides x0
+  size_t x0_tile_stride;
+  AuxD aux;                  // tcgen05 solve only: aux.x != null stores X_i, z1, z2 of every stage evaluation (segment pass of the adjoint)
 };
 
 #define CPZ_PROF_BEGIN() const long long prof_t0__ = (a.prof && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0

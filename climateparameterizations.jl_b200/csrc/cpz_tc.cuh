@@ -251,7 +251,7 @@ __device__ __forceinline__ float pcr32(float a, float b, float c, float d) {
     const float cm = __shfl_up_sync(0xffffffffu, c, s), dm = __shfl_up_sync(0xffffffffu, d, s);
     const float ap = __shfl_down_sync(0xffffffffu, a, s), bp = __shfl_down_sync(0xffffffffu, b, s);
     const float cp = __shfl_down_sync(0xffffffffu, c, s), dp = __shfl_down_sync(0xffffffffu, d, s);
-    const float al = -__fdividef(a, bm), ga = -__fdividef(c, bp);
+    const float al = -a / bm, ga = -c / bp;  // IEEE: the kappa = 10 convective-adjustment rows amplify MUFU.RCP's error
     b = fmaf(al, cm, fmaf(ga, ap, b));
     d = fmaf(al, dm, fmaf(ga, dp, d));
     a = al * am;
@@ -266,7 +266,9 @@ static __device__ __noinline__ float tc_diurnal_top(const ModelD& M, float Q, fl
 
 // ACT: shared hidden activation (-1: T.act1/T.act2 at run time); K3S: layer-3 K steps; RHS_ONLY: single evaluation (cpz_rhs)
 // CPT: real columns per thread (8, or 7 so that 4 096 columns make 147 tiles of 28 and use every SM; the 8th slot is padding)
-template <int ACT, int K3S, bool PROF = false, bool RHS_ONLY = false, int CPT = 8>
+// AUX: the segment pass of the tensor-core adjoint — every stage evaluation also stores its input X_i and the pre-activations
+//      z1, z2 as operand-image records (AuxD, cpz_solve.cuh); the start state may come from a checkpoint (a.x0_tile)
+template <int ACT, int K3S, bool PROF = false, bool RHS_ONLY = false, int CPT = 8, bool AUX = false>
 __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constant__ ModelD M, const __grid_constant__ TcD T,
                                                             const __grid_constant__ TableauD tab, const TimeD tm,
                                                             const SolveArgs a, const TcArgs ta) {
@@ -328,7 +330,8 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
 #pragma unroll
   for (int r = 0; r < CPT; ++r) {
     const int col = min(col0 + cg0 + r, a.ncol - 1);
-    x[r] = qd < 3 ? __ldg(a.x0 + (size_t)col * (a.x0_stride ? a.x0_stride : (size_t)96) + 32 * qd + lane) : 0.f;
+    if (AUX && a.x0_tile != nullptr) x[r] = qd < 3 ? __ldcg(a.x0_tile + (size_t)tile * a.x0_tile_stride + (size_t)(32 * qd + lane) * TC_CT + cg0 + r) : 0.f;
+    else x[r] = qd < 3 ? __ldg(a.x0 + (size_t)col * (a.x0_stride ? a.x0_stride : (size_t)96) + 32 * qd + lane) : 0.f;
     X[r] = x[r];
     float raw[6], eff[6];
 #pragma unroll
@@ -400,10 +403,19 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
     for (int s = 0; s < NS; ++s) tc_mma_ts(d, ahi + 8 * s, bh + s * kstep, id16, 1);
   };
 
+  // AUX records: this thread's two column quads (columns cg0..cg0+7) of row `row` of a record with `rows` rows
+  int ev = 0;  // stage evaluations done so far
+  auto aux_store = [&](float* base, int rows, int row, const float* v) {
+    float4* dst = reinterpret_cast<float4*>(base + ((size_t)tile * a.aux.n_eval + ev) * (size_t)(32 * rows)) + (size_t)(cg0 >> 2) * rows + row;
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[rows] = make_float4(v[4], v[5], v[6], v[7]);
+  };
+
   // one RHS evaluation at stage input X (registers + shared memory); returns the tendencies in dx (qd < 3)
   auto rhs_eval = [&](float t_stage, float* dx) {
     // (1) operands visible to the async proxy, previous accumulator reads done
     tick(-1);
+    if constexpr (AUX) { if (qd < 3) aux_store(a.aux.x, a.aux.rx, 32 * qd + lane, X); }
     fence_proxy_async();
     tc_fence_before();
     bar_sync_named(bar_id, 256);
@@ -471,14 +483,20 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
       tmem_ld8(dg + ((uint32_t)(32 * qd) << 16) + 8 * h, v);
       tick(12);
 #pragma unroll
-      for (int r = 0; r < CPT; ++r) v[r] = tc_act<ACT>(act1, v[r] + b1a);
+      for (int r = 0; r < CPT; ++r) v[r] += b1a;
+      if constexpr (AUX) { if (32 * qd + lane < 3 * T.h1) aux_store(a.aux.z1, a.aux.r1, 32 * qd + lane, v); }
+#pragma unroll
+      for (int r = 0; r < CPT; ++r) v[r] = tc_act<ACT>(act1, v[r]);
       store_row_hilo<CPT>(gbase + L.h1h + h1a, gbase + L.h1l + h1a, v);
       tick(13);
       if (qd == 3 && T.n1b > 0) {
         tmem_ld8(dg + ((uint32_t)96 << 16) + 16 + 8 * h, v);
         if (lane < T.n1b) {
 #pragma unroll
-          for (int r = 0; r < CPT; ++r) v[r] = tc_act<ACT>(act1, v[r] + b1b);
+          for (int r = 0; r < CPT; ++r) v[r] += b1b;
+          if constexpr (AUX) aux_store(a.aux.z1, a.aux.r1, 128 + lane, v);
+#pragma unroll
+          for (int r = 0; r < CPT; ++r) v[r] = tc_act<ACT>(act1, v[r]);
           store_row_hilo<CPT>(gbase + L.h1h + h1b, gbase + L.h1l + h1b, v);
         }
       }
@@ -513,7 +531,10 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
       tmem_ld8(dg + ((uint32_t)(32 * qd) << 16) + 16 * qd + 8 * h, v);
       if (lane < T.h2) {
 #pragma unroll
-        for (int r = 0; r < CPT; ++r) v[r] = tc_act<ACT>(act2, v[r] + b2);
+        for (int r = 0; r < CPT; ++r) v[r] += b2;
+        if constexpr (AUX) aux_store(a.aux.z2, a.aux.r2, T.h2 * qd + lane, v);
+#pragma unroll
+        for (int r = 0; r < CPT; ++r) v[r] = tc_act<ACT>(act2, v[r]);
         store_row_hilo<CPT>(gbase + L.h2h + h2a, gbase + L.h2l + h2a, v);
       }
     }
@@ -556,6 +577,7 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
       }
     }
     tick(6);
+    ++ev;
   };
 
   // Backward-Euler vertical diffusion over one sub-step with the diffusivities of the incoming state (NDE_oceananigans.jl:
