@@ -98,7 +98,7 @@ struct AdjTcArgs {
 constexpr int TCB_SIDE_ARRAYS = 11;  // X_u X_v X_T | e_u e_v e_T (face-flux cotangents) | g_u g_v g_T (cotangents of the level differences) | kbar_u kbar_v
 
 struct TcBSmem {
-  int d1h, d1l, d2h, d2l, d3, side, grp_bytes;
+  int d1h, d1l, d2h, d2l, side, grp_bytes;
   int ks, w3, misc, total;
 };
 __host__ __device__ inline TcBSmem tc_bwd_smem_layout(const TcB& B, int n_stages) {
@@ -107,7 +107,6 @@ __host__ __device__ inline TcBSmem tc_bwd_smem_layout(const TcB& B, int n_stages
   auto take = [&](int bytes) { int r = o; o += (bytes + 127) & ~127; return r; };
   L.d1h = take((B.K1 / 4) * TC_LBO); L.d1l = take((B.K1 / 4) * TC_LBO);
   L.d2h = take((3 * B.K2w / 4) * TC_LBO); L.d2l = take((3 * B.K2w / 4) * TC_LBO);
-  L.d3 = take(96 * TC_GN * 4);
   L.side = take(TCB_SIDE_ARRAYS * 4 * 32 * 16);
   L.grp_bytes = o;
   o = TC_NG * L.grp_bytes;
@@ -117,6 +116,8 @@ __host__ __device__ inline TcBSmem tc_bwd_smem_layout(const TcB& B, int n_stages
   L.total = o;
   return L;
 }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // derivative of the hidden activation at the pre-activation z (same fast MUFU forms as tc_act)
 template <int ACT>
@@ -282,8 +283,11 @@ __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_const
     for (int s = 0; s < steps; ++s) tc_mma_ts(d, alo + 8 * s, bh + s * kstep, id16, 1);
     for (int s = 0; s < steps; ++s) tc_mma_ts(d, ahi + 8 * s, bh + s * kstep, id16, 1);
   };
-  auto rec4 = [&](float* base, int rows, int ev) -> float4* {  // this thread's first column quad of a record (row 0)
-    return reinterpret_cast<float4*>(base + ((size_t)tile * a.aux.n_eval + ev) * (size_t)(32 * rows)) + (size_t)(cg0 >> 2) * rows;
+  auto rec4 = [&](float* base, int rows, int ev) -> float4* {  // this thread's first column quad of an x / z record (row 0)
+    return reinterpret_cast<float4*>(base + ((size_t)tile * a.aux.n_eval + a.aux.ev0 + ev) * (size_t)(32 * rows)) + (size_t)(cg0 >> 2) * rows;
+  };
+  auto rec4d = [&](float* base, int rows, int ev) -> float4* {  // ... of a d record
+    return reinterpret_cast<float4*>(base + ((size_t)tile * a.aux.n_eval_d + ev) * (size_t)(32 * rows)) + (size_t)(cg0 >> 2) * rows;
   };
   auto ld8g = [&](const float4* p, int rows, float* v) {
     const float4 p0 = __ldcs(p), p1 = __ldcs(p + rows);
@@ -295,16 +299,31 @@ __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_const
   };
 
   const int R = a.seg_steps * nsub;
+  // delta2 phase mapping: thread (packed row = net*h2 + o, column quad) — 4 outputs per thread, every warp of the group works
+  const int gt = tid & 255, d2row = gt & 63, d2quad = gt >> 6;
+  const bool d2valid = d2row < 3 * h2;
+  const int d2q = d2valid ? d2row / h2 : 0, d2o = d2row - d2q * h2;
+  bool have_X = false;  // X already holds the next stage's input (fetched while the previous stage's last MMAs ran)
   for (int rr = R - 1; rr >= 0; --rr) {
     const int nstep = a.seg_step0 + rr / nsub, sub = rr % nsub;
 #pragma unroll 1
     for (int i = ns - 1; i >= 0; --i) {
       const int ev = rr * ns + i;
       // ---- S0: stage input, kbar_i, cotangent of the face fluxes -------------------------------------------------
-      float z2v[8];
+      if (ev > 0) {  // pull the records of the next stage (evaluation ev - 1) into L2: one 128-byte line per thread
+        const int nx = a.aux.rx >> 1, n1 = a.aux.r1 >> 1, n2 = a.aux.r2 >> 1;
+        const size_t r = (size_t)tile * a.aux.n_eval + a.aux.ev0 + ev - 1;
+        const float* pl = nullptr;  // the group's 4 column quads of a record are contiguous: rows * 64 bytes
+        if (gt < nx) pl = a.aux.x + r * (size_t)(32 * a.aux.rx) + (size_t)g * (16 * a.aux.rx) + 32 * gt;
+        else if (gt < nx + n1) pl = a.aux.z1 + r * (size_t)(32 * a.aux.r1) + (size_t)g * (16 * a.aux.r1) + 32 * (gt - nx);
+        else if (gt < nx + n1 + n2) pl = a.aux.z2 + r * (size_t)(32 * a.aux.r2) + (size_t)g * (16 * a.aux.r2) + 32 * (gt - nx - n1);
+        if (pl != nullptr) prefetch_l2(pl);
+      }
+      float4 z2v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (d2valid) z2v = __ldcs(reinterpret_cast<const float4*>(a.aux.z2 + ((size_t)tile * a.aux.n_eval + a.aux.ev0 + ev) * (size_t)(32 * a.aux.r2)) +
+                                (size_t)(4 * g + d2quad) * a.aux.r2 + d2row);
       if (qd < 3) {
-        ld8g(rec4(a.aux.x, a.aux.rx, ev) + 32 * qd + lane, a.aux.rx, X);
-        if (lane < h2) ld8g(rec4(a.aux.z2, a.aux.r2, ev) + h2 * qd + lane, a.aux.r2, z2v);
+        if (!have_X) ld8g(rec4(a.aux.x, a.aux.rx, ev) + 32 * qd + lane, a.aux.rx, X);
         float kb[8];
         const float bi = tab.b[i];
 #pragma unroll
@@ -325,39 +344,61 @@ __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_const
         }
         sts_v4(side_addr(qd, 2 * h), X[0], X[1], X[2], X[3]);
         sts_v4(side_addr(qd, 2 * h + 1), X[4], X[5], X[6], X[7]);
+        // e arrays = delta3 (row 32*net + j, j = lane < 31; lane 31 is zero): read by the delta2 phase and the side VJP
         sts_v4(side_addr(3 + qd, 2 * h), eb[0], eb[1], eb[2], eb[3]);
         sts_v4(side_addr(3 + qd, 2 * h + 1), eb[4], eb[5], eb[6], eb[7]);
         if (qd < 2) {
           sts_v4(side_addr(9 + qd, 2 * h), kb[0], kb[1], kb[2], kb[3]);
           sts_v4(side_addr(9 + qd, 2 * h + 1), kb[4], kb[5], kb[6], kb[7]);
         }
-        // delta3 (row 32*net + j, j = lane < 31; row 31 stays zero): FP32 copy for the next phase and the record
-        const uint32_t d3a = gbase + L.d3 + (uint32_t)((32 * qd + lane) * TC_GN + 8 * h) * 4;
-        sts_v4(d3a, eb[0], eb[1], eb[2], eb[3]);
-        sts_v4(d3a + 16, eb[4], eb[5], eb[6], eb[7]);
-        st8g(rec4(a.aux.d3, a.aux.r3, ev) + 32 * qd + lane, a.aux.r3, eb);
+        st8g(rec4d(a.aux.d3, a.aux.r3, ev) + 32 * qd + lane, a.aux.r3, eb);
       }
       bar_sync_named(bar_id, 256);  // B1
-      // ---- S1: delta2 = (W3 delta3) .* act2'(z2) in FP32; side VJP ------------------------------------------------
-      if (qd < 3 && lane < h2) {
-        float acc[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) acc[r] = 0.f;
-        const float* wp = w3s + (qd * 31) * 32 + lane;
-        const uint32_t dp = gbase + L.d3 + (uint32_t)((32 * qd) * TC_GN + 8 * h) * 4;
-#pragma unroll 4
+      // ---- S1: delta2 = (W3 delta3) .* act2'(z2) in FP32 ------------------------------------------------------------
+      if (d2valid) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* wp = w3s + (d2q * 31) * 32 + d2o;
+        const uint32_t dp = side + (uint32_t)((((3 + d2q) * 4 + d2quad) * 32) * 16);
+#pragma unroll 8
         for (int j = 0; j < 31; ++j) {
           const float w = wp[j * 32];
-          const float4 p0 = lds_v4(dp + j * (TC_GN * 4)), p1 = lds_v4(dp + j * (TC_GN * 4) + 16);
+          const float4 p0 = lds_v4(dp + j * 16);
           acc[0] = fmaf(w, p0.x, acc[0]); acc[1] = fmaf(w, p0.y, acc[1]); acc[2] = fmaf(w, p0.z, acc[2]); acc[3] = fmaf(w, p0.w, acc[3]);
-          acc[4] = fmaf(w, p1.x, acc[4]); acc[5] = fmaf(w, p1.y, acc[5]); acc[6] = fmaf(w, p1.z, acc[6]); acc[7] = fmaf(w, p1.w, acc[7]);
         }
-#pragma unroll
-        for (int r = 0; r < 8; ++r) acc[r] *= tc_act_grad<ACT>(T.act2, z2v[r]);
-        const uint32_t ro = tc_row_off(B.K2w * qd + lane, h);
-        store_row_hilo<8>(gbase + L.d2h + ro, gbase + L.d2l + ro, acc);
-        st8g(rec4(a.aux.d2, a.aux.r2, ev) + h2 * qd + lane, a.aux.r2, acc);
+        acc[0] *= tc_act_grad<ACT>(T.act2, z2v.x); acc[1] *= tc_act_grad<ACT>(T.act2, z2v.y);
+        acc[2] *= tc_act_grad<ACT>(T.act2, z2v.z); acc[3] *= tc_act_grad<ACT>(T.act2, z2v.w);
+        // plane row = the net's K window; columns 4*quad .. +3 of the group
+        const uint32_t ro = tc_row_off(B.K2w * d2q + d2o, d2quad >> 1) + (uint32_t)(d2quad & 1) * 64;
+        store_row_hilo<4>(gbase + L.d2h + ro, gbase + L.d2l + ro, acc);
+        reinterpret_cast<float4*>(a.aux.d2 + ((size_t)tile * a.aux.n_eval_d + ev) * (size_t)(32 * a.aux.r2))[(size_t)(4 * g + d2quad) * a.aux.r2 + d2row] =
+            make_float4(acc[0], acc[1], acc[2], acc[3]);
       }
+      fence_proxy_async();
+      tc_fence_before();
+      bar_sync_named(bar_id, 256);  // B2
+      // ---- S2: delta1 = (W2 delta2) .* act1'(z1); the side VJP runs under the MMAs ------------------------------------
+      if (wg == 3) {
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll 1
+          for (int q = 0; q < 3; ++q) {
+            const uint64_t bh = tc_desc(gbase + L.d2h + (uint32_t)(B.K2w * q >> 2) * TC_LBO);
+            const uint64_t bl = tc_desc(gbase + L.d2l + (uint32_t)(B.K2w * q >> 2) * TC_LBO);
+            const uint32_t ahi = tb + B.c_a2 + (q == 2 ? 2 * B.K2w : 0);
+            chain(dg + 16 * q, ahi, ahi + B.K2w, bh, bl, K2S);
+          }
+          tc_commit(mbar);
+        }
+        __syncwarp();
+      }
+      // rows of delta1 this thread owns: net 0 / net 1 rows sit in lanes 0.. / 64.. of the block-0 accumulators (columns
+      // +0 / +16), net 2 rows in lanes 0.. of the block-1 accumulator (columns +32): quadrants 0, 1 own two rows
+      const int o1 = 32 * (qd & 1) + lane;  // output index inside the net
+      const int netA = qd < 2 ? 0 : 1;
+      float z1a[8], z1b[8];
+      const bool rowA = o1 < h1, rowB = qd < 2 && o1 < h1;
+      if (rowA) ld8g(rec4(a.aux.z1, a.aux.r1, ev) + netA * h1 + o1, a.aux.r1, z1a);
+      if (rowB) ld8g(rec4(a.aux.z1, a.aux.r1, ev) + 2 * h1 + o1, a.aux.r1, z1b);
       {
         // every thread: face lane+1 of two columns (8h + 2qd, +1): diffusivities and their VJP
         const uint32_t off = (uint32_t)(8 * (qd & 1));
@@ -396,20 +437,37 @@ __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_const
         asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(side_addr(7, blk) + off), "f"(gv.x), "f"(gv.y) : "memory");
         asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(side_addr(8, blk) + off), "f"(gT.x), "f"(gT.y) : "memory");
       }
+      mbar_wait(mbar, parity); parity ^= 1u;
+      tc_fence_after();
+      {
+        float v[8];
+        tmem_ld8(dg + ((uint32_t)(32 * qd) << 16) + 16 * netA + 8 * h, v);
+        if (rowA) {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) v[r] *= tc_act_grad<ACT>(T.act1, z1a[r]);
+          const uint32_t ro = tc_row_off(netA * h1 + o1, h);
+          store_row_hilo<8>(gbase + L.d1h + ro, gbase + L.d1l + ro, v);
+          st8g(rec4d(a.aux.d1, a.aux.r1, ev) + netA * h1 + o1, a.aux.r1, v);
+        }
+        if (qd < 2) {
+          tmem_ld8(dg + ((uint32_t)(32 * qd) << 16) + 32 + 8 * h, v);
+          if (rowB) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) v[r] *= tc_act_grad<ACT>(T.act1, z1b[r]);
+            const uint32_t ro = tc_row_off(2 * h1 + o1, h);
+            store_row_hilo<8>(gbase + L.d1h + ro, gbase + L.d1l + ro, v);
+            st8g(rec4d(a.aux.d1, a.aux.r1, ev) + 2 * h1 + o1, a.aux.r1, v);
+          }
+        }
+      }
       fence_proxy_async();
       tc_fence_before();
-      bar_sync_named(bar_id, 256);  // B2
-      // ---- S2: delta1 = (W2 delta2) .* act1'(z1) ------------------------------------------------------------------
-      if (wg == 3) {
+      bar_sync_named(bar_id, 256);  // B3
+      // ---- S3: Xbar_i = W1 delta1 + direct part -------------------------------------------------------------------
+      if (wg == 7) {
         tc_fence_after();
         if (elect_one()) {
-#pragma unroll 1
-          for (int q = 0; q < 3; ++q) {
-            const uint64_t bh = tc_desc(gbase + L.d2h + (uint32_t)(B.K2w * q >> 2) * TC_LBO);
-            const uint64_t bl = tc_desc(gbase + L.d2l + (uint32_t)(B.K2w * q >> 2) * TC_LBO);
-            const uint32_t ahi = tb + B.c_a2 + (q == 2 ? 2 * B.K2w : 0);
-            chain(dg + 16 * q, ahi, ahi + B.K2w, bh, bl, K2S);
-          }
+          chain(dg, tb, tb + B.K1, tc_desc(gbase + L.d1h), tc_desc(gbase + L.d1l), K1S);
           tc_commit(mbar);
         }
         __syncwarp();
@@ -433,49 +491,9 @@ __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_const
 #pragma unroll
           for (int r = 0; r < 8; ++r) direct[r] = fmaf(cso, ko[r], direct[r]);
         }
-      }
-      // rows of delta1 this thread owns: net 0 / net 1 rows sit in lanes 0.. / 64.. of the block-0 accumulators (columns
-      // +0 / +16), net 2 rows in lanes 0.. of the block-1 accumulator (columns +32): quadrants 0, 1 own two rows
-      const int o1 = 32 * (qd & 1) + lane;  // output index inside the net
-      const int netA = qd < 2 ? 0 : 1;
-      float z1a[8], z1b[8];
-      const bool rowA = o1 < h1, rowB = qd < 2 && o1 < h1;
-      if (rowA) ld8g(rec4(a.aux.z1, a.aux.r1, ev) + netA * h1 + o1, a.aux.r1, z1a);
-      if (rowB) ld8g(rec4(a.aux.z1, a.aux.r1, ev) + 2 * h1 + o1, a.aux.r1, z1b);
-      mbar_wait(mbar, parity); parity ^= 1u;
-      tc_fence_after();
-      {
-        float v[8];
-        tmem_ld8(dg + ((uint32_t)(32 * qd) << 16) + 16 * netA + 8 * h, v);
-        if (rowA) {
-#pragma unroll
-          for (int r = 0; r < 8; ++r) v[r] *= tc_act_grad<ACT>(T.act1, z1a[r]);
-          const uint32_t ro = tc_row_off(netA * h1 + o1, h);
-          store_row_hilo<8>(gbase + L.d1h + ro, gbase + L.d1l + ro, v);
-          st8g(rec4(a.aux.d1, a.aux.r1, ev) + netA * h1 + o1, a.aux.r1, v);
-        }
-        if (qd < 2) {
-          tmem_ld8(dg + ((uint32_t)(32 * qd) << 16) + 32 + 8 * h, v);
-          if (rowB) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) v[r] *= tc_act_grad<ACT>(T.act1, z1b[r]);
-            const uint32_t ro = tc_row_off(2 * h1 + o1, h);
-            store_row_hilo<8>(gbase + L.d1h + ro, gbase + L.d1l + ro, v);
-            st8g(rec4(a.aux.d1, a.aux.r1, ev) + 2 * h1 + o1, a.aux.r1, v);
-          }
-        }
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      bar_sync_named(bar_id, 256);  // B3
-      // ---- S3: Xbar_i = W1 delta1 + direct part -------------------------------------------------------------------
-      if (wg == 7) {
-        tc_fence_after();
-        if (elect_one()) {
-          chain(dg, tb, tb + B.K1, tc_desc(gbase + L.d1h), tc_desc(gbase + L.d1l), K1S);
-          tc_commit(mbar);
-        }
-        __syncwarp();
+        // the next stage's input (stage 0's X must survive until the loss terms of the step start)
+        have_X = i > 0;
+        if (have_X) ld8g(rec4(a.aux.x, a.aux.rx, ev - 1) + 32 * qd + lane, a.aux.rx, X);
       }
       mbar_wait(mbar, parity); parity ^= 1u;
       tc_fence_after();
@@ -521,13 +539,14 @@ __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_const
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512));
 }
 
-// ---- weight gradient: one contraction over every (column, stage) of the segment ------------------------------------------
+// ---- weight gradient: one contraction over every (column, stage) of the launch ------------------------------------------
 struct WgradArgs {
   AuxD aux;
-  int n_rec;     // records = tiles x stage evaluations
-  float* part;   // [grid][WG_COLS][128] accumulator images, added to (zeroed by the host before the first segment)
+  int n_tiles, n_e;  // records of this launch: (tile t, evaluation e < n_e); x / z record aux.ev0 + e, d record e
+  float* part;       // [gridDim.x][WG_COLS][128] accumulator images, added to (zeroed by the host before the first launch)
 };
-constexpr int WG_NT = 512;
+constexpr int WG_NT = 512;    // two halves of 8 warps
+constexpr int WG_HT = 256;
 constexpr int WG_COLS = 448;  // N1 + 2 N2 + 96 <= 448
 
 __device__ __forceinline__ uint64_t wg_desc(uint32_t saddr, uint32_t lbo_bytes) {  // K-major, no swizzle, SBO = 128
@@ -539,101 +558,124 @@ __device__ __forceinline__ void tc_mma_ss(uint32_t d, uint64_t adesc, uint64_t b
                : "memory");
 }
 
-// shared memory: hi planes of the six arrays (x, a1, a2, d1, d2, d3) in record order, then the lo planes; each array is the
-// record image [column quad][row][4] itself. A operands are read as M = 128 rows: rows past an array's end run into the
-// following arrays (finite values, their accumulator rows are never read).
-template <int ACT>
-__global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const __grid_constant__ TcD T, const __grid_constant__ TcB B,
-                                                            const __grid_constant__ WgradArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem_wg[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int rows[6] = {a.aux.rx, a.aux.r1, a.aux.r2, a.aux.r1, a.aux.r2, a.aux.r3};
-  int off4[7];  // float4 offsets of the arrays inside a plane set
-  off4[0] = 0;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) off4[k + 1] = off4[k] + 8 * rows[k];
-  const int set4 = off4[6];  // float4 per plane set
-  float4* hi = reinterpret_cast<float4*>(smem_wg);
-  float4* lo = hi + set4;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_wg + (size_t)2 * set4 * 16);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
-  if (tid == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+// The CTA is two independent halves of 8 warps (own operand planes, own mbarrier and named barrier, own accumulator columns),
+// free-running against each other so that one half's global fetch / hi-lo split overlaps the other's MMAs:
+//   half 0: dW1 += [X;1] d1^T   (M 128 x N1)   and  dW3 += [a2;1] d3^T (M 128 x 96)      arrays x, z2, d1, d3
+//   half 1: dW2 += [a1;1] d2^T  as two row blocks (rows 0..127, rows 128..) of M 128 x N2   arrays z1, d2
+// Operand planes of a half: hi planes of its arrays (A operands first), then the lo planes; every array is the record image
+// [column quad][row][4] itself. A operands are read as M = 128 rows: rows past an array's end run into the arrays behind
+// it (finite values whose accumulator rows are never read). Records are fetched through registers one record ahead and
+// pulled into L2 two records ahead.
+//
+// One array of a half: ID 0 x, 1 z1, 2 z2, 3 d1, 4 d2, 5 d3; NV = float4 per thread (rows <= 32 NV)
+template <int ID_, int NV_>
+struct WgArr {
+  static constexpr int ID = ID_, NV = NV_;
+};
+template <int ACT, int ID>
+__device__ __forceinline__ float4 wg_role(const TcD& T, int row, float4 v) {
+  const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  if constexpr (ID == 0) {
+    if (row == 96) v = one; else if (row > 96) v = zero;
+  } else if constexpr (ID == 1) {
+    if (row < 3 * T.h1) { v.x = tc_act<ACT>(T.act1, v.x); v.y = tc_act<ACT>(T.act1, v.y); v.z = tc_act<ACT>(T.act1, v.z); v.w = tc_act<ACT>(T.act1, v.w); }
+    else v = row == 3 * T.h1 ? one : zero;
+  } else if constexpr (ID == 2) {
+    if (row < 3 * T.h2) { v.x = tc_act<ACT>(T.act2, v.x); v.y = tc_act<ACT>(T.act2, v.y); v.z = tc_act<ACT>(T.act2, v.z); v.w = tc_act<ACT>(T.act2, v.w); }
+    else v = row == 3 * T.h2 ? one : zero;
+  } else if constexpr (ID == 3) {
+    if (row >= 3 * T.h1) v = zero;
+  } else if constexpr (ID == 4) {
+    if (row >= 3 * T.h2) v = zero;
+  } else {
+    if ((row & 31) == 31) v = zero;
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tb = *tmem_slot;
-  const float* src[6] = {a.aux.x, a.aux.z1, a.aux.z2, a.aux.d1, a.aux.d2, a.aux.d3};
-  const int h1x3 = 3 * T.h1, h2x3 = 3 * T.h2;
-  constexpr int MAXV = 3;  // float4 per thread and array: ceil(8 * 168 / 512)
-  float4 buf[6][MAXV];
-  auto fetch = [&](int rec) {
+  return v;
+}
+
+template <int ACT, int HALF>
+__device__ __forceinline__ void wgrad_half(const TcD& T, const TcB& B, const WgradArgs& a, uint8_t* smem, uint64_t* mbar, uint32_t tb) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, ht = tid & (WG_HT - 1);
+  // arrays in plane order (A operands first)
+  using A0 = std::conditional_t<HALF == 0, WgArr<0, 4>, WgArr<1, 6>>;
+  using A1 = std::conditional_t<HALF == 0, WgArr<2, 4>, WgArr<4, 4>>;
+  using A2 = WgArr<3, 6>;  // half 0 only
+  using A3 = WgArr<5, 3>;  // half 0 only
+  constexpr int NA = HALF == 0 ? 4 : 2;
+  const int rows_all[6] = {a.aux.rx, a.aux.r1, a.aux.r2, a.aux.r1, a.aux.r2, a.aux.r3};
+  float* const src_all[6] = {a.aux.x, a.aux.z1, a.aux.z2, a.aux.d1, a.aux.d2, a.aux.d3};
+  const int r0 = rows_all[A0::ID], r1 = rows_all[A1::ID], r2 = HALF == 0 ? rows_all[A2::ID] : 0, r3 = HALF == 0 ? rows_all[A3::ID] : 0;
+  const int o0 = 0, o1 = 8 * r0, o2 = o1 + 8 * r1, o3 = o2 + 8 * r2, set4 = o3 + 8 * r3;
+  const int set4_h0 = 8 * (a.aux.rx + a.aux.r2 + a.aux.r1 + a.aux.r3);
+  float4* hi = reinterpret_cast<float4*>(smem) + (HALF ? 2 * set4_h0 : 0);
+  float4* lo = hi + set4;
+  const int n_rec = a.n_tiles * a.n_e;
+  float4 b0[A0::NV], b1[A1::NV], b2[HALF == 0 ? A2::NV : 1], b3[HALF == 0 ? A3::NV : 1];
+  auto rec_ptr = [&](int idk, int rows, int rec) -> const float4* {
+    const int t = rec / a.n_e, e = rec - t * a.n_e;
+    const size_t r = idk < 3 ? (size_t)t * a.aux.n_eval + a.aux.ev0 + e : (size_t)t * a.aux.n_eval_d + e;
+    return reinterpret_cast<const float4*>(src_all[idk] + r * (size_t)(32 * rows));
+  };
+  auto fetch1 = [&](auto arr, int rows, float4* buf, int rec) {
+    using AR = decltype(arr);
+    const float4* p = rec_ptr(AR::ID, rows, rec);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const float4* p = reinterpret_cast<const float4*>(src[k] + (size_t)rec * (size_t)(32 * rows[k]));
+    for (int j = 0; j < AR::NV; ++j) {
+      const int idx = ht + j * WG_HT;
+      if (idx < 8 * rows) buf[j] = __ldcs(p + idx);
+    }
+  };
+  auto pref1 = [&](auto arr, int rows, int rec) {
+    using AR = decltype(arr);
+    const float4* p = rec_ptr(AR::ID, rows, rec);
+    for (int idx = 8 * ht; idx < 8 * rows; idx += 8 * WG_HT) prefetch_l2(p + idx);
+  };
+  auto conv1 = [&](auto arr, int rows, int off, const float4* buf) {
+    using AR = decltype(arr);
 #pragma unroll
-      for (int j = 0; j < MAXV; ++j) {
-        const int idx = tid + j * WG_NT;
-        if (idx < 8 * rows[k]) buf[k][j] = __ldcs(p + idx);
+    for (int j = 0; j < AR::NV; ++j) {
+      const int idx = ht + j * WG_HT;
+      if (idx < 8 * rows) {
+        const float4 v = wg_role<ACT, AR::ID>(T, idx % rows, buf[j]);
+        float4 vh, vl;
+        vh.x = tf32_hi(v.x); vh.y = tf32_hi(v.y); vh.z = tf32_hi(v.z); vh.w = tf32_hi(v.w);
+        vl.x = v.x - vh.x; vl.y = v.y - vh.y; vl.z = v.z - vh.z; vl.w = v.w - vh.w;
+        hi[off + idx] = vh;
+        lo[off + idx] = vl;
       }
     }
   };
-  auto put = [&](int k, int idx, float4 v) {
-    float4 vh, vl;
-    vh.x = tf32_hi(v.x); vh.y = tf32_hi(v.y); vh.z = tf32_hi(v.z); vh.w = tf32_hi(v.w);
-    vl.x = v.x - vh.x; vl.y = v.y - vh.y; vl.z = v.z - vh.z; vl.w = v.w - vh.w;
-    hi[off4[k] + idx] = vh;
-    lo[off4[k] + idx] = vl;
+  auto fetch = [&](int rec) {
+    fetch1(A0{}, r0, b0, rec); fetch1(A1{}, r1, b1, rec);
+    if constexpr (HALF == 0) { fetch1(A2{}, r2, b2, rec); fetch1(A3{}, r3, b3, rec); }
+  };
+  auto prefetch = [&](int rec) {
+    pref1(A0{}, r0, rec); pref1(A1{}, r1, rec);
+    if constexpr (HALF == 0) { pref1(A2{}, r2, rec); pref1(A3{}, r3, rec); }
   };
   auto convert = [&]() {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-#pragma unroll
-      for (int j = 0; j < MAXV; ++j) {
-        const int idx = tid + j * WG_NT;
-        if (idx < 8 * rows[k]) {
-          const int row = idx % rows[k];
-          float4 v = buf[k][j];
-          const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (k == 0) {
-            if (row == 96) v = one; else if (row > 96) v = zero;
-          } else if (k == 1) {
-            if (row < h1x3) { v.x = tc_act<ACT>(T.act1, v.x); v.y = tc_act<ACT>(T.act1, v.y); v.z = tc_act<ACT>(T.act1, v.z); v.w = tc_act<ACT>(T.act1, v.w); }
-            else v = row == h1x3 ? one : zero;
-          } else if (k == 2) {
-            if (row < h2x3) { v.x = tc_act<ACT>(T.act2, v.x); v.y = tc_act<ACT>(T.act2, v.y); v.z = tc_act<ACT>(T.act2, v.z); v.w = tc_act<ACT>(T.act2, v.w); }
-            else v = row == h2x3 ? one : zero;
-          } else if (k == 3) {
-            if (row >= h1x3) v = zero;
-          } else if (k == 4) {
-            if (row >= h2x3) v = zero;
-          } else {
-            if ((row & 31) == 31) v = zero;
-          }
-          put(k, idx, v);
-        }
-      }
-    }
+    conv1(A0{}, r0, o0, b0); conv1(A1{}, r1, o1, b1);
+    if constexpr (HALF == 0) { conv1(A2{}, r2, o2, b2); conv1(A3{}, r3, o3, b3); }
   };
+  (void)NA;
   const uint32_t sh = smem_u32(hi), sl = smem_u32(lo);
   const uint32_t id1 = tc_idesc(128, B.N1), id2 = tc_idesc(128, B.N2), id3 = tc_idesc(128, 96);
-  const uint32_t cD1 = tb, cD2a = tb + B.N1, cD2b = tb + B.N1 + B.N2, cD3 = tb + B.N1 + 2 * B.N2;
   uint32_t parity = 0;
+  const int step = gridDim.x;
   int rec = blockIdx.x;
   bool first = true;
-  if (rec < a.n_rec) fetch(rec);
-  while (rec < a.n_rec) {
+  if (rec < n_rec) fetch(rec);
+  if (rec + step < n_rec) prefetch(rec + step);
+  while (rec < n_rec) {
     if (!first) { mbar_wait(mbar, parity); parity ^= 1u; }  // the previous record's MMAs have read the planes
     convert();
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
-    const int next = rec + gridDim.x;
-    if (next < a.n_rec) fetch(next);  // in flight while the MMAs run
-    if (warp == 0) {
+    bar_sync_named(1 + HALF, WG_HT);
+    const int next = rec + step;
+    if (next < n_rec) fetch(next);  // in flight while the MMAs run
+    if (next + step < n_rec) prefetch(next + step);
+    if ((warp & 7) == 0) {
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll 1
@@ -642,12 +684,14 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const __grid_constan
 #pragma unroll 1
           for (int s = 0; s < 4; ++s) {
             const uint32_t acc = (first && pass == 0 && s == 0) ? 0u : 1u;
-            auto A = [&](int k, int row0) { return wg_desc(sa + (uint32_t)(off4[k] + 2 * s * rows[k] + row0) * 16, (uint32_t)rows[k] * 16); };
-            auto Bd = [&](int k) { return wg_desc(sb + (uint32_t)(off4[k] + 2 * s * rows[k]) * 16, (uint32_t)rows[k] * 16); };
-            tc_mma_ss(cD1, A(0, 0), Bd(3), id1, acc);
-            tc_mma_ss(cD2a, A(1, 0), Bd(4), id2, acc);
-            tc_mma_ss(cD2b, A(1, 128), Bd(4), id2, acc);
-            tc_mma_ss(cD3, A(2, 0), Bd(5), id3, acc);
+            auto D = [&](uint32_t base, int off, int rows, int row0) { return wg_desc(base + (uint32_t)(off + 2 * s * rows + row0) * 16, (uint32_t)rows * 16); };
+            if constexpr (HALF == 0) {
+              tc_mma_ss(tb, D(sa, o0, r0, 0), D(sb, o2, r2, 0), id1, acc);
+              tc_mma_ss(tb + B.N1, D(sa, o1, r1, 0), D(sb, o3, r3, 0), id3, acc);
+            } else {
+              tc_mma_ss(tb, D(sa, o0, r0, 0), D(sb, o1, r1, 0), id2, acc);
+              tc_mma_ss(tb + B.N2, D(sa, o0, r0, 128), D(sb, o1, r1, 0), id2, acc);
+            }
           }
         }
         tc_commit(mbar);
@@ -657,20 +701,44 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const __grid_constan
     first = false;
     rec = next;
   }
-  if (!first) { mbar_wait(mbar, parity); parity ^= 1u; }
-  tc_fence_after();
   if (!first) {
-    // accumulators -> this CTA's partial image (added: the image carries the sum over the segments)
-    const int ncols = B.N1 + 2 * B.N2 + 96;
+    mbar_wait(mbar, parity); parity ^= 1u;
+    tc_fence_after();
+    // accumulators -> this CTA's image (added: the image carries the sum over the launches). Image columns: dW1 [0,N1),
+    // dW2 rows 0..127 [N1,N1+N2), rows 128.. [N1+N2,N1+2N2), dW3 [N1+2N2,+96)
     float* dst = a.part + (size_t)blockIdx.x * WG_COLS * 128;
-    const int qd = warp & 3;
-    for (int c0 = 8 * (warp >> 2); c0 < ncols; c0 += 8 * (WG_NT / 128)) {
+    const int qd = warp & 3, part = (warp >> 2) & 1;
+    const int ncols = HALF == 0 ? B.N1 + 96 : 2 * B.N2;
+    for (int c0 = 8 * part; c0 < ncols; c0 += 16) {
       float v[8];
       tmem_ld8(tb + ((uint32_t)(32 * qd) << 16) + c0, v);
+      const int ic = HALF == 0 ? (c0 < B.N1 ? c0 : c0 + 2 * B.N2) : B.N1 + c0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dst[(size_t)(c0 + i) * 128 + 32 * qd + lane] += v[i];
+      for (int i = 0; i < 8; ++i) dst[(size_t)(ic + i) * 128 + 32 * qd + lane] += v[i];
     }
   }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const __grid_constant__ TcD T, const __grid_constant__ TcB B,
+                                                            const __grid_constant__ WgradArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_wg[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int half = warp >> 3;
+  const int total4 = 16 * (a.aux.rx + a.aux.r2 + a.aux.r1 + a.aux.r3) + 16 * (a.aux.r1 + a.aux.r2);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_wg + (size_t)total4 * 16);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_wg + (size_t)total4 * 16 + 16);
+  if (tid == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); fence_mbar_init(); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = *tmem_slot;
+  if (half == 0) wgrad_half<ACT, 0>(T, B, a, smem_wg, mbar, tb);
+  else wgrad_half<ACT, 1>(T, B, a, smem_wg, mbar + 1, tb + 256);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512));
@@ -696,9 +764,10 @@ __global__ void wgrad_ref_kernel(const __grid_constant__ TcD T, const __grid_con
   const bool bvalid = kb == 3 ? rowb < h1x3 : (kb == 4 ? rowb < h2x3 : (rowb < 96 && (rowb & 31) != 31));
   float s = 0.f;
   if (rowa <= va && bvalid) {
-    for (int rec = 0; rec < a.n_rec; ++rec) {
-      const float* pa = src[ka] + (size_t)rec * 32 * rows[ka];
-      const float* pb = src[kb] + (size_t)rec * 32 * rows[kb];
+    for (int rec = 0; rec < a.n_tiles * a.n_e; ++rec) {
+      const int t = rec / a.n_e, e = rec - t * a.n_e;
+      const float* pa = src[ka] + ((size_t)t * a.aux.n_eval + a.aux.ev0 + e) * 32 * rows[ka];
+      const float* pb = src[kb] + ((size_t)t * a.aux.n_eval_d + e) * 32 * rows[kb];
       for (int col = 0; col < 32; ++col) {
         float av = 1.f;
         if (rowa < va) {

@@ -16,7 +16,10 @@ namespace cpz {
 struct AuxD {
   float *x, *z1, *z2, *d1, *d2, *d3;
   int rx, r1, r2, r3;
-  int n_eval;  // stage evaluations per tile in the buffers (segment Runge–Kutta steps x stages)
+  int n_eval;    // stage evaluations per tile the x / z1 / z2 buffers hold (record of tile t, evaluation e at t*n_eval + e)
+  int n_eval_d;  // the same for the d1 / d2 / d3 buffers (they only live from a reverse launch to its weight-gradient launch)
+  int ev_skip;   // forward pass: leading stage evaluations of the launch that are NOT stored (record e holds evaluation ev_skip + e)
+  int ev0;       // reverse / weight-gradient launch: x / z record of its evaluation e is ev0 + e
 };
 
 struct SolveArgs {

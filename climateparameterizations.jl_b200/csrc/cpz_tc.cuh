@@ -404,8 +404,9 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
   };
 
   // AUX records: this thread's two column quads (columns cg0..cg0+7) of row `row` of a record with `rows` rows
-  int ev = 0;  // stage evaluations done so far
+  int ev = AUX ? -a.aux.ev_skip : 0;  // record index of the current stage evaluation (negative: not stored)
   auto aux_store = [&](float* base, int rows, int row, const float* v) {
+    if (ev < 0) return;
     float4* dst = reinterpret_cast<float4*>(base + ((size_t)tile * a.aux.n_eval + ev) * (size_t)(32 * rows)) + (size_t)(cg0 >> 2) * rows + row;
     dst[0] = make_float4(v[0], v[1], v[2], v[3]);
     dst[rows] = make_float4(v[4], v[5], v[6], v[7]);
