@@ -596,47 +596,59 @@ __device__ __forceinline__ float4 wg_role(const TcD& T, int row, float4 v) {
 template <int ACT, int HALF>
 __device__ __forceinline__ void wgrad_half(const TcD& T, const TcB& B, const WgradArgs& a, uint8_t* smem, uint64_t* mbar, uint32_t tb) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, ht = tid & (WG_HT - 1);
-  // arrays in plane order (A operands first)
-  using A0 = std::conditional_t<HALF == 0, WgArr<0, 4>, WgArr<1, 6>>;
-  using A1 = std::conditional_t<HALF == 0, WgArr<2, 4>, WgArr<4, 4>>;
-  using A2 = WgArr<3, 6>;  // half 0 only
-  using A3 = WgArr<5, 3>;  // half 0 only
-  constexpr int NA = HALF == 0 ? 4 : 2;
+  // arrays in plane order (A operands first); NV = float4 per thread of a 16-column sub-record (4 column quads x rows)
+  using A0 = std::conditional_t<HALF == 0, WgArr<0, 2>, WgArr<1, 3>>;
+  using A1 = std::conditional_t<HALF == 0, WgArr<2, 2>, WgArr<4, 2>>;
+  using A2 = WgArr<3, 3>;  // half 0 only
+  using A3 = WgArr<5, 2>;  // half 0 only
   const int rows_all[6] = {a.aux.rx, a.aux.r1, a.aux.r2, a.aux.r1, a.aux.r2, a.aux.r3};
   float* const src_all[6] = {a.aux.x, a.aux.z1, a.aux.z2, a.aux.d1, a.aux.d2, a.aux.d3};
   const int r0 = rows_all[A0::ID], r1 = rows_all[A1::ID], r2 = HALF == 0 ? rows_all[A2::ID] : 0, r3 = HALF == 0 ? rows_all[A3::ID] : 0;
-  const int o0 = 0, o1 = 8 * r0, o2 = o1 + 8 * r1, o3 = o2 + 8 * r2, set4 = o3 + 8 * r3;
-  const int set4_h0 = 8 * (a.aux.rx + a.aux.r2 + a.aux.r1 + a.aux.r3);
-  float4* hi = reinterpret_cast<float4*>(smem) + (HALF ? 2 * set4_h0 : 0);
-  float4* lo = hi + set4;
+  const int o0 = 0, o1 = 4 * r0, o2 = o1 + 4 * r1, o3 = o2 + 4 * r2, set4 = o3 + 4 * r3;  // float4 offsets inside a plane set (16 columns)
+  const int set4_h0 = 4 * (a.aux.rx + a.aux.r2 + a.aux.r1 + a.aux.r3);
+  // planes of this half: buffer 0 hi, lo, buffer 1 hi, lo
+  float4* planes = reinterpret_cast<float4*>(smem) + (HALF ? 4 * set4_h0 : 0);
   const int n_rec = a.n_tiles * a.n_e;
   float4 b0[A0::NV], b1[A1::NV], b2[HALF == 0 ? A2::NV : 1], b3[HALF == 0 ? A3::NV : 1];
-  auto rec_ptr = [&](int idk, int rows, int rec) -> const float4* {
+  int w0[A0::NV], w1[A1::NV], w2[HALF == 0 ? A2::NV : 1], w3[HALF == 0 ? A3::NV : 1];  // row of this thread's j-th float4
+#pragma unroll
+  for (int j = 0; j < A0::NV; ++j) w0[j] = (ht + j * WG_HT) % r0;
+#pragma unroll
+  for (int j = 0; j < A1::NV; ++j) w1[j] = (ht + j * WG_HT) % r1;
+  if constexpr (HALF == 0) {
+#pragma unroll
+    for (int j = 0; j < A2::NV; ++j) w2[j] = (ht + j * WG_HT) % r2;
+#pragma unroll
+    for (int j = 0; j < A3::NV; ++j) w3[j] = (ht + j * WG_HT) % r3;
+  }
+  // sub-record u of this CTA: record blockIdx.x + (u >> 1) gridDim.x, column half u & 1 (column quads 4 (u & 1) ..)
+  auto sub_ptr = [&](int idk, int rows, int u) -> const float4* {
+    const int rec = blockIdx.x + (u >> 1) * gridDim.x;
     const int t = rec / a.n_e, e = rec - t * a.n_e;
     const size_t r = idk < 3 ? (size_t)t * a.aux.n_eval + a.aux.ev0 + e : (size_t)t * a.aux.n_eval_d + e;
-    return reinterpret_cast<const float4*>(src_all[idk] + r * (size_t)(32 * rows));
+    return reinterpret_cast<const float4*>(src_all[idk] + r * (size_t)(32 * rows)) + (u & 1) * 4 * rows;
   };
-  auto fetch1 = [&](auto arr, int rows, float4* buf, int rec) {
+  auto fetch1 = [&](auto arr, int rows, float4* buf, int u) {
     using AR = decltype(arr);
-    const float4* p = rec_ptr(AR::ID, rows, rec);
+    const float4* p = sub_ptr(AR::ID, rows, u);
 #pragma unroll
     for (int j = 0; j < AR::NV; ++j) {
       const int idx = ht + j * WG_HT;
-      if (idx < 8 * rows) buf[j] = __ldcs(p + idx);
+      if (idx < 4 * rows) buf[j] = __ldcs(p + idx);
     }
   };
-  auto pref1 = [&](auto arr, int rows, int rec) {
+  auto pref1 = [&](auto arr, int rows, int u) {
     using AR = decltype(arr);
-    const float4* p = rec_ptr(AR::ID, rows, rec);
-    for (int idx = 8 * ht; idx < 8 * rows; idx += 8 * WG_HT) prefetch_l2(p + idx);
+    const float4* p = sub_ptr(AR::ID, rows, u);
+    if (8 * ht < 4 * rows) prefetch_l2(p + 8 * ht);
   };
-  auto conv1 = [&](auto arr, int rows, int off, const float4* buf) {
+  auto conv1 = [&](auto arr, int rows, int off, const float4* buf, const int* rw, float4* hi, float4* lo) {
     using AR = decltype(arr);
 #pragma unroll
     for (int j = 0; j < AR::NV; ++j) {
       const int idx = ht + j * WG_HT;
-      if (idx < 8 * rows) {
-        const float4 v = wg_role<ACT, AR::ID>(T, idx % rows, buf[j]);
+      if (idx < 4 * rows) {
+        const float4 v = wg_role<ACT, AR::ID>(T, rw[j], buf[j]);
         float4 vh, vl;
         vh.x = tf32_hi(v.x); vh.y = tf32_hi(v.y); vh.z = tf32_hi(v.z); vh.w = tf32_hi(v.w);
         vl.x = v.x - vh.x; vl.y = v.y - vh.y; vl.z = v.z - vh.z; vl.w = v.w - vh.w;
@@ -645,45 +657,45 @@ __device__ __forceinline__ void wgrad_half(const TcD& T, const TcB& B, const Wgr
       }
     }
   };
-  auto fetch = [&](int rec) {
-    fetch1(A0{}, r0, b0, rec); fetch1(A1{}, r1, b1, rec);
-    if constexpr (HALF == 0) { fetch1(A2{}, r2, b2, rec); fetch1(A3{}, r3, b3, rec); }
+  auto fetch = [&](int u) {
+    fetch1(A0{}, r0, b0, u); fetch1(A1{}, r1, b1, u);
+    if constexpr (HALF == 0) { fetch1(A2{}, r2, b2, u); fetch1(A3{}, r3, b3, u); }
   };
-  auto prefetch = [&](int rec) {
-    pref1(A0{}, r0, rec); pref1(A1{}, r1, rec);
-    if constexpr (HALF == 0) { pref1(A2{}, r2, rec); pref1(A3{}, r3, rec); }
+  auto prefetch = [&](int u) {
+    pref1(A0{}, r0, u); pref1(A1{}, r1, u);
+    if constexpr (HALF == 0) { pref1(A2{}, r2, u); pref1(A3{}, r3, u); }
   };
-  auto convert = [&]() {
-    conv1(A0{}, r0, o0, b0); conv1(A1{}, r1, o1, b1);
-    if constexpr (HALF == 0) { conv1(A2{}, r2, o2, b2); conv1(A3{}, r3, o3, b3); }
+  auto convert = [&](float4* hi, float4* lo) {
+    conv1(A0{}, r0, o0, b0, w0, hi, lo); conv1(A1{}, r1, o1, b1, w1, hi, lo);
+    if constexpr (HALF == 0) { conv1(A2{}, r2, o2, b2, w2, hi, lo); conv1(A3{}, r3, o3, b3, w3, hi, lo); }
   };
-  (void)NA;
-  const uint32_t sh = smem_u32(hi), sl = smem_u32(lo);
   const uint32_t id1 = tc_idesc(128, B.N1), id2 = tc_idesc(128, B.N2), id3 = tc_idesc(128, 96);
-  uint32_t parity = 0;
-  const int step = gridDim.x;
-  int rec = blockIdx.x;
-  bool first = true;
-  if (rec < n_rec) fetch(rec);
-  if (rec + step < n_rec) prefetch(rec + step);
-  while (rec < n_rec) {
-    if (!first) { mbar_wait(mbar, parity); parity ^= 1u; }  // the previous record's MMAs have read the planes
-    convert();
+  uint32_t parity[2] = {0u, 0u};
+  const int n_mine = blockIdx.x < n_rec ? (n_rec - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int n_sub = 2 * n_mine;
+  if (n_sub > 0) fetch(0);
+  for (int u = 1; u < 4 && u < n_sub; ++u) prefetch(u);
+  for (int u = 0; u < n_sub; ++u) {
+    const int b = u & 1;
+    float4* hi = planes + b * 2 * set4;
+    float4* lo = hi + set4;
+    if (u >= 2) { mbar_wait(mbar + b, parity[b]); parity[b] ^= 1u; }  // the MMAs that read this buffer two sub-records ago are done
+    convert(hi, lo);
     fence_proxy_async();
     tc_fence_before();
     bar_sync_named(1 + HALF, WG_HT);
-    const int next = rec + step;
-    if (next < n_rec) fetch(next);  // in flight while the MMAs run
-    if (next + step < n_rec) prefetch(next + step);
+    if (u + 1 < n_sub) fetch(u + 1);  // in flight while the MMAs run
+    if (u + 4 < n_sub) prefetch(u + 4);
     if ((warp & 7) == 0) {
       tc_fence_after();
       if (elect_one()) {
+        const uint32_t sh = smem_u32(hi), sl = smem_u32(lo);
 #pragma unroll 1
         for (int pass = 0; pass < 3; ++pass) {
           const uint32_t sa = pass == 1 ? sl : sh, sb = pass == 0 ? sl : sh;  // hi*lo, lo*hi, hi*hi
 #pragma unroll 1
-          for (int s = 0; s < 4; ++s) {
-            const uint32_t acc = (first && pass == 0 && s == 0) ? 0u : 1u;
+          for (int s = 0; s < 2; ++s) {
+            const uint32_t acc = (u == 0 && pass == 0 && s == 0) ? 0u : 1u;
             auto D = [&](uint32_t base, int off, int rows, int row0) { return wg_desc(base + (uint32_t)(off + 2 * s * rows + row0) * 16, (uint32_t)rows * 16); };
             if constexpr (HALF == 0) {
               tc_mma_ss(tb, D(sa, o0, r0, 0), D(sb, o2, r2, 0), id1, acc);
@@ -694,15 +706,16 @@ __device__ __forceinline__ void wgrad_half(const TcD& T, const TcB& B, const Wgr
             }
           }
         }
-        tc_commit(mbar);
+        tc_commit(mbar + b);
       }
       __syncwarp();
     }
-    first = false;
-    rec = next;
   }
-  if (!first) {
-    mbar_wait(mbar, parity); parity ^= 1u;
+  if (n_sub > 0) {
+    // the last two commits cover every MMA (a commit tracks all MMAs issued before it)
+    const int bl = (n_sub - 1) & 1;
+    if (n_sub >= 2) { mbar_wait(mbar + (bl ^ 1), parity[bl ^ 1]); }
+    mbar_wait(mbar + bl, parity[bl]);
     tc_fence_after();
     // accumulators -> this CTA's image (added: the image carries the sum over the launches). Image columns: dW1 [0,N1),
     // dW2 rows 0..127 [N1,N1+N2), rows 128.. [N1+N2,N1+2N2), dW3 [N1+2N2,+96)
@@ -725,10 +738,11 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const __grid_constan
   extern __shared__ __align__(1024) uint8_t smem_wg[];
   const int tid = threadIdx.x, warp = tid >> 5;
   const int half = warp >> 3;
+  // 2 halves x 2 buffers x (hi, lo) x 16 columns = the bytes of one full hi + lo record
   const int total4 = 16 * (a.aux.rx + a.aux.r2 + a.aux.r1 + a.aux.r3) + 16 * (a.aux.r1 + a.aux.r2);
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_wg + (size_t)total4 * 16);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_wg + (size_t)total4 * 16 + 16);
-  if (tid == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); fence_mbar_init(); }
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_wg + (size_t)total4 * 16 + 32);
+  if (tid == 0) { for (int i = 0; i < 4; ++i) mbar_init(mbar + i, 1); fence_mbar_init(); }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -738,7 +752,7 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const __grid_constan
   tc_fence_after();
   const uint32_t tb = *tmem_slot;
   if (half == 0) wgrad_half<ACT, 0>(T, B, a, smem_wg, mbar, tb);
-  else wgrad_half<ACT, 1>(T, B, a, smem_wg, mbar + 1, tb + 256);
+  else wgrad_half<ACT, 1>(T, B, a, smem_wg, mbar + 2, tb + 256);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512));
