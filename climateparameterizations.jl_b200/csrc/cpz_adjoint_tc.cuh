@@ -545,8 +545,9 @@ struct WgradArgs {
   int n_tiles, n_e;  // records of this launch: (tile t, evaluation e < n_e); x / z record aux.ev0 + e, d record e
   float* part;       // [gridDim.x][WG_COLS][128] accumulator images, added to (zeroed by the host before the first launch)
 };
-constexpr int WG_NT = 512;    // two halves of 8 warps
-constexpr int WG_HT = 256;
+constexpr int WG_NT = 576;    // two halves of 8 converter warps + one MMA-issuing warp each (warps 16, 17)
+constexpr int WG_HT = 256;    // converter threads of a half
+constexpr int WG_BAR = 288;   // threads at a half's barrier
 constexpr int WG_COLS = 448;  // N1 + 2 N2 + 96 <= 448
 
 __device__ __forceinline__ uint64_t wg_desc(uint32_t saddr, uint32_t lbo_bytes) {  // K-major, no swizzle, SBO = 128
@@ -596,6 +597,7 @@ __device__ __forceinline__ float4 wg_role(const TcD& T, int row, float4 v) {
 template <int ACT, int HALF>
 __device__ __forceinline__ void wgrad_half(const TcD& T, const TcB& B, const WgradArgs& a, uint8_t* smem, uint64_t* mbar, uint32_t tb) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, ht = tid & (WG_HT - 1);
+  const bool is_mma = warp >= 16;  // this half's issuing warp: no fetch / convert work, so the MMA issue is off the converters' path
   // arrays in plane order (A operands first); NV = float4 per thread of a 16-column sub-record (4 column quads x rows)
   using A0 = std::conditional_t<HALF == 0, WgArr<0, 2>, WgArr<1, 3>>;
   using A1 = std::conditional_t<HALF == 0, WgArr<2, 2>, WgArr<4, 2>>;
@@ -621,16 +623,20 @@ __device__ __forceinline__ void wgrad_half(const TcD& T, const TcB& B, const Wgr
 #pragma unroll
     for (int j = 0; j < A3::NV; ++j) w3[j] = (ht + j * WG_HT) % r3;
   }
-  // sub-record u of this CTA: record blockIdx.x + (u >> 1) gridDim.x, column half u & 1 (column quads 4 (u & 1) ..)
-  auto sub_ptr = [&](int idk, int rows, int u) -> const float4* {
-    const int rec = blockIdx.x + (u >> 1) * gridDim.x;
-    const int t = rec / a.n_e, e = rec - t * a.n_e;
-    const size_t r = idk < 3 ? (size_t)t * a.aux.n_eval + a.aux.ev0 + e : (size_t)t * a.aux.n_eval_d + e;
+  // sub-record u of this CTA: record blockIdx.x + (u >> 1) gridDim.x, column half u & 1 (column quads 4 (u & 1) ..).
+  // (tile, evaluation) of the fetch and prefetch streams are advanced incrementally (no division in the loop)
+  struct Cur { int t, e; };
+  Cur cf, cp;
+  { const int rec = blockIdx.x; cf.t = rec / a.n_e; cf.e = rec - cf.t * a.n_e; cp = cf; }
+  const int estep = gridDim.x;
+  auto advance = [&](Cur& c) { c.e += estep; while (c.e >= a.n_e) { c.e -= a.n_e; ++c.t; } };
+  auto sub_ptr = [&](int idk, int rows, const Cur& c, int u) -> const float4* {
+    const size_t r = idk < 3 ? (size_t)c.t * a.aux.n_eval + a.aux.ev0 + c.e : (size_t)c.t * a.aux.n_eval_d + c.e;
     return reinterpret_cast<const float4*>(src_all[idk] + r * (size_t)(32 * rows)) + (u & 1) * 4 * rows;
   };
   auto fetch1 = [&](auto arr, int rows, float4* buf, int u) {
     using AR = decltype(arr);
-    const float4* p = sub_ptr(AR::ID, rows, u);
+    const float4* p = sub_ptr(AR::ID, rows, cf, u);
 #pragma unroll
     for (int j = 0; j < AR::NV; ++j) {
       const int idx = ht + j * WG_HT;
@@ -639,7 +645,7 @@ __device__ __forceinline__ void wgrad_half(const TcD& T, const TcB& B, const Wgr
   };
   auto pref1 = [&](auto arr, int rows, int u) {
     using AR = decltype(arr);
-    const float4* p = sub_ptr(AR::ID, rows, u);
+    const float4* p = sub_ptr(AR::ID, rows, cp, u);
     if (8 * ht < 4 * rows) prefetch_l2(p + 8 * ht);
   };
   auto conv1 = [&](auto arr, int rows, int off, const float4* buf, const int* rw, float4* hi, float4* lo) {
@@ -657,11 +663,13 @@ __device__ __forceinline__ void wgrad_half(const TcD& T, const TcB& B, const Wgr
       }
     }
   };
-  auto fetch = [&](int u) {
+  auto fetch = [&](int u) {  // called for u = 0, 1, 2, ... in order
     fetch1(A0{}, r0, b0, u); fetch1(A1{}, r1, b1, u);
     if constexpr (HALF == 0) { fetch1(A2{}, r2, b2, u); fetch1(A3{}, r3, b3, u); }
+    if (u & 1) advance(cf);
   };
-  auto prefetch = [&](int u) {
+  auto prefetch = [&](int u) {  // called for u = 1, 2, 3, ... in order
+    if ((u & 1) == 0) advance(cp);
     pref1(A0{}, r0, u); pref1(A1{}, r1, u);
     if constexpr (HALF == 0) { pref1(A2{}, r2, u); pref1(A3{}, r3, u); }
   };
@@ -673,20 +681,25 @@ __device__ __forceinline__ void wgrad_half(const TcD& T, const TcB& B, const Wgr
   uint32_t parity[2] = {0u, 0u};
   const int n_mine = blockIdx.x < n_rec ? (n_rec - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int n_sub = 2 * n_mine;
-  if (n_sub > 0) fetch(0);
-  for (int u = 1; u < 4 && u < n_sub; ++u) prefetch(u);
+  if (!is_mma) {
+    if (n_sub > 0) fetch(0);
+    for (int u = 1; u < 4 && u < n_sub; ++u) prefetch(u);
+  }
   for (int u = 0; u < n_sub; ++u) {
     const int b = u & 1;
     float4* hi = planes + b * 2 * set4;
     float4* lo = hi + set4;
-    if (u >= 2) { mbar_wait(mbar + b, parity[b]); parity[b] ^= 1u; }  // the MMAs that read this buffer two sub-records ago are done
-    convert(hi, lo);
-    fence_proxy_async();
-    tc_fence_before();
-    bar_sync_named(1 + HALF, WG_HT);
-    if (u + 1 < n_sub) fetch(u + 1);  // in flight while the MMAs run
-    if (u + 4 < n_sub) prefetch(u + 4);
-    if ((warp & 7) == 0) {
+    if (!is_mma) {
+      if (u >= 2) { mbar_wait(mbar + b, parity[b]); parity[b] ^= 1u; }  // the MMAs that read this buffer two sub-records ago are done
+      convert(hi, lo);
+      fence_proxy_async();
+      tc_fence_before();
+    }
+    bar_sync_named(1 + HALF, WG_BAR);
+    if (!is_mma) {
+      if (u + 1 < n_sub) fetch(u + 1);  // in flight while the MMAs run
+      if (u + 4 < n_sub) prefetch(u + 4);
+    } else {
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sh = smem_u32(hi), sl = smem_u32(lo);
@@ -711,7 +724,7 @@ __device__ __forceinline__ void wgrad_half(const TcD& T, const TcB& B, const Wgr
       __syncwarp();
     }
   }
-  if (n_sub > 0) {
+  if (n_sub > 0 && !is_mma) {
     // the last two commits cover every MMA (a commit tracks all MMAs issued before it)
     const int bl = (n_sub - 1) & 1;
     if (n_sub >= 2) { mbar_wait(mbar + (bl ^ 1), parity[bl ^ 1]); }
@@ -737,7 +750,7 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const __grid_constan
                                                             const __grid_constant__ WgradArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_wg[];
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int half = warp >> 3;
+  const int half = warp < 16 ? warp >> 3 : warp - 16;
   // 2 halves x 2 buffers x (hi, lo) x 16 columns = the bytes of one full hi + lo record
   const int total4 = 16 * (a.aux.rx + a.aux.r2 + a.aux.r1 + a.aux.r3) + 16 * (a.aux.r1 + a.aux.r2);
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_wg + (size_t)total4 * 16);
