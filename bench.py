@@ -13,8 +13,8 @@ Prints ONE JSON line (rank 0). `value` = device-resident throughput, `e2e` = thr
 (pinned host buffers, H2D + D2H inside the timed region). Extra objects: roofline (tensor pipe of the tcgen05 kernel:
 ALGORITHMIC FP32-equivalent flops = 2 x MACs of SURVEY 8d over the measured bf16 peak; the 3xTF32-issued rate and the
 TF32 peak measured in this run are separate keys), roofline_hbm / roofline_compute (HBM and FP32-SIMT views of the same
-run), adjoint (forward + discrete adjoint + ADAM, BASELINE config 3, with ckpt_stride 9 = recompute and ckpt_stride 1 =
-stored stage tendencies), config1 (one T-only column, CA + mPP base, forward + gradient, beside the oracle's single-column
+run), adjoint (forward + discrete adjoint + ADAM, BASELINE config 3: the tensor-core adjoint with its stage records kept in HBM,
+the same with a per-checkpoint-segment record budget = ckpt_stride 9 recompute, and the FP32 SIMT adjoint for A/B), config1 (one T-only column, CA + mPP base, forward + gradient, beside the oracle's single-column
 CPU time), nn_free (the HBM-fair mPP-only variant), free_convection (config 4 slice), closure (config 5 slice, also as a
 10^4-call CUDA-graph replay with a stand-in dynamics kernel between calls), cpu_baseline (the oracle on host cores:
 batched on all cores, and one column at a time on one thread as the reference executes).
@@ -415,11 +415,17 @@ def main():
                              "note": "FP32-equivalent algorithmic flops against the FP32 SIMT peak (the roof of the non-tensor-core kernel)"},
     }
     if not args.no_extras:
+        # the headline model's device buffers are done with: the adjoint's stage records want the HBM
+        model.close()
+        del traj_d
+        torch.cuda.empty_cache()
         # ---- fwd + discrete adjoint + ADAM (BASELINE config 3: 9 forcing cases x 1024 columns, sharded over ranks) ----
-        # Two checkpoint policies of the same training iteration: ckpt_stride 9 (SURVEY config 3: a checkpoint every 9th
-        # step, 129 B of algorithmic HBM traffic per column-step, the segment's stage tendencies are recomputed) and
-        # ckpt_stride 1 with the forward pass's stage tendencies kept in HBM when they fit (49 GB at N = 1; the library
-        # prints a notice and recomputes when they do not).
+        # Three policies of the same training iteration (same loss, same gradient to FP32 noise):
+        #   tc_records_in_hbm   tensor-core adjoint; the per-stage records (X_i, z1, z2) of as many steps as the free HBM holds are
+        #                       written by the checkpointing forward pass itself (all 1 152 steps when they fit: no re-integration)
+        #   tc_ckpt_stride_9    the same kernels with a 2 GB record budget: every 9-step checkpoint segment is re-integrated
+        #                       (SURVEY config 3 as written: ckpt_stride 9, recompute)
+        #   fp32_simt           the round-1 FP32 SIMT adjoint kernel (CPZ_NO_TC_ADJ=1), for A/B
         try:
             from cpz_b200 import parallel
             if dist is not None:
@@ -429,9 +435,14 @@ def main():
             x3 = b3 = None
             w3 = np.array([1, 1, 1, 5e-3, 5e-3, 5e-3], dtype=np.float32)
             adj = {}
-            for ck in (9, 1):
-                d3 = syn.wind_mixing_desc(variant=RHS_TRAIN, net="uvT_small", n_steps=NSTEPS, save_stride=9, ckpt_stride=ck)
+            policies = (("tc_records_in_hbm", {}, 3), ("tc_ckpt_stride_9", {"CPZ_ADJ_AUX_GB": "2"}, 2), ("fp32_simt", {"CPZ_NO_TC_ADJ": "1"}, 1))
+            for name, env, n3 in policies:
+                for k in ("CPZ_ADJ_AUX_GB", "CPZ_NO_TC_ADJ"):
+                    os.environ.pop(k, None)
+                os.environ.update(env)
+                d3 = syn.wind_mixing_desc(variant=RHS_TRAIN, net="uvT_small", n_steps=NSTEPS, save_stride=9, ckpt_stride=9)
                 m3 = engine.Model(ctx, d3, syn.theta_init(d3, seed=42, scale=1e-5))
+                adj_desc = [ln for ln in m3.describe().splitlines() if ln.startswith("adjoint kernels")]
                 if x3 is None:
                     x3, b3 = syn.columns(d3, NC3, seed=1000)
                     x3_d, b3_d = torch.tensor(x3[lo:hi], device="cuda"), torch.tensor(b3[lo:hi], device="cuda")
@@ -441,7 +452,6 @@ def main():
                 m3.train_step_dev(x3_d, b3_d, tg, w3, 3e-4)  # warm-up (allocates scratch)
                 barrier()
                 l0 = ctx.launch_count
-                n3 = 2
                 a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
                 a0.record()
                 for _ in range(n3):
@@ -452,24 +462,34 @@ def main():
                 if dist is not None:
                     dist.all_reduce(t3, op=dist.ReduceOp.MAX)
                 ms3 = float(t3.item()) / n3
-                # fwd+adjoint = 4 x the forward MLP flops (1 fwd + 1 recompute + 2 bwd), 129 B per column-step
-                fl3 = 4 * flops_per_colstep(d3) * NC3 * NSTEPS / world
-                tf3 = fl3 / (ms3 * 1e-3) / 1e12
-                adj[f"ckpt_stride_{ck}"] = {
-                    "value": NC3 * NSTEPS / (ms3 * 1e-3), "ms_per_step": ms3,
+                # algorithmic FP32-equivalent flops: forward MLP + delta propagation + weight gradient = 3 x the forward MLP flops
+                # (re-integration not counted); algorithmic HBM bytes per column-step: 129. The tensor-core policies
+                # really move the per-stage records: per stage evaluation and column 1 224 B written + read twice (x, z1, z2)
+                # and 1 212 B written + read (d1, d2, d3).
+                mlp3 = 2 * sum(n.macs for n in d3.nets) * d3.rhs_evals_per_step
+                tf3 = 3 * mlp3 * (hi - lo) * NSTEPS / (ms3 * 1e-3) / 1e12
+                rec_bytes = d3.rhs_evals_per_step * (3 * 1224 + 2 * 1212) if name.startswith("tc") else None
+                adj[name] = {
+                    "value": NC3 * NSTEPS / (ms3 * 1e-3), "ms_per_step": ms3, "kernels": adj_desc[0] if adj_desc else None,
                     "gpu_launches_per_step": int((ctx.launch_count - l0) / n3), "loss": float(loss3[6]),
-                    "roofline": {"fp32_equiv_tflops": tf3, "frac_of_fp32_simt_peak": tf3 / peak_tf_max, "frac_of_bf16_tensor_peak": tf3 / bf16_peak,
-                                 "hbm_frac_algorithmic_129B": 129.0 * (hi - lo) * NSTEPS / (ms3 * 1e-3) / 1e9 / hbm_peak}}
+                    "roofline": {"fp32_equiv_tflops_algorithmic": tf3, "frac_of_fp32_simt_peak": tf3 / peak_tf_max, "frac_of_bf16_tensor_peak": tf3 / bf16_peak,
+                                 "hbm_frac_algorithmic_129B": 129.0 * (hi - lo) * NSTEPS / (ms3 * 1e-3) / 1e9 / hbm_peak,
+                                 "record_traffic_bytes_per_colstep": rec_bytes,
+                                 "hbm_frac_record_traffic": (rec_bytes * (hi - lo) * NSTEPS / (ms3 * 1e-3) / 1e9 / hbm_peak) if rec_bytes else None}}
                 m3.close()
-            best = max(adj.values(), key=lambda v: v["value"])
+            for k in ("CPZ_ADJ_AUX_GB", "CPZ_NO_TC_ADJ"):
+                os.environ.pop(k, None)
+            best = adj["tc_records_in_hbm"]
             line["adjoint"] = {
                 "metric": "column-steps/sec (forward + discrete adjoint + ADAM)", "value": best["value"],
                 "unit": "column-steps/s", "ms_per_step": best["ms_per_step"], "scaling": "strong",
                 "config": {"workload": "BASELINE config 3: 9 forcing cases x 1024 columns, training RHS, 1152 steps, 129 saved frames, Tsit5 x2 sub-steps, ADAM(3e-4), one allreduce of P+16 floats",
-                           "columns_total": NC3, "columns_this_rank": hi - lo,
-                           "tiles": "4-column adjoint tiles when the rank's columns fit one wave (<= 4 x SMs), else 32-column tiles"},
+                           "columns_total": NC3, "columns_this_rank": hi - lo, "tiles": "32-column tiles (two 16-column MMA groups per CTA)"},
                 **adj,
-                "note": "value = the faster of the two checkpoint policies; the adjoint kernel is FP32 SIMT (no tensor-core instruction), the forward / recompute passes run on tcgen05",
+                "note": "value = tc_records_in_hbm. The tensor-core adjoint is three tcgen05 kernels (segment forward pass with stage records, "
+                        "reverse sweep with transposed weights in tensor memory, weight-gradient contraction); they exchange ~73 KB of records "
+                        "per column-step through HBM because forward weights, transposed weights and gradient accumulators do not fit 512 TMEM "
+                        "columns together, so the real DRAM traffic (hbm_frac_record_traffic) is far above the algorithmic 129 B",
             }
         except Exception as e:  # noqa: BLE001
             line["adjoint"] = {"error": repr(e)}
@@ -518,6 +538,7 @@ def main():
         try:
             d0 = syn.wind_mixing_desc(variant=RHS_INFER, net=None, n_steps=NSTEPS, save_stride=1)
             m0 = engine.Model(ctx, d0, np.zeros(0, dtype=np.float32))
+            traj_d = torch.empty((NCOL, n_saved, S), dtype=torch.float32, device="cuda")
             m0.solve_dev(x0_d, bcs_d, traj_d)
             barrier()
             b0 = torch.cuda.Event(enable_timing=True); b1 = torch.cuda.Event(enable_timing=True)

@@ -73,6 +73,9 @@ __device__ __noinline__ void faces_vjp(const ModelD& M, const float* __restrict_
                                           float* __restrict__ zarena, float* __restrict__ gbar, double* __restrict__ pg /*[5] or null*/) {
   const int N = M.Nz, nfaces = N + 1;
   const bool has_nn = M.n_nets > 0;
+  // implicit diffusion: the stages' RHS carries the NN and boundary fluxes only (the diffusivities act in the backward-Euler
+  // solve, whose VJP is implicit_vjp_tile)
+  const bool expl = !(M.flags & F_IMPLICIT);
   if (M.variant == RHS_FC) {
     const float AN = M.rc.A[2] * M.rc.Nf;
     float* nb = has_nn ? zarena + M.nn_off[0] * CT : nullptr;
@@ -83,8 +86,8 @@ __device__ __noinline__ void faces_vjp(const ModelD& M, const float* __restrict_
         const float eb = AN * (kbar[f * CT + c] - kbar[(f - 1) * CT + c]);
         if (has_nn) nb[(f - 1) * CT + c] = eb;
         const float G = M.rc.Nf * (X[f * CT + c] - X[(f - 1) * CT + c]);
-        if ((M.flags & F_CA) && M.rc.K_ca * G < 0.f) g = -M.rc.K_ca * eb;
-        if (M.flags & F_MPP) {  // F -= c nu(G) G
+        if (expl && (M.flags & F_CA) && M.rc.K_ca * G < 0.f) g = -M.rc.K_ca * eb;
+        if (expl && (M.flags & F_MPP)) {  // F -= c nu(G) G
           float dcnu;
           const float cnu = fc_mpp_cnu(M, G, &dcnu);
           g -= eb * fmaf(dcnu, G, cnu);
@@ -94,7 +97,7 @@ __device__ __noinline__ void faces_vjp(const ModelD& M, const float* __restrict_
     }
     return;
   }
-  const bool mpp = (M.flags & F_MPP) || M.variant == RHS_INFER;
+  const bool mpp = ((M.flags & F_MPP) || M.variant == RHS_INFER) && expl;
   const float eps = M.variant == RHS_TRAIN ? M.rc.eps : 0.f;
   // smoothing filters of the training RHS (NDE_training.jl:98-102,121-123; filtering_operators.jl:1-15): both are linear
   // width-3 running means, so their VJP is the same stencil transposed. These variants are rare, so the neighbouring
@@ -145,7 +148,8 @@ __device__ __noinline__ void faces_vjp(const ModelD& M, const float* __restrict_
         const float gu = Gu + eps, gv = Gv + eps, gT = GT + eps;
         const float su = M.rc.sig_u * gu, sv = M.rc.sig_v * gv;
         const float S2 = su * su + sv * sv;
-        const float iS2 = __fdividef(1.f, S2);
+        // clamped: where the shear vanishes the step is saturated (s (1-s) = 0) and the cotangents below must be 0, not 0 * inf
+        const float iS2 = __fdividef(1.f, fmaxf(S2, 1e-18f));
         const float Ri = M.rc.BzC * gT * iS2;
         const float y2 = 2.f * ((smooth_ri ? ri_used(f) : Ri) - M.rc.Ric) * M.rc.inv_dRi;
         const float s = __fdividef(1.f, 1.f + __expf(y2));
@@ -177,7 +181,7 @@ __device__ __noinline__ void faces_vjp(const ModelD& M, const float* __restrict_
         const float t = -Rib * Ri * iS2 * 2.f;
         gb[0] += t * M.rc.sig_u * su;
         gb[1] += t * M.rc.sig_v * sv;
-      } else if (M.flags & F_CA) {
+      } else if (expl && (M.flags & F_CA)) {
         if (GT < 0.f) gb[2] = -M.rc.c[2] * M.rc.kappa * eb[2];
       }
     }
@@ -577,7 +581,7 @@ __device__ __noinline__ void implicit_vjp_tile(const ModelD& M, const float* __r
           const float Gv = M.rc.Nf * (x[(N + f) * CT + c] - x[(N + f - 1) * CT + c]);
           const float GT = M.rc.Nf * (x[(2 * N + f) * CT + c] - x[(2 * N + f - 1) * CT + c]);
           const float su = M.rc.sig_u * (Gu + eps), sv = M.rc.sig_v * (Gv + eps);
-          const float iS2 = __fdividef(1.f, su * su + sv * sv);
+          const float iS2 = __fdividef(1.f, fmaxf(su * su + sv * sv, 1e-18f));  // see faces_vjp
           const float Ri = M.rc.BzC * (GT + eps) * iS2;
           const float y2 = 2.f * (Ri - M.rc.Ric) * M.rc.inv_dRi;
           const float s = __fdividef(1.f, 1.f + __expf(y2));

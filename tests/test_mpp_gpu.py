@@ -76,7 +76,8 @@ def test_mpp_parameter_gradient_with_nets(ctx):
     print(f"NDE with nets: mPP-parameter scaled-space L2 {e_s:.2e} (fp32-oracle {f_s:.2e}) per parameter {np.array2string(e, precision=1)}  "
           f"theta gradient {e_th:.2e} (fp32-oracle {f_th:.2e})")
     assert e_s <= max(1e-4, 3 * f_s) and e_th <= max(1e-4, 3 * f_th)
-    np.testing.assert_allclose(gt, gt2, rtol=1e-5, atol=1e-9 * np.abs(gt2).max())
+    # gt comes from the FP32 SIMT reverse sweep (it carries the five parameter accumulators), gt2 from the tensor-core adjoint
+    assert np.linalg.norm(gt - gt2) / np.linalg.norm(gt2) <= max(1e-4, f_th)
 
 
 def test_set_get_mpp_params(ctx):
