@@ -159,7 +159,7 @@ int launch_solve_nnfree(cpz_model* m, const SolveArgs& a) {
   side_constants(m->fwd.M, mode, sc);
   // 2 columns per warp keep every SM busy at a few thousand columns; 4 amortise the per-warp overhead at large batches
   const int NC = (getenv("CPZ_NNFREE_NC") ? atoi(getenv("CPZ_NNFREE_NC")) : (a.ncol >= 32768 ? 4 : 2));
-  const int warps = (a.ncol + NC - 1) / NC;
+  const int warps = ((a.ckpt != nullptr ? ((a.ncol + 31) & ~31) : a.ncol) + NC - 1) / NC;
   const int grid = (warps + NF_WARPS - 1) / NF_WARPS;
   const size_t smem = (size_t)m->tab.n_stages * NF_WARPS * 32 * 3 * NC * sizeof(float);
   if (NC == 4) solve_nnfree_kernel<4><<<grid, NF_WARPS * 32, smem, m->ctx->stream>>>(m->fwd.M, sc, mode, m->tab, m->tm, a);

@@ -22,7 +22,9 @@ __global__ void __launch_bounds__(NF_WARPS * 32) solve_nnfree_kernel(const __gri
   const int lane = threadIdx.x & 31;
   const int wglobal = blockIdx.x * NF_WARPS + (threadIdx.x >> 5);
   const int c0 = wglobal * NC;  // first column of this warp
-  if (c0 >= a.ncol) return;
+  // a checkpointing solve fills every column slot of the last 32-column checkpoint tile (duplicates of the last column):
+  // the adjoint's tiles read them, and 0 * (uninitialised NaN) would poison its sums
+  if (c0 >= (a.ckpt != nullptr ? ((a.ncol + 31) & ~31) : a.ncol)) return;
   float* ks = ks_smem + (size_t)threadIdx.x * 3 * NC;
   const int ks_stride = NF_WARPS * 32 * 3 * NC;
   const size_t xs = a.x0_stride ? a.x0_stride : (size_t)96;
