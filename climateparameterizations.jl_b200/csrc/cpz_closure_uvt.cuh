@@ -1,0 +1,147 @@
+// Per-step closure of the u/v/T NDE embedded in a host ocean model: for every column of three (Nx,Ny,Nz) fields
+// the three NN forcing chains on the incoming state followed by the backward-Euler modified Pacanowski–Philander step.
+// Replaces the host-model callback progress_neural_network (wind_mixing/src/NDE_oceananigans.jl:380-405):
+//   NN_uw_forcing / NN_vw_forcing / NN_wT_forcing  (:288-344)  -> dz_uw_NN, dz_vw_NN, dz_wT_NN
+//   modified_pacanowski_philander!                 (:61-101)   -> u', v', T'   (diffusivities :17-58)
+// Everything is dimensional (the callback scales the NN input and unscales its output itself).
+//
+// Same tile scheme as closure_kernel: the fields are x-fastest, so CT consecutive columns at one level are one coalesced
+// row of the [row][column] shared-memory layout the MLP phases read. One thread per (field, column) runs the Thomas sweep.
+#pragma once
+#include "cpz_device.cuh"
+#include "cpz_solve.cuh"
+
+namespace cpz {
+
+struct ClosureUvtD {
+  int Nx, Ny, Nz;
+  float inv_dz, r;          // 1/dz, dt/dz^2
+  float top[3];             // uw, vw, wT at the surface face
+  int ca;                   // nu_T = Ri > 0 ? nu/Pr : kappa_ca
+  float kappa_ca;
+  float g_alpha;            // g alpha: Ri = g alpha dT/dz / (du/dz^2 + dv/dz^2)
+  float nu0, nu_m, Ric, inv_dRi, inv_Pr;
+  float mu[6], sig[6], inv_sig[3];
+};
+
+struct ClosureUvtArgs {
+  const float* theta;
+  const float* f[3];  // u, v, T: [Nz][Ny*Nx]
+  float* dzf;         // [3][Nz][Ny*Nx]  dz_uw_NN, dz_vw_NN, dz_wT_NN
+  float* out;         // [3][Nz][Ny*Nx]  u', v', T'
+  int ncol, n_tiles;
+};
+
+struct ClosureUvtSmem {
+  int w, st, xin, arena, cp, model, total_floats;
+};
+__host__ __device__ inline ClosureUvtSmem closure_uvt_smem_layout(const ModelD& M, int CT) {
+  ClosureUvtSmem L;
+  int o = 0;
+  L.w = o; o += M.w_in_smem ? M.smem_w_floats : 0;
+  L.st = o; o += 3 * M.Nz * CT;     // incoming u, v, T (dimensional)
+  L.xin = o; o += 3 * M.Nz * CT;    // scaled NN input; after the MLP: Thomas d'
+  L.arena = o; o += M.arena_floats * CT;
+  L.cp = o; o += 3 * M.Nz * CT;     // Thomas c'
+  L.model = o; o += (int)((sizeof(ModelD) + 15) / 16) * 4;
+  L.total_floats = o + 4;
+  return L;
+}
+
+template <int CT, int NT, bool WS>
+__global__ void __launch_bounds__(NT, 1) closure_uvt_kernel(const __grid_constant__ ModelD Mp, const __grid_constant__ ClosureUvtD cd,
+                                                            const __grid_constant__ ClosureUvtArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const ClosureUvtSmem L = closure_uvt_smem_layout(Mp, CT);
+  const ModelD& M = model_to_smem<NT>(Mp, smem + L.model);
+  float* wsm = smem + L.w;
+  float* st = smem + L.st;
+  float* xin = smem + L.xin;
+  float* arena = smem + L.arena;
+  float* cp = smem + L.cp;
+  const int N = M.Nz;
+  if (WS) load_weights_smem<NT>(M, wsm, a.theta);
+  __syncthreads();
+  PhaseCache pc;
+  build_phase_cache<WS, CT, NT>(M, pc);
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const int col0 = tile * CT;
+    // coalesced loads: row (q, k) of the tile = CT consecutive floats of field q at level k
+    for (int i = threadIdx.x; i < 3 * N * CT; i += NT) {
+      const int row = i / CT, c = i - row * CT;
+      const int q = row / N, k = row - q * N;
+      const int col = min(col0 + c, a.ncol - 1);
+      const float v = __ldg(a.f[q] + (size_t)k * a.ncol + col);
+      st[i] = v;
+      xin[i] = (v - cd.mu[q]) * cd.inv_sig[q];
+    }
+    __syncthreads();
+    for (int p = 0; p < M.n_phase; ++p) {
+      run_phase_cached<CT, NT, WS, false>(M, p, pc, xin, arena, nullptr, wsm, a.theta);
+      __syncthreads();
+    }
+    // F = [0; unscaled NN - shift; top flux]; output dF/dz at the centres
+    for (int i = threadIdx.x; i < 3 * N * CT; i += NT) {
+      const int row = i / CT, c = i - row * CT;
+      if (col0 + c >= a.ncol) continue;
+      const int q = row / N, k = row - q * N;
+      const float* nn = arena + M.nn_off[q] * CT;
+      const float sg = cd.sig[3 + q], mu = cd.mu[3 + q];
+      const float u0 = fmaf(sg, nn[c], mu);
+      const float shift = q < 2 ? fmaf(sg, u0, mu) : u0;  // :292,301 (momentum, literal) / :324 (temperature)
+      const float lo = k == 0 ? 0.f : fmaf(sg, nn[(k - 1) * CT + c], mu) - shift;
+      const float hi = k == N - 1 ? cd.top[q] : fmaf(sg, nn[k * CT + c], mu) - shift;
+      a.dzf[((size_t)q * N + k) * a.ncol + col0 + c] = (hi - lo) * cd.inv_dz;
+    }
+    __syncthreads();  // the d' sweep below reuses xin
+    // backward-Euler mPP step: one thread per (field, column)
+    if (threadIdx.x < 3 * CT) {
+      const int q = threadIdx.x / CT, c = threadIdx.x - q * CT;
+      const float* su = st + c;
+      const float* sv = st + N * CT + c;
+      const float* sT = st + 2 * N * CT + c;
+      const float* sq = st + q * N * CT + c;
+      float* dpv = xin + q * N * CT + c;
+      float* cpv = cp + q * N * CT + c;
+      // diffusivity of this thread's field on face f (between levels f-1 and f); 0 on the boundary faces
+      auto nuq = [&](int f) -> float {
+        if (f <= 0 || f >= N) return 0.f;
+        const float du = (su[f * CT] - su[(f - 1) * CT]) * cd.inv_dz, dv = (sv[f * CT] - sv[(f - 1) * CT]) * cd.inv_dz;
+        const float dT = (sT[f * CT] - sT[(f - 1) * CT]) * cd.inv_dz;
+        const float Ri = cd.g_alpha * dT / (du * du + dv * dv);  // IEEE: +-Inf at zero shear, NaN at 0/0 (as the reference)
+        const float nu = cd.nu0 + cd.nu_m * (0.5f * (1.f - tanhf((Ri - cd.Ric) * cd.inv_dRi)));
+        if (q < 2) return nu;
+        return (cd.ca && !(Ri > 0.f)) ? cd.kappa_ca : nu * cd.inv_Pr;
+      };
+      float nk = nuq(0), nn1 = nuq(1);
+      float diag = 1.f + cd.r * (nk + nn1);
+      float cprev = -cd.r * nn1 / diag;
+      float dprev = sq[0] / diag;
+      cpv[0] = cprev;
+      dpv[0] = dprev;
+      for (int k = 1; k < N; ++k) {
+        nk = nn1;
+        nn1 = nuq(k + 1);
+        const float lo = -cd.r * nk;
+        diag = 1.f + cd.r * (nk + nn1);
+        const float den = diag - lo * cprev;
+        cprev = -cd.r * nn1 / den;
+        dprev = (sq[k * CT] - lo * dprev) / den;
+        cpv[k * CT] = cprev;
+        dpv[k * CT] = dprev;
+      }
+      const float bottom = sq[0];
+      const bool live = col0 + c < a.ncol;
+      float* o = a.out + (size_t)q * N * a.ncol + col0 + c;
+      float xn = dprev;
+      if (live) o[(size_t)(N - 1) * a.ncol] = xn;
+      for (int k = N - 2; k >= 0; --k) {
+        xn = dpv[k * CT] - cpv[k * CT] * xn;
+        if (live) o[(size_t)k * a.ncol] = (q == 2 && k == 0) ? bottom : xn;  // T'[1] = T_bottom (:93)
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace cpz

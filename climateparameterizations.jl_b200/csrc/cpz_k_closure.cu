@@ -5,6 +5,7 @@
 
 #include "cpz_launch.h"
 #include "cpz_closure_tc.cuh"
+#include "cpz_closure_uvt.cuh"
 #include "cpz_fc_tc.cuh"
 
 namespace cpz {
@@ -129,6 +130,25 @@ int launch_solve_fc_tc(cpz_model* m, const SolveArgs& a) {
   if (same && C.act1 == ACT_RELU) return launch_fc_tc_t<ACT_RELU, false>(m, C, a);
   if (same && C.act1 == ACT_MISH) return launch_fc_tc_t<ACT_MISH, false>(m, C, a);
   return launch_fc_tc_t<-1, false>(m, C, a);
+}
+
+template <int CT, int NT, bool WS>
+static int launch_closure_uvt_t(cpz_model* m, const ClosureUvtD& cd, const ClosureUvtArgs& a) {
+  const ClosureUvtSmem L = closure_uvt_smem_layout(m->fwd.M, CT);
+  const size_t smem = (size_t)L.total_floats * sizeof(float);
+  if (smem > m->ctx->smem_optin) return fail(CPZ_ERR_INVALID, "u/v/T closure kernel needs %zu B shared memory", smem);
+  auto kern = closure_uvt_kernel<CT, NT, WS>;
+  CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = std::min(a.n_tiles, m->ctx->sm_count);
+  kern<<<grid, NT, smem, m->ctx->stream>>>(m->fwd.M, cd, a);
+  CPZ_CUDA(cudaGetLastError());
+  m->ctx->launches++;
+  return CPZ_OK;
+}
+
+int launch_closure_uvt(cpz_model* m, const ClosureUvtD& cd, const ClosureUvtArgs& a) {
+  if (m->fwd.M.w_in_smem) return launch_closure_uvt_t<32, 256, true>(m, cd, a);
+  return launch_closure_uvt_t<32, 256, false>(m, cd, a);
 }
 
 int launch_closure(cpz_model* m, const ClosureD& cd, const ClosureArgs& a) {

@@ -109,13 +109,18 @@ static int launch_tc_t(cpz_model* m, const TcD& T, const SolveArgs& a, const TcA
   const int sms = m->ctx->sm_count > 0 ? m->ctx->sm_count : 148;
   const int t32 = (a.ncol + 31) / 32, t28 = (a.ncol + 27) / 28;
   const bool aux = a.aux.x != nullptr;  // segment pass of the tensor-core adjoint
-  const bool seven = !aux && a.ckpt == nullptr && getenv("CPZ_TC_CPT8") == nullptr && (t28 + sms - 1) / sms <= (t32 + sms - 1) / sms && t28 > t32;
+  const bool seven = !aux && !((m->desc.flags & CPZ_FLAG_IMPLICIT_DIFFUSION) != 0 && !a.rhs_only) && a.ckpt == nullptr && getenv("CPZ_TC_CPT8") == nullptr && (t28 + sms - 1) / sms <= (t32 + sms - 1) / sms && t28 > t32;
   auto kern = a.rhs_only ? (seven ? solve_tc_kernel<ACT, K3S, false, true, 7> : solve_tc_kernel<ACT, K3S, false, true, 8>)
                          : (seven ? solve_tc_kernel<ACT, K3S, false, false, 7> : solve_tc_kernel<ACT, K3S, false, false, 8>);
   if (aux) kern = solve_tc_kernel<ACT, K3S, false, false, 8, true>;
+  const bool impl = (m->desc.flags & CPZ_FLAG_IMPLICIT_DIFFUSION) != 0 && !a.rhs_only;
+  if (impl) {
+    if (aux) return fail(CPZ_ERR_INVALID, "the tensor-core adjoint's segment pass has no implicit-diffusion step");
+    kern = solve_tc_kernel<ACT, K3S, false, false, 8, false, true>;
+  }
   CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
   const int n_tiles = seven ? t28 : t32;
-  if (getenv("CPZ_TC_PROF") != nullptr && !a.rhs_only && !seven && !aux) {  // debug: per-phase cycle counters of CTA 0
+  if (getenv("CPZ_TC_PROF") != nullptr && !a.rhs_only && !seven && !aux && !(m->desc.flags & CPZ_FLAG_IMPLICIT_DIFFUSION)) {  // debug: per-phase cycle counters of CTA 0
     auto pk = solve_tc_kernel<ACT, K3S, true>;
     CPZ_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     SolveArgs ap = a;

@@ -4,6 +4,7 @@
 #include "cpz_solve.cuh"
 #include "cpz_adjoint.cuh"
 #include "cpz_closure.cuh"
+#include "cpz_closure_uvt.cuh"
 
 namespace cpz {
 int launch_solve(cpz_model* m, const SolveArgs& a);
@@ -27,6 +28,7 @@ int launch_adjoint_small(cpz_model* m, const AdjArgs& a, int grid, int CT);
 // column tile the training pass (checkpointing forward + adjoint) uses for `ncol` columns
 int train_tile(const cpz_model* m, size_t ncol);
 int launch_closure(cpz_model* m, const ClosureD& cd, const ClosureArgs& a);
+int launch_closure_uvt(cpz_model* m, const ClosureUvtD& cd, const ClosureUvtArgs& a);
 int launch_reduce_slabs(cpz_model* m, const float* part, int n_slabs, int P, float* out);
 int launch_pack_loss(cpz_model* m, const float* lpart, int n_slabs, int stride, float ncol, float* pack_tail);
 int launch_finalize_loss(cpz_model* m, const float* pack_tail, const float* w6, float inv_prof, float inv_grad, float* loss_out);

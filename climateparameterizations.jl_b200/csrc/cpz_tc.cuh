@@ -268,7 +268,9 @@ static __device__ __noinline__ float tc_diurnal_top(const ModelD& M, float Q, fl
 // CPT: real columns per thread (8, or 7 so that 4 096 columns make 147 tiles of 28 and use every SM; the 8th slot is padding)
 // AUX: the segment pass of the tensor-core adjoint — every stage evaluation also stores its input X_i and the pre-activations
 //      z1, z2 as operand-image records (AuxD, cpz_solve.cuh); the start state may come from a checkpoint (a.x0_tile)
-template <int ACT, int K3S, bool PROF = false, bool RHS_ONLY = false, int CPT = 8, bool AUX = false>
+// IMPL: CPZ_FLAG_IMPLICIT_DIFFUSION solves — the backward-Euler step is compiled only into this instantiation (inlined into the
+//       explicit kernel it cost 6 registers + a spill and 8 % of the config-2 time)
+template <int ACT, int K3S, bool PROF = false, bool RHS_ONLY = false, int CPT = 8, bool AUX = false, bool IMPL = false>
 __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constant__ ModelD M, const __grid_constant__ TcD T,
                                                             const __grid_constant__ TableauD tab, const TimeD tm,
                                                             const SolveArgs a, const TcArgs ta) {
@@ -668,7 +670,7 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
     for (int n = 0; n < tm.n_steps; ++n) {
       for (int sub = 0; sub < tm.n_substeps; ++sub) {
         const float tbase = tm.t0 + (float)(tm.step0 + n) * tm.dt + (float)sub * hstep;
-        if (implicit) implicit_step(hstep);
+        if constexpr (IMPL) implicit_step(hstep);
 #pragma unroll 1
         for (int i = 0; i < ns; ++i) {
           float dx[8];

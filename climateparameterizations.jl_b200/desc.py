@@ -76,6 +76,15 @@ class CClosureDesc(C.Structure):
     ]
 
 
+class CClosureUvtDesc(C.Structure):
+    _fields_ = [
+        ("Nx", C.c_int32), ("Ny", C.c_int32), ("Nz", C.c_int32),
+        ("dz", C.c_float), ("dt", C.c_float),
+        ("uw_top", C.c_float), ("vw_top", C.c_float), ("wT_top", C.c_float),
+        ("convective_adjustment", C.c_int32), ("kappa_ca", C.c_float),
+    ]
+
+
 @dataclass
 class NetDesc:
     """One Flux.Chain of Dense layers: sizes = [in, hidden..., out], acts per layer."""
@@ -213,4 +222,29 @@ class ClosureDesc:
             setattr(c, k, int(getattr(self, k)))
         for k in ("dz", "dt", "K", "T_shift", "T_div", "mu_relax", "T_mid", "dT", "Ly"):
             setattr(c, k, float(getattr(self, k)))
+        return c
+
+
+@dataclass
+class ClosureUvtDesc:
+    """Per-step closure of the u/v/T NDE inside a host ocean model (wind_mixing/src/NDE_oceananigans.jl:17-101,288-344,380-405).
+    Defaults: the reference's single-column run (Lz = 256 m over 32 levels, dt = 60 s, kappa_ca = 1)."""
+    Nx: int
+    Ny: int
+    Nz: int = 32
+    dz: float = 8.0
+    dt: float = 60.0
+    uw_top: float = 0.0
+    vw_top: float = 0.0
+    wT_top: float = 0.0
+    convective_adjustment: bool = False
+    kappa_ca: float = 1.0
+
+    def to_c(self) -> CClosureUvtDesc:
+        c = CClosureUvtDesc()
+        for k in ("Nx", "Ny", "Nz"):
+            setattr(c, k, int(getattr(self, k)))
+        for k in ("dz", "dt", "uw_top", "vw_top", "wT_top", "kappa_ca"):
+            setattr(c, k, float(getattr(self, k)))
+        c.convective_adjustment = 1 if self.convective_adjustment else 0
         return c

@@ -9,7 +9,7 @@ from typing import Optional
 
 import numpy as np
 
-from .desc import CClosureDesc, CModelDesc, ClosureDesc, ModelDesc
+from .desc import CClosureDesc, CClosureUvtDesc, CModelDesc, ClosureDesc, ClosureUvtDesc, ModelDesc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcpz.so")
@@ -20,6 +20,7 @@ EXPORTS = [
     "cpz_model_n_params", "cpz_model_n_saved", "cpz_model_describe", "cpz_set_theta", "cpz_get_theta", "cpz_model_set_time", "cpz_rhs",
     "cpz_rhs_dev", "cpz_predict_flux", "cpz_predict_flux_dev", "cpz_solve", "cpz_solve_dev", "cpz_loss_grad", "cpz_loss_grad_dev", "cpz_train_step",
     "cpz_train_step_dev", "cpz_set_mpp_params", "cpz_get_mpp_params", "cpz_loss_grad_mpp", "cpz_loss_grad_mpp_dev", "cpz_adam_get_state", "cpz_adam_set_state", "cpz_closure_step", "cpz_closure_step_dev",
+    "cpz_sizeof_closure_uvt_desc", "cpz_closure_step_uvt", "cpz_closure_step_uvt_dev",
 ]
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
@@ -81,12 +82,16 @@ def lib() -> C.CDLL:
     L.cpz_adam_set_state.argtypes = [vp, vp, vp, vp, sz]
     for name in ("cpz_closure_step", "cpz_closure_step_dev"):
         getattr(L, name).argtypes = [vp, C.POINTER(CClosureDesc), vp, vp, vp, vp]
+    for name in ("cpz_closure_step_uvt", "cpz_closure_step_uvt_dev"):
+        getattr(L, name).argtypes = [vp, C.POINTER(CClosureUvtDesc), vp, vp, vp, vp, vp]
     for name in EXPORTS:
-        if name not in ("cpz_last_error", "cpz_sizeof_model_desc", "cpz_sizeof_closure_desc"):
+        if name not in ("cpz_last_error", "cpz_sizeof_model_desc", "cpz_sizeof_closure_desc", "cpz_sizeof_closure_uvt_desc"):
             getattr(L, name).restype = C.c_int
     L.cpz_sizeof_model_desc.restype = C.c_size_t
     L.cpz_sizeof_closure_desc.restype = C.c_size_t
-    if L.cpz_sizeof_model_desc() != C.sizeof(CModelDesc) or L.cpz_sizeof_closure_desc() != C.sizeof(CClosureDesc):
+    L.cpz_sizeof_closure_uvt_desc.restype = C.c_size_t
+    if (L.cpz_sizeof_model_desc() != C.sizeof(CModelDesc) or L.cpz_sizeof_closure_desc() != C.sizeof(CClosureDesc)
+            or L.cpz_sizeof_closure_uvt_desc() != C.sizeof(CClosureUvtDesc)):
         raise CpzError(-1, "ABI mismatch between desc.py and libcpz.so (rebuild the library)")
     _lib = L
     return L
@@ -337,6 +342,16 @@ class Model:
         _check(lib().cpz_closure_step(self._h, C.byref(c), _ptr(T), _ptr(y), _ptr(forcing), _ptr(T_out)))
         return forcing, T_out
 
+    def closure_step_uvt(self, cdesc: ClosureUvtDesc, u, v, T):
+        """One host-model step of the embedded u/v/T NDE: (dz_flux [3,Nz,Ny,Nx], uvT' [3,Nz,Ny,Nx]); fields are [Nz,Ny,Nx]."""
+        shp = (cdesc.Nz, cdesc.Ny, cdesc.Nx)
+        u, v, T = _np(u, shp), _np(v, shp), _np(T, shp)
+        dzf = np.empty((3,) + shp, dtype=np.float32)
+        out = np.empty((3,) + shp, dtype=np.float32)
+        c = cdesc.to_c()
+        _check(lib().cpz_closure_step_uvt(self._h, C.byref(c), _ptr(u), _ptr(v), _ptr(T), _ptr(dzf), _ptr(out)))
+        return dzf, out
+
     # -- device-pointer flavour (torch CUDA tensors or raw addresses; enqueued on the context's stream, no sync)
     def rhs_dev(self, x, bcs, out, t: float = 0.0, Q=None, ncol: Optional[int] = None) -> None:
         ncol = ncol if ncol is not None else x.shape[0]
@@ -364,6 +379,10 @@ class Model:
     def closure_step_dev(self, cdesc: ClosureDesc, T, y, forcing, T_out) -> None:
         c = cdesc.to_c()
         _check(lib().cpz_closure_step_dev(self._h, C.byref(c), _ptr(T), _ptr(y), _ptr(forcing), _ptr(T_out)))
+
+    def closure_step_uvt_dev(self, cdesc: ClosureUvtDesc, u, v, T, dz_flux, uvT_out) -> None:
+        c = cdesc.to_c()
+        _check(lib().cpz_closure_step_uvt_dev(self._h, C.byref(c), _ptr(u), _ptr(v), _ptr(T), _ptr(dz_flux), _ptr(uvT_out)))
 
     def close(self) -> None:
         if self._h:

@@ -180,3 +180,18 @@ def gyre_field(Nx: int, Ny: int, Nz: int = 32, seed: int = 4000, Ly: float = 6.0
     base = 2.0 + 24.0 * k[:, None, None] ** 2 * (0.6 + 0.4 * (y[None, :, None] / Ly + 0.5))
     T = base + 0.3 * rng.standard_normal((Nz, Ny, Nx))
     return np.ascontiguousarray(T, dtype=np.float32), y
+
+
+def uvt_fields(desc: ModelDesc, Nx: int, Ny: int, seed: int = 5000, unstable_every: int = 0
+               ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Dimensional u, v [m/s] and T [deg C] fields [Nz, Ny, Nx] for the embedded u/v/T closure (NDE_oceananigans.jl): the
+    profiles of `columns` un-scaled; every `unstable_every`-th column gets a statically unstable top third so that the
+    convective-adjustment branch of the diffusivity acts."""
+    x0, _ = columns(desc, Nx * Ny, seed=seed)
+    N = desc.Nz
+    f = [x0[:, q * N:(q + 1) * N].astype(np.float64) * desc.sigma[q] + desc.mu[q] for q in range(3)]
+    if unstable_every > 0:
+        k0 = 2 * N // 3
+        f[2][::unstable_every, k0:] = f[2][::unstable_every, k0:][:, ::-1] - 0.02 * np.arange(N - k0)[None, :]
+    to_field = lambda a: np.ascontiguousarray(a.T.reshape(N, Ny, Nx), dtype=np.float32)
+    return to_field(f[0]), to_field(f[1]), to_field(f[2])

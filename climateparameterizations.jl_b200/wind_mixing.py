@@ -407,3 +407,37 @@ def optimise_modified_pacanowski_philander(data: ProfileData, tsteps, timesteppe
         model.close()
         if own_ctx:
             ctx.close()
+
+
+# ---- the trained NDE embedded in a host ocean model -----------------------------------------------------
+
+def _standin_dynamics(u, v, T, dz_flux, dt, f):
+    """Stand-in for the host model's own time step between two callbacks (Oceananigans' IncompressibleModel is third-party
+    and out of scope): forward Euler with the three NN forcings -dz_flux (NDE_oceananigans.jl:346-359) and the f-plane
+    Coriolis terms (:366). Works on numpy arrays and torch tensors alike."""
+    return (u + dt * (-dz_flux[0] + f * v), v + dt * (-dz_flux[1] - f * u), T + dt * (-dz_flux[2]))
+
+
+def oceananigans_modified_pacanowski_philander_nn(model: engine.Model, cdesc, u, v, T, n_iterations: int, output_every: int = 10,
+                                                  f: float = 1e-4, wT_flux: Optional[Callable[[float], float]] = None,
+                                                  dynamics: Optional[Callable] = None) -> List[Tuple[np.ndarray, np.ndarray, np.ndarray]]:
+    """Mirror of the neural-network simulation of oceananigans_modified_pacanowski_philander_nn
+    (wind_mixing/src/NDE_oceananigans.jl:103-475): every iteration the callback progress_neural_network (:380-405) — the
+    three NN forcing chains on the current state, then the backward-Euler modified Pacanowski–Philander step — runs on the
+    GPU through cpz_closure_step_uvt for every column of the (Nz, Ny, Nx) fields, and the host model advances the state with
+    those forcings (`dynamics(u, v, T, dz_flux, dt, f)`; default: the forward-Euler stand-in above). A time-dependent top
+    temperature flux is `wT_flux(t)` (:129,332). Returns the frames saved every `output_every` iterations (the reference
+    writes every 600 s at dt = 60 s, :407-440), frame 0 = initial state."""
+    import copy
+    dyn = dynamics or _standin_dynamics
+    cd = copy.copy(cdesc)
+    u, v, T = (np.ascontiguousarray(a, dtype=np.float32) for a in (u, v, T))
+    frames = [(u.copy(), v.copy(), T.copy())]
+    for it in range(n_iterations):
+        if wT_flux is not None:
+            cd.wT_top = float(wT_flux(it * cd.dt))
+        dz_flux, out = model.closure_step_uvt(cd, u, v, T)
+        u, v, T = (np.ascontiguousarray(a, dtype=np.float32) for a in dyn(out[0], out[1], out[2], dz_flux, cd.dt, f))
+        if (it + 1) % output_every == 0:
+            frames.append((u.copy(), v.copy(), T.copy()))
+    return frames

@@ -248,6 +248,30 @@ int cpz_closure_step(cpz_model* m, const cpz_closure_desc* c, const float* T, co
 int cpz_closure_step_dev(cpz_model* m, const cpz_closure_desc* c, const float* T, const float* y, float* forcing_out,
                          float* T_out);
 
+/* ---- S7b: per-step closure of the u/v/T NDE inside a host ocean model ---------- */
+/* replaces the Simulation callback progress_neural_network (wind_mixing/src/NDE_oceananigans.jl:380-405): the NN forcing
+ * chains NN_uw_forcing / NN_vw_forcing / NN_wT_forcing on the incoming state (:288-344; dz of [0; unscaled NN - shift;
+ * top flux]) followed by modified_pacanowski_philander! (:61-101, diffusivities :17-58): a backward-Euler tridiagonal
+ * solve of the vertical diffusion of u, v (nu) and T (nu_T) over dt, T'[bottom] kept. The model is a u/v/T model
+ * (n_fields = 3, three nets); mu/sigma, g, alpha, nu0, nu_m, dRi, Ric, Pr come from its description. Everything here is
+ * DIMENSIONAL. u, v, T: [Nz][Ny][Nx]; dz_flux_out: [3][Nz][Ny][Nx] = dz_uw_NN, dz_vw_NN, dz_wT_NN (the Forcing functions
+ * apply the minus sign, :346-359); uvT_out: [3][Nz][Ny][Nx] = u', v', T'. A time-dependent wT_flux(t) (:129,332) is
+ * evaluated by the caller and passed as wT_top. On the two boundary faces nu = nu_T = 0 (the reference's boundary-face
+ * Ri comes from Oceananigans halo values; 0 is what its gradient boundary conditions give). */
+typedef struct {
+  int32_t Nx, Ny, Nz;
+  float dz;                       /* metres (grid.dz = Lz/Nz)                          */
+  float dt;                       /* host-model time step, seconds (:104: 60)          */
+  float uw_top, vw_top, wT_top;   /* BCs.top fluxes (:112)                             */
+  int32_t convective_adjustment;  /* nu_T = Ri > 0 ? nu/Pr : kappa_ca (:50-53)         */
+  float kappa_ca;                 /* :52 hard-codes 1f0                                */
+} cpz_closure_uvt_desc;
+size_t cpz_sizeof_closure_uvt_desc(void);
+int cpz_closure_step_uvt(cpz_model* m, const cpz_closure_uvt_desc* c, const float* u, const float* v, const float* T,
+                         float* dz_flux_out, float* uvT_out);
+int cpz_closure_step_uvt_dev(cpz_model* m, const cpz_closure_uvt_desc* c, const float* u, const float* v, const float* T,
+                             float* dz_flux_out, float* uvT_out);
+
 #ifdef __cplusplus
 }
 #endif

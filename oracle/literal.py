@@ -284,3 +284,81 @@ def gyre_closure_column(desc, theta, cdesc, T_col, y):
     wT_int = sgw * wT_int + muw
     wT = np.concatenate([[0.0], wT_int, [surface_flux]])
     return (wT[1:] - wT[:-1]) / np.float64(np.float32(cdesc.dz))
+
+
+# ---- u/v/T NDE embedded in Oceananigans (wind_mixing) -----------------------------------------------------------
+
+def mpp_diffusivity_oceananigans(desc, cdesc, u, v, T):
+    """modified_pacanowski_philander_diffusivity: wind_mixing/src/NDE_oceananigans.jl:17-58, one column, dimensional.
+    Ri at the interior faces is Oceanostics' richardson_number_ccf! (dz b / (dz u^2 + dz v^2), b = g alpha T, third-party,
+    restated). nu is filled on faces 2..Nz only (:45-47). With convective adjustment nu_T = Ri > 0 ? nu/Pr : kappa_ca
+    (:50-53, kappa_ca hard-coded 1f0). On the two boundary faces the reference's Ri comes from Oceananigans halo values
+    (third-party); nu is 0 there and nu_T is taken as 0 too (what a stably stratified gradient boundary condition gives:
+    Ri = +Inf > 0 -> nu/Pr = 0). Returns (nu, nu_T) on the Nz+1 faces."""
+    u, v, T = (np.asarray(a, dtype=np.float64) for a in (u, v, T))
+    N = desc.Nz
+    f64 = lambda x: np.float64(np.float32(x))
+    g, alpha, dz = f64(desc.g), f64(desc.alpha), f64(cdesc.dz)
+    nu0, nu_m, dRi, Ric, Pr = f64(desc.nu0), f64(desc.nu_m), f64(desc.dRi), f64(desc.Ric), f64(desc.Pr)
+    nu = np.zeros(N + 1)
+    nu_T = np.zeros(N + 1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for i in range(1, N):  # Julia faces 2..Nz
+            dudz, dvdz, dTdz = (u[i] - u[i - 1]) / dz, (v[i] - v[i - 1]) / dz, (T[i] - T[i - 1]) / dz
+            Ri = g * alpha * dTdz / (dudz ** 2 + dvdz ** 2)
+            nu[i] = nu0 + nu_m * tanh_step((Ri - Ric) / dRi)
+            if cdesc.convective_adjustment:
+                nu_T[i] = nu[i] / Pr if Ri > 0 else f64(cdesc.kappa_ca)
+            else:
+                nu_T[i] = nu[i] / Pr
+    return nu, nu_T
+
+
+def modified_pacanowski_philander_step(desc, cdesc, u, v, T):
+    """modified_pacanowski_philander!: wind_mixing/src/NDE_oceananigans.jl:61-101 — backward-Euler tridiagonal solve of the
+    vertical diffusion of u, v (nu) and T (nu_T) over dt, then T'[1] = T_bottom. Dense solve, one column."""
+    u, v, T = (np.asarray(a, dtype=np.float64) for a in (u, v, T))
+    N = desc.Nz
+    dz, dt = np.float64(np.float32(cdesc.dz)), np.float64(np.float32(cdesc.dt))
+    nu, nu_T = mpp_diffusivity_oceananigans(desc, cdesc, u, v, T)
+
+    def L(nuq):
+        ld = np.array([-dt / dz ** 2 * nuq[i] for i in range(1, N)])       # Julia i in 2:Nz
+        ud = np.array([-dt / dz ** 2 * nuq[i + 1] for i in range(0, N - 1)])  # Julia i in 1:Nz-1
+        d = np.zeros(N)
+        for i in range(N - 1):
+            d[i] = 1 + dt / dz ** 2 * (nuq[i] + nuq[i + 1])
+        d[N - 1] = 1 + dt / dz ** 2 * nuq[N - 1]
+        return np.diag(d) + np.diag(ld, -1) + np.diag(ud, 1)
+
+    u2 = np.linalg.solve(L(nu), u)
+    v2 = np.linalg.solve(L(nu), v)
+    T2 = np.linalg.solve(L(nu_T), T)
+    T2[0] = T[0]
+    return u2, v2, T2
+
+
+def uvt_forcing_column(desc, theta, cdesc, u, v, T):
+    """NN_uw_forcing / NN_vw_forcing / NN_wT_forcing: wind_mixing/src/NDE_oceananigans.jl:288-344 (and the callback that fills
+    dz_uw_NN, dz_vw_NN, dz_wT_NN, :380-405), one column, dimensional in and out. The momentum chains subtract
+    inv(scaling)(uw[1]) of the ALREADY unscaled first output (:292,301 — followed literally); the temperature chain
+    subtracts the unscaled first output (:324). enforce_fluxes: [0; NN; top flux] (:281-285); dz at the centres."""
+    u, v, T = (np.asarray(a, dtype=np.float64) for a in (u, v, T))
+    f64 = lambda x: np.float64(np.float32(x))
+    mu = [f64(m) for m in desc.mu]
+    sg = [f64(s) for s in desc.sigma]
+    th = _net_thetas(desc, np.asarray(theta, dtype=np.float64))
+    uvT = np.concatenate([(u - mu[0]) / sg[0], (v - mu[1]) / sg[1], (T - mu[2]) / sg[2]])
+    tops = [f64(cdesc.uw_top), f64(cdesc.vw_top), f64(cdesc.wT_top)]
+    dz = f64(cdesc.dz)
+    out = []
+    for q in range(3):
+        nn = chain_numpy(th[q], desc.nets[q].sizes, desc.nets[q].acts, uvT)
+        un = sg[3 + q] * nn + mu[3 + q]
+        if q < 2:
+            un = un - (sg[3 + q] * un[0] + mu[3 + q])
+        else:
+            un = un - (sg[5] * nn[0] + mu[5])
+        F = np.concatenate([[0.0], un, [tops[q]]])
+        out.append((F[1:] - F[:-1]) / dz)
+    return out

@@ -381,3 +381,60 @@ def closure_step(desc, theta, cdesc, T, y):
     wT = torch.cat([z, nn, surface_flux.reshape(-1, 1)], dim=1)
     forcing = (wT[:, 1:] - wT[:, :-1]) / dz
     return forcing.t().reshape(Nz, Ny, Nx).contiguous(), Tn.t().reshape(Nz, Ny, Nx).contiguous()
+
+
+def closure_step_uvt(desc, theta, cdesc, u, v, T):
+    """One host-model step of the u/v/T NDE embedded in Oceananigans (progress_neural_network,
+    wind_mixing/src/NDE_oceananigans.jl:380-405): the three NN forcing chains on the incoming state (:288-344), then the
+    backward-Euler modified Pacanowski–Philander step (:17-101). Fields [Nz, Ny, Nx], dimensional. Returns
+    (dz_flux [3, Nz, Ny, Nx] = dz_uw_NN, dz_vw_NN, dz_wT_NN;  state [3, Nz, Ny, Nx] = u', v', T').
+    Boundary-face nu_T and the literal momentum shift: see oracle/literal.py."""
+    Nz, Ny, Nx = T.shape
+    dtype = T.dtype
+    cols = [f.reshape(Nz, Ny * Nx).t().contiguous() for f in (u, v, T)]  # [ncol, Nz]
+    mu = [_c32(m) for m in desc.mu]
+    sg = [_c32(s) for s in desc.sigma]
+    dz, dt = _c32(cdesc.dz), _c32(cdesc.dt)
+    z = torch.zeros_like(cols[0][:, :1])
+    # NN forcing chains
+    x = torch.cat([(cols[q] - mu[q]) / sg[q] for q in range(3)], dim=1)
+    thetas = split_thetas(desc, theta)
+    tops = [_c32(cdesc.uw_top), _c32(cdesc.vw_top), _c32(cdesc.wT_top)]
+    dzf = []
+    for q in range(3):
+        nn = chain_torch(thetas[q], desc.nets[q].sizes, desc.nets[q].acts, x)
+        un = sg[3 + q] * nn + mu[3 + q]
+        shift = (sg[3 + q] * un[:, :1] + mu[3 + q]) if q < 2 else un[:, :1]
+        F = torch.cat([z, un - shift, torch.full_like(z, tops[q])], dim=1)
+        dzf.append((F[:, 1:] - F[:, :-1]) / dz)
+    # implicit mPP step
+    G = [(c[:, 1:] - c[:, :-1]) / dz for c in cols]  # interior faces
+    Ri = _c32(desc.g) * _c32(desc.alpha) * G[2] / (G[0] ** 2 + G[1] ** 2)
+    nu = _c32(desc.nu0) + _c32(desc.nu_m) * (1 - torch.tanh((Ri - _c32(desc.Ric)) / _c32(desc.dRi))) / 2
+    nu_T = nu / _c32(desc.Pr)
+    if cdesc.convective_adjustment:
+        nu_T = torch.where(Ri > 0, nu_T, torch.full_like(nu_T, _c32(cdesc.kappa_ca)))
+    r = dt / dz ** 2
+    out = []
+    for q in range(3):
+        nq = torch.cat([z, nu if q < 2 else nu_T, z], dim=1)  # faces 0..Nz (Julia 1..Nz+1); only faces 0..Nz-1 enter the matrix
+        lower = -r * nq[:, :-1]                                # row k: multiplies x[k-1] (k >= 1)
+        upper = -r * nq[:, 1:]                                 # row k: multiplies x[k+1] (k <= Nz-2)
+        diag = 1 + r * (nq[:, :-1] + nq[:, 1:])                # the last row's nq[Nz] is 0: 1 + r nu[Nz-1], as :85-86
+        cq = cols[q]
+        cp, dp = [None] * Nz, [None] * Nz
+        cp[0] = upper[:, 0] / diag[:, 0]
+        dp[0] = cq[:, 0] / diag[:, 0]
+        for k in range(1, Nz):
+            den = diag[:, k] - lower[:, k] * cp[k - 1]
+            cp[k] = upper[:, k] / den
+            dp[k] = (cq[:, k] - lower[:, k] * dp[k - 1]) / den
+        y = [None] * Nz
+        y[Nz - 1] = dp[Nz - 1]
+        for k in range(Nz - 2, -1, -1):
+            y[k] = dp[k] - cp[k] * y[k + 1]
+        if q == 2:
+            y[0] = cq[:, 0]
+        out.append(torch.stack(y, dim=1))
+    to_field = lambda c: c.t().reshape(Nz, Ny, Nx).contiguous()
+    return torch.stack([to_field(c) for c in dzf]), torch.stack([to_field(c) for c in out])

@@ -7,7 +7,7 @@ import re
 import pytest
 
 from cpz_b200 import engine
-from cpz_b200.desc import CClosureDesc, CModelDesc
+from cpz_b200.desc import CClosureUvtDesc, CClosureDesc, CModelDesc
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -31,6 +31,7 @@ def test_struct_sizes_match_the_library():
     L = engine.lib()
     assert L.cpz_sizeof_model_desc() == C.sizeof(CModelDesc)
     assert L.cpz_sizeof_closure_desc() == C.sizeof(CClosureDesc)
+    assert L.cpz_sizeof_closure_uvt_desc() == C.sizeof(CClosureUvtDesc)
     assert L.cpz_version() == 1
 
 

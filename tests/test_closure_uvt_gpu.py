@@ -1,0 +1,94 @@
+"""S7b parity: per-step closure of the u/v/T NDE embedded in a host ocean model — NN forcing chains + backward-Euler
+modified Pacanowski–Philander step (wind_mixing/src/NDE_oceananigans.jl:17-101,288-344,380-405), CUDA vs the FP64 oracle."""
+import numpy as np
+import pytest
+
+from cpz_b200 import engine, synthetic as syn
+from cpz_b200.desc import ClosureUvtDesc, RHS_INFER
+from oracle import literal, nde
+from util import rel_inf, t64
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(ctx, d, th, cd, u, v, T):
+    m = engine.Model(ctx, d, th)
+    dzf, out = m.closure_step_uvt(cd, u, v, T)
+    m.close()
+    return dzf, out
+
+
+@pytest.mark.parametrize("nx,ny,ca", [(64, 8, False), (64, 8, True), (50, 7, True), (3, 1, True), (1, 1, False)])
+def test_closure_step_uvt(ctx, nx, ny, ca):
+    d = syn.wind_mixing_desc(variant=RHS_INFER)
+    th = syn.theta_random(d, scale=0.5)
+    u, v, T = syn.uvt_fields(d, nx, ny, unstable_every=3 if ca else 0)
+    cd = ClosureUvtDesc(Nx=nx, Ny=ny, Nz=32, dz=d.H / 32, dt=60.0, uw_top=-1e-4, vw_top=2e-5, wT_top=3e-5, convective_adjustment=ca)
+    dzf, out = _run(ctx, d, th, cd, u, v, T)
+    dzf_ref, out_ref = nde.closure_step_uvt(d, t64(th), cd, t64(u), t64(v), t64(T))
+    dzf_ref, out_ref = dzf_ref.numpy(), out_ref.numpy()
+    # the implicit step moves the state by a small increment: compare the increments too, relative to the largest one
+    inc, inc_ref = out.astype(np.float64) - np.stack([u, v, T]), out_ref - np.stack([u, v, T]).astype(np.float64)
+    e = [rel_inf(dzf[q], dzf_ref[q]) for q in range(3)] + [rel_inf(out[q], out_ref[q]) for q in range(3)]
+    e_inc = [float(np.abs(inc[q] - inc_ref[q]).max() / max(np.abs(inc_ref[q]).max(), 1e-30)) for q in range(3)]
+    print(f"uvT closure {nx}x{ny} ca={ca}: dz_flux {e[0]:.1e} {e[1]:.1e} {e[2]:.1e}  state {e[3]:.1e} {e[4]:.1e} {e[5]:.1e}  "
+          f"increments {e_inc[0]:.1e} {e_inc[1]:.1e} {e_inc[2]:.1e} (largest |dT| {np.abs(inc_ref[2]).max():.2e})")
+    assert max(e) <= 1e-5
+    # increments are differences of O(1e-7)-accurate FP32 states: bounded by the state's rounding, not by 1e-5 of themselves
+    for q in range(3):
+        assert np.abs(inc[q] - inc_ref[q]).max() <= 4e-7 * np.abs(np.stack([u, v, T])[q]).max() + 1e-5 * np.abs(inc_ref[q]).max()
+    assert np.all(out[2][0] == T[0])  # T'[bottom] = T_bottom exactly
+    if ca:
+        assert np.abs(inc_ref[2]).max() > 1e-3  # the kappa_ca branch acted
+    # one column against the line-by-line restatement (dense tridiagonal solve)
+    j, i = 0, min(3, nx - 1)
+    f_col = literal.uvt_forcing_column(d, th, cd, u[:, j, i], v[:, j, i], T[:, j, i])
+    s_col = literal.modified_pacanowski_philander_step(d, cd, u[:, j, i], v[:, j, i], T[:, j, i])
+    for q in range(3):
+        assert np.abs(dzf[q][:, j, i] - f_col[q]).max() <= 1e-5 * np.abs(dzf_ref[q]).max()
+        assert rel_inf(out[q][:, j, i], s_col[q]) <= 1e-5
+
+
+def test_closure_step_uvt_large_nets_stream_weights(ctx):
+    """400-wide nets do not fit shared memory: the kernel streams the weights from L2 (WS = false instantiation)."""
+    d = syn.wind_mixing_desc(variant=RHS_INFER, net="uvT_large")
+    th = syn.theta_random(d, scale=0.3)
+    u, v, T = syn.uvt_fields(d, 40, 2)
+    cd = ClosureUvtDesc(Nx=40, Ny=2, Nz=32, dz=d.H / 32, dt=60.0, uw_top=-1e-4, wT_top=1e-5)
+    dzf, out = _run(ctx, d, th, cd, u, v, T)
+    dzf_ref, out_ref = nde.closure_step_uvt(d, t64(th), cd, t64(u), t64(v), t64(T))
+    assert rel_inf(dzf, dzf_ref.numpy()) <= 1e-5 and rel_inf(out, out_ref.numpy()) <= 1e-5
+
+
+def test_closure_step_uvt_rejects_wrong_models(ctx):
+    d = syn.free_convection_desc(ca=False)
+    m = engine.Model(ctx, d, syn.theta_random(d))
+    cd = ClosureUvtDesc(Nx=4, Ny=1)
+    z = np.zeros((32, 1, 4), dtype=np.float32)
+    with pytest.raises(engine.CpzError) as ei:
+        m.closure_step_uvt(cd, z, z, z)
+    assert ei.value.code == engine.ERR_INVALID
+    m.close()
+
+
+def test_oceananigans_mirror_runs_the_callback_sequence(ctx):
+    """wind_mixing.oceananigans_modified_pacanowski_philander_nn: callback order and the stand-in explicit update between calls
+    equal the same sequence run on the oracle."""
+    from cpz_b200 import wind_mixing as wm
+    d = syn.wind_mixing_desc(variant=RHS_INFER)
+    th = syn.theta_random(d, scale=0.3)
+    u, v, T = syn.uvt_fields(d, 6, 1)
+    # no convective-adjustment switch here: over 20 chained steps an FP32-vs-FP64 flip of the discontinuous Ri > 0 branch at a
+    # near-neutral face changes that face's diffusivity by O(1) (the single-step tests above cover the branch)
+    cd = ClosureUvtDesc(Nx=6, Ny=1, Nz=32, dz=d.H / 32, dt=60.0, uw_top=-1e-4, wT_top=2e-5, convective_adjustment=False)
+    m = engine.Model(ctx, d, th)
+    frames = wm.oceananigans_modified_pacanowski_philander_nn(m, cd, u, v, T, n_iterations=20, output_every=10, f=d.f)
+    m.close()
+    uu, vv, TT = (t64(a) for a in (u, v, T))
+    for it in range(20):
+        dzf, out = nde.closure_step_uvt(d, t64(th), cd, uu, vv, TT)
+        uu, vv, TT = wm._standin_dynamics(out[0], out[1], out[2], dzf, cd.dt, d.f)
+    assert len(frames) == 3
+    errs = [rel_inf(frames[-1][q], ref.numpy()) for q, ref in enumerate((uu, vv, TT))]
+    print(f"embedded u/v/T run, 20 iterations: u {errs[0]:.1e} v {errs[1]:.1e} T {errs[2]:.1e}")
+    assert max(errs) <= 2e-5

@@ -274,3 +274,30 @@ def test_closure_batched_equals_literal():
         np.testing.assert_allclose(forcing[:, j, i].numpy(), literal.gyre_closure_column(d, th, cd, T_adj, float(y[j])), rtol=1e-9, atol=1e-16)
     # note: the reference's matrix (kappa located at centres, d_1 = 1 + r(kappa_1 + kappa_2)) is not conservative at the
     # bottom cell when kappa_1 != 0; the oracle follows the code, so no column-mean invariant is asserted here.
+
+
+def test_uvt_closure_restatements_agree():
+    """oracle/nde.closure_step_uvt (batched Thomas) vs oracle/literal (dense solve, line by line) for the embedded u/v/T
+    closure (wind_mixing/src/NDE_oceananigans.jl:17-101,288-344), with and without the convective-adjustment branch."""
+    import torch
+    from cpz_b200 import synthetic as syn
+    from cpz_b200.desc import ClosureUvtDesc, RHS_INFER
+    from oracle import literal, nde
+    d = syn.wind_mixing_desc(variant=RHS_INFER)
+    th = syn.theta_random(d, scale=0.5)
+    u, v, T = syn.uvt_fields(d, 5, 2, unstable_every=2)
+    for ca in (False, True):
+        cd = ClosureUvtDesc(Nx=5, Ny=2, Nz=32, dz=d.H / 32, dt=60.0, uw_top=-1e-4, vw_top=2e-5, wT_top=3e-5, convective_adjustment=ca)
+        t64 = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64)
+        dzf, out = nde.closure_step_uvt(d, t64(th), cd, t64(u), t64(v), t64(T))
+        for (j, i) in ((0, 0), (1, 2), (1, 4)):
+            f_col = literal.uvt_forcing_column(d, th, cd, u[:, j, i], v[:, j, i], T[:, j, i])
+            s_col = literal.modified_pacanowski_philander_step(d, cd, u[:, j, i], v[:, j, i], T[:, j, i])
+            for q in range(3):
+                np.testing.assert_allclose(dzf[q][:, j, i].numpy(), f_col[q], rtol=1e-10, atol=1e-16)
+                np.testing.assert_allclose(out[q][:, j, i].numpy(), s_col[q], rtol=1e-10, atol=1e-14)
+        assert float(out[2][0].sub(t64(T)[0]).abs().max()) == 0.0
+        # a uniform, unsheared-gradient-free column: diffusion leaves constants alone (rows of L sum to 1 except the top row's
+        # missing upper face, which is 0 too)
+    nu, nu_T = literal.mpp_diffusivity_oceananigans(d, ClosureUvtDesc(Nx=1, Ny=1, dz=8.0, convective_adjustment=True), u[:, 0, 0], v[:, 0, 0], T[:, 0, 0])
+    assert nu[0] == 0 and nu[-1] == 0 and nu_T[0] == 0 and nu_T[-1] == 0 and (nu[1:-1] >= d.nu0 * 0.999).all()
