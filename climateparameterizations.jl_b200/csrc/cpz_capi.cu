@@ -298,6 +298,8 @@ int cpz_model_describe(const cpz_model* m, char* buf, size_t buf_len) {
       s += "adjoint kernels: tcgen05 3xTF32 (stage records in HBM; reverse sweep with transposed weights in tensor memory; weight gradient as one contraction over columns x stages)\n";
     else if (m->P > 0)
       s += "adjoint kernels: fp32-simt (tensor-core adjoint not eligible: " + why + ")\n";
+    if (m->P > 0 && fc1_eligible(m, 1))
+      s += "small batches (<= 32 columns, CPZ_FC1_MAX_NCOL): one CTA per column, weights in shared memory, weight gradients in registers\n";
   }
   dump("forward", m->fwd, solve_other_smem(m->desc, m->CT, m->tab.n_stages));
   if (m->has_bwd) dump("adjoint", m->bwd, adjoint_other_smem(m->desc.n_fields * m->desc.Nz, m->desc.n_fields == 3 ? 6 : 2, m->CT));

@@ -27,6 +27,10 @@ int launch_solve_small(cpz_model* m, const SolveArgs& a, int CT);
 int launch_adjoint_small(cpz_model* m, const AdjArgs& a, int grid, int CT);
 // column tile the training pass (checkpointing forward + adjoint) uses for `ncol` columns
 int train_tile(const cpz_model* m, size_t ncol);
+// small-batch T-only training pass, one CTA per column (cpz_k_fc1.cu)
+bool fc1_eligible(const cpz_model* m, size_t ncol);
+int loss_grad_fc1(cpz_model* m, const float* x0, const float* bcs, const float* targets, size_t ncol, float wT, float inv_prof,
+                  int n_saved, const float** lpart_out);
 int launch_closure(cpz_model* m, const ClosureD& cd, const ClosureArgs& a);
 int launch_closure_uvt(cpz_model* m, const ClosureUvtD& cd, const ClosureUvtArgs& a);
 int launch_reduce_slabs(cpz_model* m, const float* part, int n_slabs, int P, float* out);

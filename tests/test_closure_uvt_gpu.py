@@ -72,23 +72,27 @@ def test_closure_step_uvt_rejects_wrong_models(ctx):
 
 
 def test_oceananigans_mirror_runs_the_callback_sequence(ctx):
-    """wind_mixing.oceananigans_modified_pacanowski_philander_nn: callback order and the stand-in explicit update between calls
-    equal the same sequence run on the oracle."""
+    """wind_mixing.oceananigans_modified_pacanowski_philander_nn: every transition frame k -> k+1 of the embedded run (callback,
+    then the stand-in explicit update) equals the same step on the oracle from the same frame. (A free-running FP64 chain is
+    not comparable: in the weakly stratified mixed layer the Richardson number amplifies a 1e-7 rounding of T ~ 20 into an
+    O(1e-3) change of the diffusivity at the next step.)"""
     from cpz_b200 import wind_mixing as wm
     d = syn.wind_mixing_desc(variant=RHS_INFER)
     th = syn.theta_random(d, scale=0.3)
     u, v, T = syn.uvt_fields(d, 6, 1)
-    # no convective-adjustment switch here: over 20 chained steps an FP32-vs-FP64 flip of the discontinuous Ri > 0 branch at a
-    # near-neutral face changes that face's diffusivity by O(1) (the single-step tests above cover the branch)
-    cd = ClosureUvtDesc(Nx=6, Ny=1, Nz=32, dz=d.H / 32, dt=60.0, uw_top=-1e-4, wT_top=2e-5, convective_adjustment=False)
+    cd = ClosureUvtDesc(Nx=6, Ny=1, Nz=32, dz=d.H / 32, dt=60.0, uw_top=-1e-4, wT_top=2e-5, convective_adjustment=True)
+    flux = lambda t: 2e-5 * (1.0 + t / 600.0)  # a time-dependent top temperature flux (NDE_oceananigans.jl:129,332)
     m = engine.Model(ctx, d, th)
-    frames = wm.oceananigans_modified_pacanowski_philander_nn(m, cd, u, v, T, n_iterations=20, output_every=10, f=d.f)
+    frames = wm.oceananigans_modified_pacanowski_philander_nn(m, cd, u, v, T, n_iterations=12, output_every=1, f=d.f, wT_flux=flux)
     m.close()
-    uu, vv, TT = (t64(a) for a in (u, v, T))
-    for it in range(20):
+    assert len(frames) == 13
+    worst = 0.0
+    for it in range(12):
+        cd.wT_top = flux(it * cd.dt)
+        uu, vv, TT = (t64(a) for a in frames[it])
         dzf, out = nde.closure_step_uvt(d, t64(th), cd, uu, vv, TT)
-        uu, vv, TT = wm._standin_dynamics(out[0], out[1], out[2], dzf, cd.dt, d.f)
-    assert len(frames) == 3
-    errs = [rel_inf(frames[-1][q], ref.numpy()) for q, ref in enumerate((uu, vv, TT))]
-    print(f"embedded u/v/T run, 20 iterations: u {errs[0]:.1e} v {errs[1]:.1e} T {errs[2]:.1e}")
-    assert max(errs) <= 2e-5
+        ref = wm._standin_dynamics(out[0], out[1], out[2], dzf, cd.dt, d.f)
+        worst = max([worst] + [rel_inf(frames[it + 1][q], ref[q].numpy()) for q in range(3)])
+    print(f"embedded u/v/T run, 12 transitions: worst {worst:.1e}")
+    assert worst <= 1e-5
+    assert np.abs(frames[-1][2] - frames[0][2]).max() > 1e-4
