@@ -6,14 +6,16 @@
 // ConvectiveAdjustmentNDE (free_convection/src/convective_adjustment_nde.jl:33-48) with the mPP base of
 // wind_mixing/src/NDE_training.jl:114-139 at u = v = 0. Same discrete adjoint as adjoint_kernel (cpz_adjoint.cuh); the
 // difference is the mapping: with one column there is no batch dimension to tile over, so
-//   * the weights stay in shared memory as a plain copy of theta (Flux's [in][out] order) and every layer is a mat-vec whose
-//     outputs are spread over the 512 threads (output o, K quarter kq), partial sums combined through shared memory;
+//   * the weights stay in shared memory in Flux's [in][out] order and every layer is a mat-vec whose outputs are spread over
+//     the 512 threads (output o, K quarter kq), partial sums combined through shared memory;
 //   * every thread owns a FIXED set of weight-gradient entries in registers for the whole reverse sweep
 //     (dW2: 32, dW1: 8, dW3: 8, biases: 3) — no gradient slab is read-modify-written per stage;
 //   * the transposed products of the delta propagation read the same weight copy with a lane skew that keeps the
 //     shared-memory banks distinct.
-// Step checkpoints every ckpt_stride steps; a segment's sub-step start states are re-integrated into shared memory, each
-// step's stage records (stage input, z1, a1, z2, a2) are recomputed right before its reverse stages.
+// The shared-memory weight copy is zero-padded to 32 x 128, 128 x 128, 128 x 32 so that every loop has a constant trip count
+// (fully unrolled, loads ahead of the FMAs). The forward pass stores the start state of EVERY sub-step (128 B each: 2.2 MB
+// for config 1) instead of sparse checkpoints, so the reverse sweep only recomputes the stage records (stage input, z1, a1,
+// z2, a2) of the step it is about to reverse.
 #pragma once
 #include "cpz_device.cuh"
 
@@ -34,22 +36,26 @@ struct Fc1Args {
   size_t x0_stride;
   const float* bcs;      // [ncol][2]
   const float* targets;  // [ncol][n_saved][32]
-  float* ckpt;           // [ncol][n_seg + 1][32]: segment start states, then the final state
+  float* states;         // [ncol][n_sub + 1][32]: start state of every sub-step, then the final state
   float* gpart;          // [ncol][P]: d(unnormalised loss of this column)/dtheta
   float* lpart;          // [ncol][8]: squared-error sum of the T profiles at index 2
-  int ncol, n_saved, n_seg;
+  int ncol, n_saved, n_sub;  // n_sub = n_steps * n_substeps
   float wT, inv_prof;
 };
 
+// zero-padded weight copy in shared memory
+constexpr int FC1_W1 = 0, FC1_W2 = 32 * 128, FC1_W3 = FC1_W2 + 128 * 128, FC1_B1 = FC1_W3 + 128 * 32, FC1_B2 = FC1_B1 + 128,
+              FC1_B3 = FC1_B2 + 128, FC1_WTOT = FC1_B3 + 32;
+
 struct Fc1Smem {
-  int w, xs, xbar, ks, yb, ys, z1, a1, z2, a2, part, d1, d2, d3, nn, segx, total_floats;
+  int w, xs, xr, xbar, ks, yb, ys, z1, a1, z2, a2, part, d1, d2, d3, nn, total_floats;
 };
-__host__ __device__ inline Fc1Smem fc1_smem_layout(const Fc1D& F, int n_stages, int seg_states) {
+__host__ __device__ inline Fc1Smem fc1_smem_layout(int n_stages) {
   Fc1Smem L;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
-  L.w = take(F.P);
-  L.xs = take(32); L.xbar = take(32);
+  L.w = take(FC1_WTOT);
+  L.xs = take(32); L.xr = take(32); L.xbar = take(32);
   L.ks = take(n_stages * 32);   // forward: stage tendencies k_i
   L.yb = take(n_stages * 32);   // reverse: cotangents of the stage inputs
   L.ys = take(n_stages * 32);   // stage inputs
@@ -58,7 +64,6 @@ __host__ __device__ inline Fc1Smem fc1_smem_layout(const Fc1D& F, int n_stages, 
   L.part = take(4 * 128);       // partial sums: [4][128] or [16][32]
   L.d1 = take(128); L.d2 = take(128); L.d3 = take(32);
   L.nn = take(32);
-  L.segx = take(seg_states * 32);
   L.total_floats = o;
   return L;
 }
@@ -67,10 +72,11 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
                                                               const __grid_constant__ TableauD tab, const TimeD tm,
                                                               const __grid_constant__ Fc1Args a) {
   extern __shared__ __align__(16) float smem[];
-  const int ns = tab.n_stages, nsub = tm.n_substeps, cs = tm.ckpt_stride;
-  const Fc1Smem L = fc1_smem_layout(F, ns, cs * nsub);
+  const int ns = tab.n_stages, nsub = tm.n_substeps;
+  const Fc1Smem L = fc1_smem_layout(ns);
   float* wsm = smem + L.w;
   float* xs = smem + L.xs;
+  float* xr = smem + L.xr;
   float* xbar = smem + L.xbar;
   float* ks = smem + L.ks;
   float* yb = smem + L.yb;
@@ -84,24 +90,32 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
   float* d2s = smem + L.d2;
   float* d3s = smem + L.d3;
   float* nns = smem + L.nn;
-  float* segx = smem + L.segx;
 
   const int t = threadIdx.x, lane = t & 31;
   const int o128 = t & 127, kq4 = t >> 7;   // (output, K quarter) of the 128-wide layers
   const int o32 = t & 31, kq16 = t >> 5;    // (output, K sixteenth) of the 31-wide output layer
   const int col = blockIdx.x;
   const int h1 = F.h1, h2 = F.h2;
-  const float* W1 = wsm + F.w_off[0];  // [32][h1]
-  const float* W2 = wsm + F.w_off[1];  // [h1][h2]
-  const float* W3 = wsm + F.w_off[2];  // [h2][31]
-  const float* B1 = wsm + F.b_off[0];
-  const float* B2 = wsm + F.b_off[1];
-  const float* B3 = wsm + F.b_off[2];
+  const float* W1 = wsm + FC1_W1;  // [32][128]
+  const float* W2 = wsm + FC1_W2;  // [128][128]
+  const float* W3 = wsm + FC1_W3;  // [128][32]
+  const float* B1 = wsm + FC1_B1;
+  const float* B2 = wsm + FC1_B2;
+  const float* B3 = wsm + FC1_B3;
   const float Nf = M.rc.Nf, AN = M.rc.A[2] * M.rc.Nf;
   const bool mpp = (M.flags & F_MPP) != 0, ca = (M.flags & F_CA) != 0;
   const float hstep = tm.dt / (float)nsub;
 
-  for (int i = t; i < F.P; i += FC1_NT) wsm[i] = __ldg(a.theta + i);
+  for (int i = t; i < FC1_WTOT; i += FC1_NT) {
+    float w = 0.f;
+    if (i < FC1_W2) { const int k = i >> 7, o = i & 127; if (o < h1) w = __ldg(a.theta + F.w_off[0] + k * h1 + o); }
+    else if (i < FC1_W3) { const int k = (i - FC1_W2) >> 7, o = i & 127; if (k < h1 && o < h2) w = __ldg(a.theta + F.w_off[1] + k * h2 + o); }
+    else if (i < FC1_B1) { const int k = (i - FC1_W3) >> 5, o = i & 31; if (k < h2 && o < 31) w = __ldg(a.theta + F.w_off[2] + k * 31 + o); }
+    else if (i < FC1_B2) { const int o = i - FC1_B1; if (o < h1) w = __ldg(a.theta + F.b_off[0] + o); }
+    else if (i < FC1_B3) { const int o = i - FC1_B2; if (o < h2) w = __ldg(a.theta + F.b_off[1] + o); }
+    else { const int o = i - FC1_B3; if (o < 31) w = __ldg(a.theta + F.b_off[2] + o); }
+    wsm[i] = w;
+  }
   if (t < 32) {
     xs[t] = __ldg(a.x0 + (size_t)col * (a.x0_stride ? a.x0_stride : (size_t)32) + t);
     xbar[t] = 0.f;
@@ -113,13 +127,13 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
   auto mlp_forward = [&](const float* __restrict__ y, float* __restrict__ z1o, float* __restrict__ a1o, float* __restrict__ z2o,
                          float* __restrict__ a2o) {
     {  // layer 1: K = 32 split in four
-      float acc = 0.f;
-      if (o128 < h1) {
-        const float* w = W1 + (8 * kq4) * h1 + o128;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc = fmaf(w[i * h1], y[8 * kq4 + i], acc);
-      }
-      part[kq4 * 128 + o128] = acc;
+      const float* w = W1 + (8 * kq4) * 128 + o128;
+      const float4 y0 = reinterpret_cast<const float4*>(y + 8 * kq4)[0], y1 = reinterpret_cast<const float4*>(y + 8 * kq4)[1];
+      float acc0 = w[0] * y0.x, acc1 = w[128] * y0.y;
+      acc0 = fmaf(w[256], y0.z, acc0); acc1 = fmaf(w[384], y0.w, acc1);
+      acc0 = fmaf(w[512], y1.x, acc0); acc1 = fmaf(w[640], y1.y, acc1);
+      acc0 = fmaf(w[768], y1.z, acc0); acc1 = fmaf(w[896], y1.w, acc1);
+      part[kq4 * 128 + o128] = acc0 + acc1;
     }
     __syncthreads();
     if (t < 128) {
@@ -132,18 +146,16 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
     }
     __syncthreads();
     {  // layer 2: K = h1 (<= 128) split in four
-      float acc0 = 0.f, acc1 = 0.f;
-      if (o128 < h2) {
-        const int k0 = 32 * kq4, kn = min(32, h1 - k0);
-        const float* w = W2 + k0 * h2 + o128;
-        int i = 0;
-        for (; i + 1 < kn; i += 2) {
-          acc0 = fmaf(w[i * h2], a1o[k0 + i], acc0);
-          acc1 = fmaf(w[(i + 1) * h2], a1o[k0 + i + 1], acc1);
-        }
-        if (i < kn) acc0 = fmaf(w[i * h2], a1o[k0 + i], acc0);
+      float acc0 = 0.f, acc1 = 0.f, acc2_ = 0.f, acc3_ = 0.f;
+      const float* w = W2 + (32 * kq4) * 128 + o128;
+      const float4* av = reinterpret_cast<const float4*>(a1o + 32 * kq4);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 v = av[q];
+        acc0 = fmaf(w[(4 * q) * 128], v.x, acc0); acc1 = fmaf(w[(4 * q + 1) * 128], v.y, acc1);
+        acc2_ = fmaf(w[(4 * q + 2) * 128], v.z, acc2_); acc3_ = fmaf(w[(4 * q + 3) * 128], v.w, acc3_);
       }
-      part[kq4 * 128 + o128] = acc0 + acc1;
+      part[kq4 * 128 + o128] = (acc0 + acc1) + (acc2_ + acc3_);
     }
     __syncthreads();
     if (t < 128) {
@@ -156,13 +168,13 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
     }
     __syncthreads();
     {  // layer 3: 31 outputs, K = h2 split in sixteen
-      float acc = 0.f;
-      if (o32 < 31) {
-        const int k0 = 8 * kq16, kn = min(8, h2 - k0);
-        const float* w = W3 + k0 * 31 + o32;
-        for (int i = 0; i < kn; ++i) acc = fmaf(w[i * 31], a2o[k0 + i], acc);
-      }
-      part[kq16 * 32 + o32] = acc;
+      const float* w = W3 + (8 * kq16) * 32 + o32;
+      const float4 v0 = reinterpret_cast<const float4*>(a2o + 8 * kq16)[0], v1 = reinterpret_cast<const float4*>(a2o + 8 * kq16)[1];
+      float acc0 = w[0] * v0.x, acc1 = w[32] * v0.y;
+      acc0 = fmaf(w[64], v0.z, acc0); acc1 = fmaf(w[96], v0.w, acc1);
+      acc0 = fmaf(w[128], v1.x, acc0); acc1 = fmaf(w[160], v1.y, acc1);
+      acc0 = fmaf(w[192], v1.z, acc0); acc1 = fmaf(w[224], v1.w, acc1);
+      part[kq16 * 32 + o32] = acc0 + acc1;
     }
     __syncthreads();
     if (t < 32) {
@@ -214,13 +226,13 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
     __syncthreads();
   };
 
-  // ---- forward pass with segment checkpoints ----------------------------------------------------------------------------
-  float* ck = a.ckpt + (size_t)col * (a.n_seg + 1) * 32;
-  for (int n = 0; n < tm.n_steps; ++n) {
-    if (n % cs == 0 && t < 32) ck[(n / cs) * 32 + t] = xs[t];
-    for (int sub = 0; sub < nsub; ++sub) rk_step(false);
+  // ---- forward pass; the start state of every sub-step goes to HBM (read back by the same thread in the reverse sweep) ------
+  float* st = a.states + (size_t)col * (a.n_sub + 1) * 32;
+  for (int r = 0; r < a.n_sub; ++r) {
+    if (t < 32) st[(size_t)r * 32 + t] = xs[t];
+    rk_step(false);
   }
-  if (t < 32) ck[a.n_seg * 32 + t] = xs[t];
+  if (t < 32) st[(size_t)a.n_sub * 32 + t] = xs[t];
 
   // ---- reverse sweep -------------------------------------------------------------------------------------------------------
   auto frame_of = [&](int step) -> int {
@@ -238,26 +250,21 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
   for (int i = 0; i < 8; ++i) { acc1[i] = 0.f; acc3[i] = 0.f; }
 #pragma unroll
   for (int i = 0; i < 32; ++i) acc2[i] = 0.f;
-  const int skew2 = (h2 & 1) ? 0 : lane;  // lane skew of the transposed layer-2 reads: (row stride + skew step) must be odd
 
   if (t < 32) {
     const int fr = frame_of(tm.n_steps);
     if (fr >= 0) loss_frame(xs, fr);
   }
-  for (int seg = a.n_seg - 1; seg >= 0; --seg) {
-    const int step0 = seg * cs, steps = min(cs, tm.n_steps - step0), R = steps * nsub;
-    __syncthreads();
-    if (t < 32) xs[t] = ck[seg * 32 + t];
-    __syncthreads();
-    for (int r = 0; r < R; ++r) {  // sub-step start states of the segment
-      if (t < 32) segx[r * 32 + t] = xs[t];
-      if (r + 1 < R) rk_step(false);
-    }
-    for (int r = R - 1; r >= 0; --r) {
+  float xnext = (t < 32 && a.n_sub > 0) ? st[(size_t)(a.n_sub - 1) * 32 + t] : 0.f;
+  {
+    for (int r = a.n_sub - 1; r >= 0; --r) {
       __syncthreads();
-      if (t < 32) xs[t] = segx[r * 32 + t];
+      if (t < 32) {
+        xs[t] = xnext; xr[t] = xnext;
+        if (r > 0) xnext = st[(size_t)(r - 1) * 32 + t];  // in flight during this sub-step's reverse stages
+      }
       __syncthreads();
-      rk_step(true);  // stage records of this step (xs moves on to the step's end state; its start stays in segx)
+      rk_step(true);  // stage records of this sub-step (xs moves on to its end state; the start state stays in xr)
       for (int i = ns - 1; i >= 0; --i) {
         const float* y = ys + i * 32;
         // B0 (warp 0): kbar_i, cotangent of the face fluxes = delta3, direct part of Ybar_i through the diffusive flux
@@ -290,13 +297,16 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
 #pragma unroll
           for (int q = 0; q < 8; ++q) acc3[q] = fmaf(av[q], d3, acc3[q]);
           if (t < 31) db3 += d3s[t];
-          float acc = 0.f;
-          if (o128 < h2) {
-            const int ob = 8 * kq4, on = min(8, 31 - ob);
-            const float* w = W3 + o128 * 31 + ob;
-            for (int q = 0; q < on; ++q) acc = fmaf(w[q], d3s[ob + q], acc);
+          // row k = o128 of W3 over the outputs (8 kq4 + q + k) mod 32: the row-dependent rotation keeps the banks distinct
+          const float* w = W3 + o128 * 32;
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int q = 0; q < 8; q += 2) {
+            const int oa = (8 * kq4 + q + o128) & 31, oc = (8 * kq4 + q + 1 + o128) & 31;
+            s0 = fmaf(w[oa], d3s[oa], s0);
+            s1 = fmaf(w[oc], d3s[oc], s1);
           }
-          part[kq4 * 128 + o128] = acc;
+          part[kq4 * 128 + o128] = s0 + s1;
         }
         __syncthreads();
         if (t < 128) {
@@ -316,19 +326,17 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
             acc2[4 * q] = fmaf(v.x, d2, acc2[4 * q]); acc2[4 * q + 1] = fmaf(v.y, d2, acc2[4 * q + 1]);
             acc2[4 * q + 2] = fmaf(v.z, d2, acc2[4 * q + 2]); acc2[4 * q + 3] = fmaf(v.w, d2, acc2[4 * q + 3]);
           }
-          float s0 = 0.f, s1 = 0.f;
-          if (o128 < h1) {
-            const int ob = 32 * kq4;
-            const float* w = W2 + o128 * h2 + ob;
-            const float* dv = d2s + ob;
-#pragma unroll 4
-            for (int q = 0; q < 32; q += 2) {
-              const int oa = (q + skew2) & 31, oc = (q + 1 + skew2) & 31;
-              if (ob + oa < h2) s0 = fmaf(w[oa], dv[oa], s0);
-              if (ob + oc < h2) s1 = fmaf(w[oc], dv[oc], s1);
-            }
+          // row k = o128 of W2 over the outputs 32 kq4 + (q + lane) mod 32 (lane rotation: distinct banks at row stride 128)
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          const float* w = W2 + o128 * 128 + 32 * kq4;
+          const float* dv = d2s + 32 * kq4;
+#pragma unroll
+          for (int q = 0; q < 32; q += 4) {
+            const int oa = (q + lane) & 31, ob = (q + 1 + lane) & 31, oc = (q + 2 + lane) & 31, od = (q + 3 + lane) & 31;
+            s0 = fmaf(w[oa], dv[oa], s0); s1 = fmaf(w[ob], dv[ob], s1);
+            s2 = fmaf(w[oc], dv[oc], s2); s3 = fmaf(w[od], dv[od], s3);
           }
-          part[kq4 * 128 + o128] = s0 + s1;
+          part[kq4 * 128 + o128] = (s0 + s1) + (s2 + s3);
         }
         __syncthreads();
         if (t < 128) {
@@ -345,13 +353,10 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
 #pragma unroll
           for (int q = 0; q < 8; ++q) acc1[q] = fmaf(yv[q], d1, acc1[q]);
           const int k = t >> 4, oq = t & 15;
-          const float* w = W1 + k * h1;
+          const float* w = W1 + k * 128 + oq;
           float s = 0.f;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int o = oq + 16 * q;
-            if (o < h1) s = fmaf(w[o], d1s[o], s);
-          }
+          for (int q = 0; q < 8; ++q) s = fmaf(w[16 * q], d1s[oq + 16 * q], s);
           s += __shfl_xor_sync(0xffffffffu, s, 8);
           s += __shfl_xor_sync(0xffffffffu, s, 4);
           s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -365,8 +370,8 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
         for (int i = 0; i < ns; ++i) s += yb[i * 32 + t];
         xbar[t] = s;
         if (r % nsub == 0) {
-          const int fr = frame_of(step0 + r / nsub);
-          if (fr >= 0) loss_frame(segx + r * 32, fr);
+          const int fr = frame_of(r / nsub);
+          if (fr >= 0) loss_frame(xr, fr);
         }
       }
     }

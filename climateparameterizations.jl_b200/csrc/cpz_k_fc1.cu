@@ -45,8 +45,9 @@ bool fc1_eligible(const cpz_model* m, size_t ncol) {
   if (getenv("CPZ_PROF") != nullptr) return false;  // the phase counters live in the tile kernels
   Fc1D F;
   if (!fc1_plan(m, F)) return false;
-  if (m->tab.n_stages > CPZ_MAX_STAGES || m->tm.ckpt_stride < 1) return false;
-  const Fc1Smem L = fc1_smem_layout(F, m->tab.n_stages, m->tm.ckpt_stride * m->tm.n_substeps);
+  if (m->tab.n_stages > CPZ_MAX_STAGES) return false;
+  if (ncol * ((size_t)m->tm.n_steps * m->tm.n_substeps + 1) * 128 > ((size_t)2 << 30)) return false;  // stored sub-step states
+  const Fc1Smem L = fc1_smem_layout(m->tab.n_stages);
   return (size_t)L.total_floats * sizeof(float) <= m->ctx->smem_optin;
 }
 
@@ -56,16 +57,16 @@ int loss_grad_fc1(cpz_model* m, const float* x0, const float* bcs, const float* 
                   int n_saved, const float** lpart_out) {
   Fc1D F;
   if (!fc1_plan(m, F)) return fail(CPZ_ERR_INVALID, "single-column training kernel not eligible");
-  const int P = F.P, cs = m->tm.ckpt_stride;
-  const int n_seg = (m->tm.n_steps + cs - 1) / cs;
+  const int P = F.P;
+  const int n_sub = m->tm.n_steps * m->tm.n_substeps;
   int rc;
-  if ((rc = fc1_ensure(m->b_ckpt, ncol * (size_t)(n_seg + 1) * 32))) return rc;
+  if ((rc = fc1_ensure(m->b_ckpt, ncol * (size_t)(n_sub + 1) * 32))) return rc;
   if ((rc = fc1_ensure(m->b_part, ncol * ((size_t)P + 8)))) return rc;
   Fc1Args a{};
   a.theta = m->d_theta; a.x0 = x0; a.x0_stride = 0; a.bcs = bcs; a.targets = targets;
-  a.ckpt = m->b_ckpt.p; a.gpart = m->b_part.p; a.lpart = m->b_part.p + ncol * (size_t)P;
-  a.ncol = (int)ncol; a.n_saved = n_saved; a.n_seg = n_seg; a.wT = wT; a.inv_prof = inv_prof;
-  const Fc1Smem L = fc1_smem_layout(F, m->tab.n_stages, cs * m->tm.n_substeps);
+  a.states = m->b_ckpt.p; a.gpart = m->b_part.p; a.lpart = m->b_part.p + ncol * (size_t)P;
+  a.ncol = (int)ncol; a.n_saved = n_saved; a.n_sub = n_sub; a.wT = wT; a.inv_prof = inv_prof;
+  const Fc1Smem L = fc1_smem_layout(m->tab.n_stages);
   const size_t smem = (size_t)L.total_floats * sizeof(float);
   CPZ_CUDA(cudaFuncSetAttribute(fc1_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fc1_train_kernel<<<(unsigned)ncol, FC1_NT, smem, m->ctx->stream>>>(m->fwd.M, F, m->tab, m->tm, a);
