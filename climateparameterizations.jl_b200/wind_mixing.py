@@ -266,6 +266,12 @@ def train_NDE(uw_NN: Chain, vw_NN: Chain, wT_NN: Chain, data: ProfileData, tstep
                              100 * grad / total, stage, i + 1, len(optimizers), epoch, epochs, it, maxiters)
                     record.losses.append(losses)
                     record.totals.append(total)
+                    if FILE_PATH is not None:  # write_data_NDE_training inside cb (:364-366): the networks at the evaluated theta
+                        from . import data_writing
+                        data_writing.write_data_NDE_training(
+                            FILE_PATH, losses, loss_scalings, NN_constructions["uw"](theta_before[NN_ranges["uw"]]),
+                            NN_constructions["vw"](theta_before[NN_ranges["vw"]]), NN_constructions["wT"](theta_before[NN_ranges["wT"]]),
+                            stage, opt)
                     if callback is not None:
                         callback(theta_before, total, losses, loss_scalings)
                 m_, v_, bp_ = model.adam_state()

@@ -157,3 +157,27 @@ def test_coarse_grain_face_preserves_end_points_and_block_means():
     z = np.arange(1.0, 102.0)            # N = 101, n = 12: non-integer ratio -> rounded windows
     zc = coarse_grain(z, 12, Face)
     assert zc[0] == 1.0 and zc[-1] == 101.0 and np.all(np.diff(zc) > 0)
+
+
+def test_training_history_file_keeps_the_reference_layout(tmp_path):
+    """data_writing.py mirrors wind_mixing/src/data_writing.jl:1-78: same group hierarchy and 1-based counts per stage."""
+    from cpz_b200 import data_writing as dw
+    from cpz_b200.flux import ADAM, Chain, Dense, destructure
+    rng = np.random.default_rng(0)
+    nets = [Chain(Dense(96, 5, "mish", rng=rng), Dense(5, 31, rng=rng)) for _ in range(3)]
+    opts = [ADAM(3e-4), ADAM(1e-4)]
+    path = str(tmp_path / "history.npz")
+    dw.write_metadata_NDE_training(path, ["wind_-5e-4_cooling_3e-8_new"], [2, 2], [[0, 100]], {"ν₀": 1e-4, "Pr": 1.0}, opts, *nets)
+    scal = {k: 1.0 for k in dw.LOSS_KEYS}
+    for it in range(3):
+        losses = {k: float(it + 1 + i) for i, k in enumerate(dw.LOSS_KEYS)}
+        c = dw.write_data_NDE_training(path, losses, scal, *nets, 1, opts[0], state={"m": np.zeros(3), "v": np.ones(3), "beta_pow": [0.9, 0.999]})
+        assert c == it + 1
+    assert dw.write_data_NDE_training(path, losses, scal, *nets, 2, opts[1]) == 1  # a new stage starts at 1
+    h = dw.read_training_history(path)
+    assert float(h["training_data/loss/total/1/2"]) == sum(2 + i for i in range(6))
+    assert float(h["training_data/loss/profile/1/1"]) == 1 + 2 + 3 and float(h["training_data/loss/gradient/1/1"]) == 4 + 5 + 6
+    np.testing.assert_array_equal(h["training_data/neural_network/uw/1/3/theta"], destructure(nets[0])[0])
+    assert list(h["training_info/uw_neural_network/sizes"]) == [96, 5, 31]
+    assert float(h["training_data/optimizer/η/2/1"]) == 1e-4 and "training_info/loss_scalings/∂T∂z" in h
+    np.testing.assert_allclose(dw.loss_series(path, "T", 1), [3.0, 4.0, 5.0])
