@@ -33,7 +33,7 @@ struct ClosureUvtArgs {
 };
 
 struct ClosureUvtSmem {
-  int w, st, xin, arena, cp, model, total_floats;
+  int w, st, xin, arena, cp, nu, model, total_floats;
 };
 __host__ __device__ inline ClosureUvtSmem closure_uvt_smem_layout(const ModelD& M, int CT) {
   ClosureUvtSmem L;
@@ -43,9 +43,22 @@ __host__ __device__ inline ClosureUvtSmem closure_uvt_smem_layout(const ModelD& 
   L.xin = o; o += 3 * M.Nz * CT;    // scaled NN input; after the MLP: Thomas d'
   L.arena = o; o += M.arena_floats * CT;
   L.cp = o; o += 3 * M.Nz * CT;     // Thomas c'
+  L.nu = o; o += 3 * M.Nz * CT;     // face diffusivities of each field (face f of column c at [q][f][c]; face 0 unused)
   L.model = o; o += (int)((sizeof(ModelD) + 15) / 16) * 4;
   L.total_floats = o + 4;
   return L;
+}
+
+__device__ __forceinline__ float uvt_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// a / b for the Thomas pivots (|b| >= 1): MUFU.RCP, one Newton step on the reciprocal, one residual correction of the quotient.
+// Besides being ~4x shorter than the IEEE division sequence, this keeps ptxas' division slow-path subroutines out of this
+// 255-register kernel: with them, two lanes of the temperature warp returned NaN on B200 (same source with a debug printf
+// compiled in was clean; not understood further).
+__device__ __forceinline__ float uvt_div(float a, float b) {
+  float r = uvt_rcp(b);
+  r = fmaf(r, fmaf(-b, r, 1.f), r);
+  const float q = a * r;
+  return fmaf(r, fmaf(-b, q, a), q);
 }
 
 template <int CT, int NT, bool WS>
@@ -59,6 +72,7 @@ __global__ void __launch_bounds__(NT, 1) closure_uvt_kernel(const __grid_constan
   float* xin = smem + L.xin;
   float* arena = smem + L.arena;
   float* cp = smem + L.cp;
+  float* nus = smem + L.nu;
   const int N = M.Nz;
   if (WS) load_weights_smem<NT>(M, wsm, a.theta);
   __syncthreads();
@@ -94,29 +108,31 @@ __global__ void __launch_bounds__(NT, 1) closure_uvt_kernel(const __grid_constan
       a.dzf[((size_t)q * N + k) * a.ncol + col0 + c] = (hi - lo) * cd.inv_dz;
     }
     __syncthreads();  // the d' sweep below reuses xin
-    // backward-Euler mPP step: one thread per (field, column)
+    // backward-Euler mPP step: one thread per (field, column). The thread first evaluates its field's diffusivity on the 31
+    // interior faces of its column (independent evaluations, kept in its own shared-memory column), then runs the recurrence.
     if (threadIdx.x < 3 * CT) {
       const int q = threadIdx.x / CT, c = threadIdx.x - q * CT;
       const float* su = st + c;
       const float* sv = st + N * CT + c;
       const float* sT = st + 2 * N * CT + c;
       const float* sq = st + q * N * CT + c;
+      float* nv = nus + q * N * CT + c;
       float* dpv = xin + q * N * CT + c;
       float* cpv = cp + q * N * CT + c;
-      // diffusivity of this thread's field on face f (between levels f-1 and f); 0 on the boundary faces
-      auto nuq = [&](int f) -> float {
-        if (f <= 0 || f >= N) return 0.f;
+      for (int f = 1; f < N; ++f) {
         const float du = (su[f * CT] - su[(f - 1) * CT]) * cd.inv_dz, dv = (sv[f * CT] - sv[(f - 1) * CT]) * cd.inv_dz;
         const float dT = (sT[f * CT] - sT[(f - 1) * CT]) * cd.inv_dz;
-        const float Ri = cd.g_alpha * dT / (du * du + dv * dv);  // IEEE: +-Inf at zero shear, NaN at 0/0 (as the reference)
+        // MUFU.RCP keeps the IEEE corner cases of the reference's division: +-Inf at zero shear, NaN at 0/0
+        const float Ri = cd.g_alpha * dT * uvt_rcp(du * du + dv * dv);
         const float nu = cd.nu0 + cd.nu_m * (0.5f * (1.f - tanhf((Ri - cd.Ric) * cd.inv_dRi)));
-        if (q < 2) return nu;
-        return (cd.ca && !(Ri > 0.f)) ? cd.kappa_ca : nu * cd.inv_Pr;
-      };
+        nv[f * CT] = q < 2 ? nu : ((cd.ca && !(Ri > 0.f)) ? cd.kappa_ca : nu * cd.inv_Pr);
+      }
+      // diffusivity on face f (between levels f-1 and f); 0 on the boundary faces
+      auto nuq = [&](int f) -> float { return (f <= 0 || f >= N) ? 0.f : nv[f * CT]; };
       float nk = nuq(0), nn1 = nuq(1);
       float diag = 1.f + cd.r * (nk + nn1);
-      float cprev = -cd.r * nn1 / diag;
-      float dprev = sq[0] / diag;
+      float cprev = uvt_div(-cd.r * nn1, diag);
+      float dprev = uvt_div(sq[0], diag);
       cpv[0] = cprev;
       dpv[0] = dprev;
       for (int k = 1; k < N; ++k) {
@@ -125,8 +141,8 @@ __global__ void __launch_bounds__(NT, 1) closure_uvt_kernel(const __grid_constan
         const float lo = -cd.r * nk;
         diag = 1.f + cd.r * (nk + nn1);
         const float den = diag - lo * cprev;
-        cprev = -cd.r * nn1 / den;
-        dprev = (sq[k * CT] - lo * dprev) / den;
+        cprev = uvt_div(-cd.r * nn1, den);
+        dprev = uvt_div(sq[k * CT] - lo * dprev, den);
         cpv[k * CT] = cprev;
         dpv[k * CT] = dprev;
       }

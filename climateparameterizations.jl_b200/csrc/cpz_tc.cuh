@@ -244,6 +244,15 @@ __device__ __forceinline__ void side_column(const SideC& C, float du, float dv, 
 // and c = 0 on lane 31, by parallel cyclic reduction — five shuffle steps, no shared memory, no serial sweep. After the step
 // with stride s every equation couples level k to k-2s and k+2s only; a coefficient that would point outside the column is
 // zero by induction, so out-of-range shuffles (which return the lane's own value) are multiplied by zero.
+// a / b from MUFU.RCP plus one Newton step on the reciprocal and one residual correction of the quotient: within an ulp of the
+// IEEE quotient for the well-scaled, diagonally dominant pivots here (|b| >= 1), at a quarter of the instructions of the
+// IEEE division sequence (which dominated the implicit step)
+__device__ __forceinline__ float div_nr(float a, float b) {
+  float r = rcp_fast(b);
+  r = fmaf(r, fmaf(-b, r, 1.f), r);
+  const float q = a * r;
+  return fmaf(r, fmaf(-b, q, a), q);
+}
 __device__ __forceinline__ float pcr32(float a, float b, float c, float d) {
 #pragma unroll
   for (int s = 1; s < 32; s <<= 1) {
@@ -251,13 +260,13 @@ __device__ __forceinline__ float pcr32(float a, float b, float c, float d) {
     const float cm = __shfl_up_sync(0xffffffffu, c, s), dm = __shfl_up_sync(0xffffffffu, d, s);
     const float ap = __shfl_down_sync(0xffffffffu, a, s), bp = __shfl_down_sync(0xffffffffu, b, s);
     const float cp = __shfl_down_sync(0xffffffffu, c, s), dp = __shfl_down_sync(0xffffffffu, d, s);
-    const float al = -a / bm, ga = -c / bp;  // IEEE: the kappa = 10 convective-adjustment rows amplify MUFU.RCP's error
+    const float al = -div_nr(a, bm), ga = -div_nr(c, bp);  // a bare MUFU.RCP is not enough: the kappa = 10 convective-adjustment rows amplify its error
     b = fmaf(al, cm, fmaf(ga, ap, b));
     d = fmaf(al, dm, fmaf(ga, dp, d));
     a = al * am;
     c = ga * cp;
   }
-  return d / b;  // IEEE division: at kappa = 10 the off-diagonals are ~100 and MUFU.RCP's error shows up in the profiles
+  return div_nr(d, b);  // at kappa = 10 the off-diagonals are ~100 and a bare MUFU.RCP's error shows up in the profiles
 }
 
 // ---- the solve kernel ---------------------------------------------------------------------------------------------
