@@ -110,14 +110,38 @@ def test_grad_T_only_ca_mpp(ctx, ncol):
     th = syn.theta_random(d, scale=0.3)
     x0, bcs = syn.columns(d, ncol)
     x0 = _unstable(x0)
-    e_l, e_g, floor, g_small, desc = _grad_check(ctx, d, th, x0, bcs, W_T)
-    e_l2, e_g2, _, g_big, _ = _grad_check(ctx, d, th, x0, bcs, W_T, env=dict(CPZ_SMALL_NCOL="0"))
-    print(f"T-only CA+mPP gradient ncol={ncol}: 4-column tiles loss {e_l:.2e} grad {e_g:.2e} | 32-column tiles loss {e_l2:.2e} grad {e_g2:.2e} "
-          f"(fp32-oracle {floor:.2e})")
-    assert "small-batch training pass" in desc
-    assert e_l <= TOL and e_l2 <= TOL
-    assert e_g <= max(TOL, floor) and e_g2 <= max(TOL, floor)
+    # default: ncol <= 32 runs one CTA per column (fc1_train_kernel); CPZ_FC1_MAX_NCOL=0 falls back to the 4-column tiles,
+    # CPZ_SMALL_NCOL=0 on top of that to the 32-column tiles
+    e_l0, e_g0, floor, g_fc1, desc = _grad_check(ctx, d, th, x0, bcs, W_T)
+    e_l, e_g, _, g_small, _ = _grad_check(ctx, d, th, x0, bcs, W_T, env=dict(CPZ_FC1_MAX_NCOL="0"))
+    e_l2, e_g2, _, g_big, _ = _grad_check(ctx, d, th, x0, bcs, W_T, env=dict(CPZ_FC1_MAX_NCOL="0", CPZ_SMALL_NCOL="0"))
+    print(f"T-only CA+mPP gradient ncol={ncol}: one CTA per column loss {e_l0:.2e} grad {e_g0:.2e} | 4-column tiles loss {e_l:.2e} grad {e_g:.2e} | "
+          f"32-column tiles loss {e_l2:.2e} grad {e_g2:.2e} (fp32-oracle {floor:.2e})")
+    assert "small-batch training pass" in desc and "one CTA per column" in desc
+    assert e_l0 <= TOL and e_l <= TOL and e_l2 <= TOL
+    assert e_g0 <= max(TOL, floor) and e_g <= max(TOL, floor) and e_g2 <= max(TOL, floor)
     assert np.linalg.norm(g_small - g_big) <= max(TOL, floor) * np.linalg.norm(g_big)
+    assert np.linalg.norm(g_fc1 - g_big) <= max(TOL, floor) * np.linalg.norm(g_big)
+
+
+@pytest.mark.parametrize("h1,h2,act,integrator,flags", [(128, 128, "relu", "tsit5", "ca+mpp"), (50, 20, "mish", "rk4", "ca"), (33, 127, "tanh", "euler", "mpp"),
+                                                      (1, 1, "swish", "tsit5", "none"), (64, 48, "leakyrelu", "tsit5", "ca+mpp")])
+def test_single_column_kernel_net_shapes_and_integrators(ctx, h1, h2, act, integrator, flags):
+    """fc1_train_kernel pads every layer to 128-wide blocks in shared memory: odd widths, every activation, every tableau,
+    final-state-only and strided saves, 1..5 columns — loss and gradient against the FP64 oracle and the tile kernels."""
+    from cpz_b200.desc import NetDesc
+    for ncol, save in ((1, 3), (5, 0)):
+        d = syn.free_convection_desc(ca="ca" in flags, mpp="mpp" in flags, n_steps=12, save_stride=save, ckpt_stride=4, integrator=integrator, net=None)
+        d.nets = [NetDesc([32, h1, h2, 31], [act, act, "identity"])]
+        th = syn.theta_random(d, scale=0.4)
+        x0, bcs = syn.columns(d, ncol)
+        x0 = _unstable(x0)
+        e_l, e_g, floor, g_fc1, desc = _grad_check(ctx, d, th, x0, bcs, W_T)
+        _, e_gt, _, g_tile, _ = _grad_check(ctx, d, th, x0, bcs, W_T, env=dict(CPZ_FC1_MAX_NCOL="0"))
+        print(f"single-column kernel {h1}x{h2} {act} {integrator} {flags} ncol={ncol} save={save}: loss {e_l:.2e} grad {e_g:.2e} (tiles {e_gt:.2e}, fp32-oracle {floor:.2e})")
+        assert "one CTA per column" in desc
+        assert e_l <= TOL and e_g <= max(TOL, 1.5 * floor)  # the FP32 oracle itself sits at 1.3e-4 on the mPP-only Euler case
+        assert np.linalg.norm(g_fc1 - g_tile) <= max(TOL, 2 * floor) * max(np.linalg.norm(g_tile), 1e-30)
 
 
 @pytest.mark.parametrize("ncol,ckpt", [(1, 3), (9, 1), (18, 9), (45, 4)])
