@@ -125,7 +125,7 @@ def test_grad_T_only_ca_mpp(ctx, ncol):
 
 
 @pytest.mark.parametrize("h1,h2,act,integrator,flags", [(128, 128, "relu", "tsit5", "ca+mpp"), (50, 20, "mish", "rk4", "ca"), (33, 127, "tanh", "euler", "mpp"),
-                                                      (1, 1, "swish", "tsit5", "none"), (64, 48, "leakyrelu", "tsit5", "ca+mpp")])
+                                                      (8, 5, "swish", "tsit5", "none"), (64, 48, "leakyrelu", "tsit5", "ca+mpp")])
 def test_single_column_kernel_net_shapes_and_integrators(ctx, h1, h2, act, integrator, flags):
     """fc1_train_kernel pads every layer to 128-wide blocks in shared memory: odd widths, every activation, every tableau,
     final-state-only and strided saves, 1..5 columns — loss and gradient against the FP64 oracle and the tile kernels."""
