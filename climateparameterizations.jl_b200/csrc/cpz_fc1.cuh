@@ -13,9 +13,9 @@
 //   * the transposed products of the delta propagation read the same weight copy with a lane skew that keeps the
 //     shared-memory banks distinct.
 // The shared-memory weight copy is zero-padded to 32 x 128, 128 x 128, 128 x 32 so that every loop has a constant trip count
-// (fully unrolled, loads ahead of the FMAs). The forward pass stores the start state of EVERY sub-step (128 B each: 2.2 MB
-// for config 1) instead of sparse checkpoints, so the reverse sweep only recomputes the stage records (stage input, z1, a1,
-// z2, a2) of the step it is about to reverse.
+// (fully unrolled, loads ahead of the FMAs). The forward pass writes the RECORD of every stage evaluation (stage input, z1,
+// a1, z2, a2: 544 floats, 226 MB for config 1) to HBM instead of sparse checkpoints; the reverse sweep streams them back one
+// sub-step ahead with cp.async into a double buffer and recomputes nothing.
 #pragma once
 #include "cpz_device.cuh"
 
@@ -36,7 +36,7 @@ struct Fc1Args {
   size_t x0_stride;
   const float* bcs;      // [ncol][2]
   const float* targets;  // [ncol][n_saved][32]
-  float* states;         // [ncol][n_sub + 1][32]: start state of every sub-step, then the final state
+  float* records;        // [ncol][n_sub * n_stages][FC1_REC]: y (32), z1 (128), a1 (128), z2 (128), a2 (128) of every stage evaluation
   float* gpart;          // [ncol][P]: d(unnormalised loss of this column)/dtheta
   float* lpart;          // [ncol][8]: squared-error sum of the T profiles at index 2
   int ncol, n_saved, n_sub;  // n_sub = n_steps * n_substeps
@@ -47,20 +47,20 @@ struct Fc1Args {
 constexpr int FC1_W1 = 0, FC1_W2 = 32 * 128, FC1_W3 = FC1_W2 + 128 * 128, FC1_B1 = FC1_W3 + 128 * 32, FC1_B2 = FC1_B1 + 128,
               FC1_B3 = FC1_B2 + 128, FC1_WTOT = FC1_B3 + 32;
 
+constexpr int FC1_REC = 544, FC1_Y = 0, FC1_Z1 = 32, FC1_A1 = 160, FC1_Z2 = 288, FC1_A2 = 416;  // floats of one stage record
+
 struct Fc1Smem {
-  int w, xs, xr, xbar, ks, yb, ys, z1, a1, z2, a2, part, d1, d2, d3, nn, total_floats;
+  int w, xs, xbar, ks, yb, rec, part, d1, d2, d3, nn, total_floats;
 };
 __host__ __device__ inline Fc1Smem fc1_smem_layout(int n_stages) {
   Fc1Smem L;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
   L.w = take(FC1_WTOT);
-  L.xs = take(32); L.xr = take(32); L.xbar = take(32);
+  L.xs = take(32); L.xbar = take(32);
   L.ks = take(n_stages * 32);   // forward: stage tendencies k_i
   L.yb = take(n_stages * 32);   // reverse: cotangents of the stage inputs
-  L.ys = take(n_stages * 32);   // stage inputs
-  L.z1 = take(n_stages * 128); L.a1 = take(n_stages * 128);
-  L.z2 = take(n_stages * 128); L.a2 = take(n_stages * 128);
+  L.rec = take(2 * n_stages * FC1_REC);  // forward: one scratch record; reverse: the records of two sub-steps (double buffer)
   L.part = take(4 * 128);       // partial sums: [4][128] or [16][32]
   L.d1 = take(128); L.d2 = take(128); L.d3 = take(32);
   L.nn = take(32);
@@ -76,15 +76,10 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
   const Fc1Smem L = fc1_smem_layout(ns);
   float* wsm = smem + L.w;
   float* xs = smem + L.xs;
-  float* xr = smem + L.xr;
   float* xbar = smem + L.xbar;
   float* ks = smem + L.ks;
   float* yb = smem + L.yb;
-  float* ys = smem + L.ys;
-  float* z1s = smem + L.z1;
-  float* a1s = smem + L.a1;
-  float* z2s = smem + L.z2;
-  float* a2s = smem + L.a2;
+  float* recs = smem + L.rec;
   float* part = smem + L.part;
   float* d1s = smem + L.d1;
   float* d2s = smem + L.d2;
@@ -124,8 +119,8 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
   __syncthreads();
 
   // ---- MLP forward at the stage input y; the pre-activations / activations go to z1o, a1o, z2o, a2o; result in nns[0..30] ----
-  auto mlp_forward = [&](const float* __restrict__ y, float* __restrict__ z1o, float* __restrict__ a1o, float* __restrict__ z2o,
-                         float* __restrict__ a2o) {
+  auto mlp_forward = [&](const float* __restrict__ y, float* __restrict__ g) {  // g: this evaluation's record in HBM
+    float* z1o = recs + FC1_Z1; float* a1o = recs + FC1_A1; float* z2o = recs + FC1_Z2; float* a2o = recs + FC1_A2;
     {  // layer 1: K = 32 split in four
       const float* w = W1 + (8 * kq4) * 128 + o128;
       const float4 y0 = reinterpret_cast<const float4*>(y + 8 * kq4)[0], y1 = reinterpret_cast<const float4*>(y + 8 * kq4)[1];
@@ -143,6 +138,7 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
         av = act_fwd(F.act1, z);
       }
       z1o[t] = z; a1o[t] = av;
+      g[FC1_Z1 + t] = z; g[FC1_A1 + t] = av;
     }
     __syncthreads();
     {  // layer 2: K = h1 (<= 128) split in four
@@ -165,6 +161,7 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
         av = act_fwd(F.act2, z);
       }
       z2o[t] = z; a2o[t] = av;
+      g[FC1_Z2 + t] = z; g[FC1_A2 + t] = av;
     }
     __syncthreads();
     {  // layer 3: 31 outputs, K = h2 split in sixteen
@@ -203,18 +200,20 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
     return -AN * (Fu - Fl);
   };
 
-  // one Runge–Kutta step from xs (in place); with RECORD the stage records stay in ys / z1s / a1s / z2s / a2s
-  auto rk_step = [&](bool record) {
+  // one Runge–Kutta step from xs (in place); the record of stage i goes to g0 + i * FC1_REC
+  auto rk_step = [&](float* g0) {
+    float* y = recs + FC1_Y;
     for (int i = 0; i < ns; ++i) {
-      float* y = ys + (record ? i : 0) * 32;
+      float* g = g0 + (size_t)i * FC1_REC;
       if (t < 32) {
         float yv = 0.f;
         for (int j = 0; j < i; ++j) yv = fmaf(tab.a[i][j], ks[j * 32 + t], yv);
-        y[t] = fmaf(hstep, yv, xs[t]);
+        yv = fmaf(hstep, yv, xs[t]);
+        y[t] = yv;
+        g[FC1_Y + t] = yv;
       }
       __syncthreads();
-      const int r = record ? i : 0;
-      mlp_forward(y, z1s + r * 128, a1s + r * 128, z2s + r * 128, a2s + r * 128);
+      mlp_forward(y, g);
       if (t < 32) ks[i * 32 + t] = tendency(y);
       __syncwarp();
     }
@@ -226,13 +225,10 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
     __syncthreads();
   };
 
-  // ---- forward pass; the start state of every sub-step goes to HBM (read back by the same thread in the reverse sweep) ------
-  float* st = a.states + (size_t)col * (a.n_sub + 1) * 32;
-  for (int r = 0; r < a.n_sub; ++r) {
-    if (t < 32) st[(size_t)r * 32 + t] = xs[t];
-    rk_step(false);
-  }
-  if (t < 32) st[(size_t)a.n_sub * 32 + t] = xs[t];
+  // ---- forward pass; every stage record goes to HBM ---------------------------------------------------------------------------
+  float* grec = a.records + (size_t)col * a.n_sub * ns * FC1_REC;
+  for (int r = 0; r < a.n_sub; ++r) rk_step(grec + (size_t)r * ns * FC1_REC);
+  __threadfence();  // the records are read back by other threads of this CTA through cp.async (L2)
 
   // ---- reverse sweep -------------------------------------------------------------------------------------------------------
   auto frame_of = [&](int step) -> int {
@@ -255,18 +251,27 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
     const int fr = frame_of(tm.n_steps);
     if (fr >= 0) loss_frame(xs, fr);
   }
-  float xnext = (t < 32 && a.n_sub > 0) ? st[(size_t)(a.n_sub - 1) * 32 + t] : 0.f;
+  // records of sub-step r -> buffer b (16-byte cp.async; the records were written by this CTA: visible after the barrier)
+  const int rec4 = ns * FC1_REC / 4;  // float4 per sub-step
+  auto prefetch = [&](int r, int b) {
+    const float4* src = reinterpret_cast<const float4*>(grec + (size_t)r * ns * FC1_REC);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(recs + (size_t)b * ns * FC1_REC);
+    for (int i4 = t; i4 < rec4; i4 += FC1_NT)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i4), "l"(src + i4) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  __syncthreads();
+  if (a.n_sub > 0) prefetch(a.n_sub - 1, 0);
   {
     for (int r = a.n_sub - 1; r >= 0; --r) {
-      __syncthreads();
-      if (t < 32) {
-        xs[t] = xnext; xr[t] = xnext;
-        if (r > 0) xnext = st[(size_t)(r - 1) * 32 + t];  // in flight during this sub-step's reverse stages
-      }
-      __syncthreads();
-      rk_step(true);  // stage records of this sub-step (xs moves on to its end state; the start state stays in xr)
+      const int b = (a.n_sub - 1 - r) & 1;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();  // buffer b complete for every thread; nobody still reads buffer b ^ 1
+      if (r > 0) prefetch(r - 1, b ^ 1);
+      const float* rb = recs + (size_t)b * ns * FC1_REC;
       for (int i = ns - 1; i >= 0; --i) {
-        const float* y = ys + i * 32;
+        const float* rec = rb + i * FC1_REC;
+        const float* y = rec + FC1_Y;
         // B0 (warp 0): kbar_i, cotangent of the face fluxes = delta3, direct part of Ybar_i through the diffusive flux
         if (t < 32) {
           float kb = tab.b[i] * xbar[t];
@@ -293,7 +298,7 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
         // B1: dW3 += a2 d3^T, db3; abar2 = W3 d3
         {
           const float d3 = d3s[o32];
-          const float* av = a2s + i * 128 + 8 * kq16;
+          const float* av = rec + FC1_A2 + 8 * kq16;
 #pragma unroll
           for (int q = 0; q < 8; ++q) acc3[q] = fmaf(av[q], d3, acc3[q]);
           if (t < 31) db3 += d3s[t];
@@ -311,7 +316,7 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
         __syncthreads();
         if (t < 128) {
           float d = 0.f;
-          if (t < h2) d = ((part[t] + part[128 + t]) + (part[256 + t] + part[384 + t])) * act_grad(F.act2, z2s[i * 128 + t]);
+          if (t < h2) d = ((part[t] + part[128 + t]) + (part[256 + t] + part[384 + t])) * act_grad(F.act2, rec[FC1_Z2 + t]);
           d2s[t] = d;
           db2 += d;
         }
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
         // B3: dW2 += a1 d2^T; abar1 = W2 d2
         {
           const float d2 = d2s[o128];
-          const float4* av = reinterpret_cast<const float4*>(a1s + i * 128 + 32 * kq4);
+          const float4* av = reinterpret_cast<const float4*>(rec + FC1_A1 + 32 * kq4);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 v = av[q];
@@ -341,7 +346,7 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
         __syncthreads();
         if (t < 128) {
           float d = 0.f;
-          if (t < h1) d = ((part[t] + part[128 + t]) + (part[256 + t] + part[384 + t])) * act_grad(F.act1, z1s[i * 128 + t]);
+          if (t < h1) d = ((part[t] + part[128 + t]) + (part[256 + t] + part[384 + t])) * act_grad(F.act1, rec[FC1_Z1 + t]);
           d1s[t] = d;
           db1 += d;
         }
@@ -371,7 +376,7 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
         xbar[t] = s;
         if (r % nsub == 0) {
           const int fr = frame_of(r / nsub);
-          if (fr >= 0) loss_frame(xr, fr);
+          if (fr >= 0) loss_frame(rb + FC1_Y, fr);  // the input of stage 0 is the sub-step's start state
         }
       }
     }

@@ -46,7 +46,8 @@ bool fc1_eligible(const cpz_model* m, size_t ncol) {
   Fc1D F;
   if (!fc1_plan(m, F)) return false;
   if (m->tab.n_stages > CPZ_MAX_STAGES) return false;
-  if (ncol * ((size_t)m->tm.n_steps * m->tm.n_substeps + 1) * 128 > ((size_t)2 << 30)) return false;  // stored sub-step states
+  // stage records of the whole solve (config 1: 226 MB per column)
+  if (ncol * (size_t)m->tm.n_steps * m->tm.n_substeps * m->tab.n_stages * FC1_REC * sizeof(float) > ((size_t)8 << 30)) return false;
   const Fc1Smem L = fc1_smem_layout(m->tab.n_stages);
   return (size_t)L.total_floats * sizeof(float) <= m->ctx->smem_optin;
 }
@@ -60,11 +61,11 @@ int loss_grad_fc1(cpz_model* m, const float* x0, const float* bcs, const float* 
   const int P = F.P;
   const int n_sub = m->tm.n_steps * m->tm.n_substeps;
   int rc;
-  if ((rc = fc1_ensure(m->b_ckpt, ncol * (size_t)(n_sub + 1) * 32))) return rc;
+  if ((rc = fc1_ensure(m->b_ckpt, ncol * (size_t)n_sub * m->tab.n_stages * FC1_REC))) return rc;
   if ((rc = fc1_ensure(m->b_part, ncol * ((size_t)P + 8)))) return rc;
   Fc1Args a{};
   a.theta = m->d_theta; a.x0 = x0; a.x0_stride = 0; a.bcs = bcs; a.targets = targets;
-  a.states = m->b_ckpt.p; a.gpart = m->b_part.p; a.lpart = m->b_part.p + ncol * (size_t)P;
+  a.records = m->b_ckpt.p; a.gpart = m->b_part.p; a.lpart = m->b_part.p + ncol * (size_t)P;
   a.ncol = (int)ncol; a.n_saved = n_saved; a.n_sub = n_sub; a.wT = wT; a.inv_prof = inv_prof;
   const Fc1Smem L = fc1_smem_layout(m->tab.n_stages);
   const size_t smem = (size_t)L.total_floats * sizeof(float);
