@@ -90,6 +90,7 @@ struct AdjTcArgs {
   AuxD aux;
   int ncol, n_saved;
   int first;             // last segment of the solve: xbar starts from the loss cotangent of the final frame
+  int split;             // two CTAs per tile: CTA b sweeps column group b & 1 of tile b >> 1 (lpart is then indexed by CTA)
   int seg_step0, seg_steps;
   float w[6];
   float inv_prof, inv_grad;
@@ -179,7 +180,8 @@ __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_tcb + L.misc + 64);
   float* red = reinterpret_cast<float*>(smem_tcb + L.misc + 128);  // [16 warps][2]
   float* w3s = reinterpret_cast<float*>(smem_tcb + L.w3);          // [net][j][32]: W3_net[j][o] at o
-  const int tile = blockIdx.x, col0 = tile * TC_CT;
+  const bool active = !a.split || g == (int)(blockIdx.x & 1);
+  const int tile = a.split ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, col0 = tile * TC_CT;
   const int cg0 = 16 * g + 8 * h;
 
   for (int i = tid; i < L.total / 16; i += TC_NT) reinterpret_cast<float4*>(smem_tcb)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_const
     }
   };
   float* xb_g = a.xbar + ((size_t)tile * 96 + 32 * qd + lane) * TC_CT + cg0;
-  if (qd < 3) {
+  if (qd < 3 && active) {
     if (a.first) {
       const float* src = a.xN + (size_t)tile * a.xN_stride + (size_t)(32 * qd + lane) * TC_CT + cg0;
       const float4 p0 = __ldcg(reinterpret_cast<const float4*>(src)), p1 = __ldcg(reinterpret_cast<const float4*>(src) + 1);
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_const
       xbar[0] = p0.x; xbar[1] = p0.y; xbar[2] = p0.z; xbar[3] = p0.w; xbar[4] = p1.x; xbar[5] = p1.y; xbar[6] = p1.z; xbar[7] = p1.w;
     }
   }
-  if (a.first) {
+  if (a.first && active) {
     const int fr = frame_of(tm.n_steps);
     if (fr >= 0) loss_frame(X, fr);
   }
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_const
   const bool d2valid = d2row < 3 * h2;
   const int d2q = d2valid ? d2row / h2 : 0, d2o = d2row - d2q * h2;
   bool have_X = false;  // X already holds the next stage's input (fetched while the previous stage's last MMAs ran)
-  for (int rr = R - 1; rr >= 0; --rr) {
+  for (int rr = active ? R - 1 : -1; rr >= 0; --rr) {
     const int nstep = a.seg_step0 + rr / nsub, sub = rr % nsub;
 #pragma unroll 1
     for (int i = ns - 1; i >= 0; --i) {
@@ -520,7 +522,7 @@ __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_const
       if (fr >= 0) loss_frame(X, fr);
     }
   }
-  if (qd < 3) {
+  if (qd < 3 && active) {
     reinterpret_cast<float4*>(xb_g)[0] = make_float4(xbar[0], xbar[1], xbar[2], xbar[3]);
     reinterpret_cast<float4*>(xb_g)[1] = make_float4(xbar[4], xbar[5], xbar[6], xbar[7]);
   }
@@ -534,7 +536,7 @@ __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_const
     float s = 0.f;
     for (int w = 0; w < TC_NT / 32; ++w)
       if ((w & 3) == q) s += red[2 * w + kind];
-    a.lpart[(size_t)tile * 8 + tid] += s;
+    a.lpart[(size_t)blockIdx.x * 8 + tid] += s;
   }
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512));
 }

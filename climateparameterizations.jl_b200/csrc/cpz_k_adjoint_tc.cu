@@ -45,12 +45,12 @@ bool adjoint_tc_eligible(cpz_model* m, std::string* why_out) {
 }
 
 template <int ACT>
-static int launch_reverse_t(cpz_model* m, const TcD& T, const TcB& B, const AdjTcArgs& aa, const TimeD& tm, int n_tiles, const WgradArgs& wa,
+static int launch_reverse_t(cpz_model* m, const TcD& T, const TcB& B, const AdjTcArgs& aa, const TimeD& tm, int n_ctas, const WgradArgs& wa,
                             int wg_grid, size_t wg_smem, bool ref) {
   const TcBSmem L = tc_bwd_smem_layout(B, m->tab.n_stages);
   auto kern = adjoint_tc_kernel<ACT>;
   CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-  kern<<<n_tiles, TC_NT, L.total, m->ctx->stream>>>(m->fwd.M, T, B, m->tab, tm, aa);
+  kern<<<n_ctas, TC_NT, L.total, m->ctx->stream>>>(m->fwd.M, T, B, m->tab, tm, aa);
   CPZ_CUDA(cudaGetLastError());
   m->ctx->launches++;
   if (ref) {
@@ -94,11 +94,16 @@ int loss_grad_tc(cpz_model* m, const float* x0, const float* bcs, const float* Q
   if ((rc = ensure_buf(m->b_bwimg, (size_t)B.n_wcols * 128))) return rc;
   const bool ref = getenv("CPZ_WGRAD_REF") != nullptr;
   const int sms = m->ctx->sm_count > 0 ? m->ctx->sm_count : 148;
+  // few tiles (config 3 on 4 or 8 GPUs: 72 / 36 tiles): one column group per CTA, two CTAs per tile, so that the forward
+  // pass with records and the reverse sweep use twice the SMs and a group does not share its SM (CPZ_TC_SPLIT=0 disables)
+  const char* split_env = getenv("CPZ_TC_SPLIT");
+  const int split = (split_env ? atoi(split_env) != 0 : 2 * n_tiles <= sms) ? 1 : 0;
+  const int n_ctas = n_tiles * (split ? 2 : 1);
   // reverse launches: as many steps as 4 GB of d records hold
   const int rs = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_steps, ((size_t)1 << 30) / std::max<size_t>(d_step, 1)));
   const int wg_grid = ref ? 1 : (int)std::min<size_t>((size_t)sms, (size_t)n_tiles * epst);
   // [xbar: n_tiles*96*32][lpart: n_tiles*8][accumulator images: wg_grid*WG_COLS*128]
-  const size_t f_xbar = (size_t)n_tiles * S * 32, f_lp = (size_t)n_tiles * 8, f_img = (size_t)wg_grid * WG_COLS * 128;
+  const size_t f_xbar = (size_t)n_tiles * S * 32, f_lp = (size_t)n_ctas * 8, f_img = (size_t)wg_grid * WG_COLS * 128;
   if ((rc = ensure_buf(m->b_tcadj, f_xbar + f_lp + f_img))) return rc;
   // record segment length from the memory budget
   size_t budget;  // floats for the x / z records
@@ -151,6 +156,7 @@ int loss_grad_tc(cpz_model* m, const float* x0, const float* bcs, const float* Q
   fa.ncol = (int)ncol; fa.n_saved = n_saved; fa.n_ckpt = n_ckpt; fa.rhs_only = 0;
   fa.aux = A;
   fa.aux.ev_skip = s_last * epst;
+  fa.split = split;
   if ((rc = launch_solve_tc(m, fa))) return rc > 0 ? fail(CPZ_ERR_INVALID, "tcgen05 forward solve not eligible") : rc;
 
   tc_bwd_image_kernel<<<(B.n_wcols * 128 + 255) / 256, 256, 0, st>>>(T, B, m->d_theta, m->b_bwimg.p);
@@ -169,6 +175,7 @@ int loss_grad_tc(cpz_model* m, const float* x0, const float* bcs, const float* Q
       sa.x0_tile = m->b_ckpt.p + (size_t)(a0 / cs) * SL; sa.x0_tile_stride = (size_t)n_ckpt * SL;
       sa.aux = A;
       sa.aux.ev_skip = 0;
+      sa.split = split;
       m->tm = tm_full;
       m->tm.step0 = tm_full.step0 + a0;
       m->tm.n_steps = a1 - a0;
@@ -185,15 +192,15 @@ int loss_grad_tc(cpz_model* m, const float* x0, const float* bcs, const float* Q
       aa.xbar = xbar; aa.lpart = lpart; aa.aux = A;
       aa.aux.ev0 = (n0 - a0) * epst;
       aa.ncol = (int)ncol; aa.n_saved = n_saved; aa.first = n1 == n_steps ? 1 : 0;
-      aa.seg_step0 = n0; aa.seg_steps = n1 - n0;
+      aa.seg_step0 = n0; aa.seg_steps = n1 - n0; aa.split = split;
       for (int q = 0; q < 6; ++q) aa.w[q] = loss_w[q];
       aa.inv_prof = inv_prof; aa.inv_grad = inv_grad;
       WgradArgs wa{};
       wa.aux = aa.aux; wa.n_tiles = n_tiles; wa.n_e = (n1 - n0) * epst; wa.part = img;
       const bool mish = T.act1 == T.act2 && T.act1 == ACT_MISH, relu = T.act1 == T.act2 && T.act1 == ACT_RELU;
-      if (mish) rc = launch_reverse_t<ACT_MISH>(m, T, B, aa, tm_full, n_tiles, wa, wg_grid, wg_smem, ref);
-      else if (relu) rc = launch_reverse_t<ACT_RELU>(m, T, B, aa, tm_full, n_tiles, wa, wg_grid, wg_smem, ref);
-      else rc = launch_reverse_t<-1>(m, T, B, aa, tm_full, n_tiles, wa, wg_grid, wg_smem, ref);
+      if (mish) rc = launch_reverse_t<ACT_MISH>(m, T, B, aa, tm_full, n_ctas, wa, wg_grid, wg_smem, ref);
+      else if (relu) rc = launch_reverse_t<ACT_RELU>(m, T, B, aa, tm_full, n_ctas, wa, wg_grid, wg_smem, ref);
+      else rc = launch_reverse_t<-1>(m, T, B, aa, tm_full, n_ctas, wa, wg_grid, wg_smem, ref);
       if (rc) return rc;
     }
   }
@@ -202,7 +209,7 @@ int loss_grad_tc(cpz_model* m, const float* x0, const float* bcs, const float* Q
   CPZ_CUDA(cudaGetLastError());
   m->ctx->launches++;
   *lpart_out = lpart;
-  *n_lpart = n_tiles;
+  *n_lpart = n_ctas;
   return CPZ_OK;
 }
 

@@ -119,7 +119,7 @@ static int launch_tc_t(cpz_model* m, const TcD& T, const SolveArgs& a, const TcA
     kern = solve_tc_kernel<ACT, K3S, false, false, 8, false, true>;
   }
   CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-  const int n_tiles = seven ? t28 : t32;
+  const int n_tiles = (seven ? t28 : t32) * ((aux && a.split) ? 2 : 1);  // split segment pass: two CTAs per tile
   if (getenv("CPZ_TC_PROF") != nullptr && !a.rhs_only && !seven && !aux && !(m->desc.flags & CPZ_FLAG_IMPLICIT_DIFFUSION)) {  // debug: per-phase cycle counters of CTA 0
     auto pk = solve_tc_kernel<ACT, K3S, true>;
     CPZ_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));

@@ -43,6 +43,7 @@ struct SolveArgs {
   const float* x0_tile;      // tcgen05 solve only: start state in the checkpoint layout, tile t at x0_tile + t*x0_tile_stride ([S][32]); overrides x0
   size_t x0_tile_stride;
   AuxD aux;                  // tcgen05 solve only: aux.x != null stores X_i, z1, z2 of every stage evaluation (segment pass of the adjoint)
+  int split;                 // tcgen05 segment pass only: two CTAs per 32-column tile, CTA b integrates column group b & 1 of tile b >> 1
 };
 
 #define CPZ_PROF_BEGIN() const long long prof_t0__ = (a.prof && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0

@@ -291,7 +291,11 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
   const uint32_t gbase = sbase + g * L.grp_bytes;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_tc + L.misc) + g;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_tc + L.misc + 64);
-  const int tile = blockIdx.x, col0 = tile * (4 * CPT);
+  // split mode (segment pass of the adjoint with few tiles): CTA b runs only column group b & 1 of tile b >> 1, so that a batch
+  // of n tiles spreads over 2 n SMs and a group has the SM's pipes to itself; the other group's warps skip the time loop
+  const bool split = AUX && a.split != 0;
+  const bool active = !split || g == (int)(blockIdx.x & 1);
+  const int tile = split ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, col0 = tile * (4 * CPT);
   const int cg0 = 2 * CPT * g + CPT * h;  // first of this thread's CPT columns inside the tile
 
   // ---- prologue: zero shared memory, barriers, TMEM allocation, weights -> TMEM ----
@@ -649,7 +653,7 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
         if (col < a.ncol) a.dxdt[(size_t)col * 96 + 32 * qd + lane] = dx[r];
       }
     }
-  } else {
+  } else if (active) {
     const float hstep = tm.dt / (float)tm.n_substeps;
     const int ns = tab.n_stages;
     int frame = 0, ci = 0;
@@ -675,7 +679,7 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
     write_X();
     // start the second column group roughly half an RHS evaluation late so that its epilogues overlap the first group's
     // MMAs; contention for the tensor pipe keeps the two apart afterwards
-    if (g == 1 && ta.stagger_ns > 0) __nanosleep(ta.stagger_ns);
+    if (g == 1 && ta.stagger_ns > 0 && !split) __nanosleep(ta.stagger_ns);
     for (int n = 0; n < tm.n_steps; ++n) {
       for (int sub = 0; sub < tm.n_substeps; ++sub) {
         const float tbase = tm.t0 + (float)(tm.step0 + n) * tm.dt + (float)sub * hstep;
