@@ -501,6 +501,7 @@ def main():
                 for k in ("CPZ_ADJ_AUX_GB", "CPZ_NO_TC_ADJ"):
                     os.environ.pop(k, None)
                 os.environ.update(env)
+                os.environ["CPZ_VERBOSE"] = "1"  # the library reports its record-segment policy (columns, GB, segments) on stderr
                 d3 = syn.wind_mixing_desc(variant=RHS_TRAIN, net="uvT_small", n_steps=NSTEPS, save_stride=9, ckpt_stride=9)
                 m3 = engine.Model(ctx, d3, syn.theta_init(d3, seed=42, scale=1e-5))
                 adj_desc = [ln for ln in m3.describe().splitlines() if ln.startswith("adjoint kernels")]
@@ -538,7 +539,7 @@ def main():
                                  "record_traffic_bytes_per_colstep": rec_bytes,
                                  "hbm_frac_record_traffic": (rec_bytes * (hi - lo) * NSTEPS / (ms3 * 1e-3) / 1e9 / hbm_peak) if rec_bytes else None}}
                 m3.close()
-            for k in ("CPZ_ADJ_AUX_GB", "CPZ_NO_TC_ADJ"):
+            for k in ("CPZ_ADJ_AUX_GB", "CPZ_NO_TC_ADJ", "CPZ_VERBOSE"):
                 os.environ.pop(k, None)
             best = adj["tc_records_in_hbm"]
             line["adjoint"] = {

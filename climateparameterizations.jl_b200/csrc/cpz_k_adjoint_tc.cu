@@ -131,7 +131,8 @@ int loss_grad_tc(cpz_model* m, const float* x0, const float* bcs, const float* Q
     if (getenv("CPZ_VERBOSE") != nullptr && told_len != seg_len) {
       told_len = seg_len;
       fprintf(stderr, "[cpz] tensor-core adjoint: %zu columns, stage records of %d of %d steps per forward launch (%.2f GB), %d record "
-                      "segment(s), reverse launches of %d steps\n", ncol, seg_len, n_steps, (double)seg_len * xz_step * 4e-9, nrseg, rs);
+                      "segment(s), reverse launches of %d steps, %s\n", ncol, seg_len, n_steps, (double)seg_len * xz_step * 4e-9, nrseg, rs,
+              split ? "one column group per CTA (two CTAs per tile)" : "two column groups per CTA");
     }
   }
   if ((rc = ensure_buf(m->b_aux, (size_t)seg_len * xz_step + (size_t)rs * d_step))) return rc;
