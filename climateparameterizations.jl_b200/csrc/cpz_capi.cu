@@ -471,7 +471,7 @@ int cpz_solve(cpz_model* m, const float* x0, const float* bcs, const float* diur
   const TimeD tm_full = m->tm;
   const int n_frames = tm_full.save_stride > 0 ? tm_full.n_steps / tm_full.save_stride : 0;
   int n_chunks = 1;
-  if (tm_full.save_stride > 0 && tm_full.n_steps % tm_full.save_stride == 0 && n * sizeof(float) >= ((size_t)64 << 20)) n_chunks = std::min(8, n_frames / 16);
+  if (tm_full.save_stride > 0 && tm_full.n_steps % tm_full.save_stride == 0 && n * sizeof(float) >= ((size_t)64 << 20)) n_chunks = std::min(32, n_frames / 16);  // the un-overlapped tail is the last chunk's copy: 1/32 of the trajectory
   if (n_chunks > 1) {
     // The overlap needs a page-locked destination: cudaMemcpy2DAsync into pageable memory blocks the host until the copy
     // is done, so the next chunk's kernel would only be launched afterwards and chunking would be pure overhead.
