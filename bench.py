@@ -496,13 +496,18 @@ def main():
             x3 = b3 = None
             w3 = np.array([1, 1, 1, 5e-3, 5e-3, 5e-3], dtype=np.float32)
             adj = {}
-            policies = (("tc_records_in_hbm", {}, 3), ("tc_ckpt_stride_9", {"CPZ_ADJ_AUX_GB": "2"}, 2), ("fp32_simt", {"CPZ_NO_TC_ADJ": "1"}, 1))
+            policies = (("tc_records_in_hbm", {}, 3), ("tc_ckpt_stride_9", {"CPZ_ADJ_AUX_GB": "2"}, 2), ("fp32_simt", {"CPZ_NO_TC_ADJ": "1"}, 1),
+                        ("tc_implicit_diffusion", {"IMPLICIT": "1"}, 3))
             for name, env, n3 in policies:
                 for k in ("CPZ_ADJ_AUX_GB", "CPZ_NO_TC_ADJ"):
                     os.environ.pop(k, None)
-                os.environ.update(env)
+                os.environ.update({k: v for k, v in env.items() if k.startswith("CPZ_")})
                 os.environ["CPZ_VERBOSE"] = "1"  # the library reports its record-segment policy (columns, GB, segments) on stderr
                 d3 = syn.wind_mixing_desc(variant=RHS_TRAIN, net="uvT_small", n_steps=NSTEPS, save_stride=9, ckpt_stride=9)
+                if env.get("IMPLICIT"):  # the same training iteration with the diffusive flux implicit: one sub-step per step
+                    from cpz_b200.desc import FLAG_IMPLICIT_DIFFUSION
+                    d3 = syn.wind_mixing_desc(variant=RHS_TRAIN, net="uvT_small", n_steps=NSTEPS, save_stride=9, ckpt_stride=9, n_substeps=1)
+                    d3.flags |= FLAG_IMPLICIT_DIFFUSION
                 m3 = engine.Model(ctx, d3, syn.theta_init(d3, seed=42, scale=1e-5))
                 adj_desc = [ln for ln in m3.describe().splitlines() if ln.startswith("adjoint kernels")]
                 if x3 is None:
@@ -532,7 +537,7 @@ def main():
                 tf3 = 3 * mlp3 * (hi - lo) * NSTEPS / (ms3 * 1e-3) / 1e12
                 rec_bytes = d3.rhs_evals_per_step * (3 * 1224 + 2 * 1212) if name.startswith("tc") else None
                 adj[name] = {
-                    "value": NC3 * NSTEPS / (ms3 * 1e-3), "ms_per_step": ms3, "kernels": adj_desc[0] if adj_desc else None,
+                    "value": NC3 * NSTEPS / (ms3 * 1e-3), "ms_per_step": ms3, "n_substeps": d3.n_substeps, "kernels": adj_desc[0] if adj_desc else None,
                     "gpu_launches_per_step": int((ctx.launch_count - l0) / n3), "loss": float(loss3[6]),
                     "roofline": {"fp32_equiv_tflops_algorithmic": tf3, "frac_of_fp32_simt_peak": tf3 / peak_tf_max, "frac_of_bf16_tensor_peak": tf3 / bf16_peak,
                                  "hbm_frac_algorithmic_129B": 129.0 * (hi - lo) * NSTEPS / (ms3 * 1e-3) / 1e9 / hbm_peak,

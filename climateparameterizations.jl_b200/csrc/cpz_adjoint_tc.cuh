@@ -166,7 +166,8 @@ __device__ __forceinline__ void side_column_vjp(const SideC& C, float du, float 
 }
 
 // ---- reverse sweep over one checkpoint segment -----------------------------------------------------------------------
-template <int ACT>
+// IMPL: CPZ_FLAG_IMPLICIT_DIFFUSION models (the VJP of the implicit step is compiled only into this instantiation)
+template <int ACT, bool IMPL = false>
 __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_constant__ ModelD M, const __grid_constant__ TcD T,
                                                               const __grid_constant__ TcB B, const __grid_constant__ TableauD tab,
                                                               const TimeD tm, const __grid_constant__ AdjTcArgs a) {
@@ -275,7 +276,9 @@ __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_const
   const int bar_id = 1 + g;
   const float Aq = qd < 3 ? M.rc.A[qd] * M.rc.Nf : 0.f;
   const float cso = qd == 0 ? -M.rc.cor_v_s : (qd == 1 ? M.rc.cor_u_s : 0.f);  // Xbar_u += -cor_v_s kbar_v, Xbar_v += cor_u_s kbar_u
-  const int side_mode = T.side_mode;
+  // CPZ_FLAG_IMPLICIT_DIFFUSION: the Runge–Kutta stages carry no diffusive flux; the diffusivities act in the backward-Euler
+  // solve at the start of every sub-step, reversed below after the stages of the sub-step
+  const int side_mode = IMPL ? (int)SIDE_NONE : T.side_mode;
   const int K1S = B.K1 / 8, K2S = B.K2w / 8;
   const int h1 = T.h1, h2 = T.h2;
 
@@ -517,9 +520,96 @@ __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_const
         xbar[0] += p0.x; xbar[1] += p0.y; xbar[2] += p0.z; xbar[3] += p0.w; xbar[4] += p1.x; xbar[5] += p1.y; xbar[6] += p1.z; xbar[7] += p1.w;
       }
     }
-    if (sub == 0) {  // X still holds the input of stage 0 = x_n
-      const int fr = frame_of(nstep);
-      if (fr >= 0) loss_frame(X, fr);
+    if constexpr (IMPL) {
+      // ---- VJP of x' = L(nu(x))^-1 x (cpz_tc.cuh implicit_step): L is symmetric, so lambda = L^-1 xbar' with the same
+      // coefficients; rbar(face) = -(lambda_up - lambda)(x'_up - x'); Dbar = h A_q rbar goes through the VJP of the
+      // diffusivities at the INCOMING state x (record xp); xbar = lambda + the face-gradient cotangents scattered to the levels.
+      // X holds x' (the input of stage 0), xbar its cotangent.
+      float xp[8], Xq[3][8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) xp[r] = 0.f;
+      if (qd < 3) {
+        const size_t rec = (size_t)tile * (a.aux.n_eval / ns) + a.aux.ev0 / ns + rr;
+        ld8g(reinterpret_cast<float4*>(a.aux.xp + rec * (size_t)(32 * a.aux.rx)) + (size_t)(cg0 >> 2) * a.aux.rx + 32 * qd + lane, a.aux.rx, xp);
+        sts_v4(side_addr(qd, 2 * h), xp[0], xp[1], xp[2], xp[3]);
+        sts_v4(side_addr(qd, 2 * h + 1), xp[4], xp[5], xp[6], xp[7]);
+      }
+      bar_sync_named(bar_id, 256);
+      float du[8], dv[8], dT[8], lam[8], rb[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) { du[r] = 0.f; dv[r] = 0.f; dT[r] = 0.f; lam[r] = 0.f; rb[r] = 0.f; }
+      if (qd < 3) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          if (q == qd) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) Xq[q][r] = xp[r];
+          } else {
+            lds8(side_addr(q, 2 * h), side_addr(q, 2 * h + 1), Xq[q]);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          du[r] = __shfl_down_sync(0xffffffffu, Xq[0][r], 1) - Xq[0][r];
+          dv[r] = __shfl_down_sync(0xffffffffu, Xq[1][r], 1) - Xq[1][r];
+          dT[r] = __shfl_down_sync(0xffffffffu, Xq[2][r], 1) - Xq[2][r];
+          float Du = 0.f, Dv = 0.f, DT = 0.f;
+          switch (T.side_mode) {
+            case SIDE_MPP: side_column<SIDE_MPP>(T.sc, du[r], dv[r], dT[r], Du, Dv, DT); break;
+            case SIDE_MPP_CA_T: side_column<SIDE_MPP_CA_T>(T.sc, du[r], dv[r], dT[r], Du, Dv, DT); break;
+            case SIDE_MPP_CA_U: side_column<SIDE_MPP_CA_U>(T.sc, du[r], dv[r], dT[r], Du, Dv, DT); break;
+            case SIDE_CA_ONLY: side_column<SIDE_CA_ONLY>(T.sc, du[r], dv[r], dT[r], Du, Dv, DT); break;
+            default: break;
+          }
+          const float D = qd == 0 ? Du : (qd == 1 ? Dv : DT);
+          const float rup = lane == 31 ? 0.f : hstep * Aq * D;
+          float rdn = __shfl_up_sync(0xffffffffu, rup, 1);
+          if (lane == 0) rdn = 0.f;
+          lam[r] = pcr32(-rdn, 1.f + rdn + rup, -rup, xbar[r]);
+          const float lup = __shfl_down_sync(0xffffffffu, lam[r], 1), xup = __shfl_down_sync(0xffffffffu, X[r], 1);
+          rb[r] = lane == 31 ? 0.f : -hstep * Aq * (lup - lam[r]) * (xup - X[r]);  // cotangent of D_q at face lane+1
+        }
+        sts_v4(side_addr(3 + qd, 2 * h), rb[0], rb[1], rb[2], rb[3]);
+        sts_v4(side_addr(3 + qd, 2 * h + 1), rb[4], rb[5], rb[6], rb[7]);
+      }
+      bar_sync_named(bar_id, 256);
+      if (qd < 3) {
+        float Db[3][8];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          if (q == qd) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) Db[q][r] = rb[r];
+          } else {
+            lds8(side_addr(3 + q, 2 * h), side_addr(3 + q, 2 * h + 1), Db[q]);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          float Du, Dv, DT, gu = 0.f, gv = 0.f, gT = 0.f;
+          switch (T.side_mode) {
+            case SIDE_MPP: side_column_vjp<SIDE_MPP>(T.sc, du[r], dv[r], dT[r], Db[0][r], Db[1][r], Db[2][r], Du, Dv, DT, gu, gv, gT); break;
+            case SIDE_MPP_CA_T: side_column_vjp<SIDE_MPP_CA_T>(T.sc, du[r], dv[r], dT[r], Db[0][r], Db[1][r], Db[2][r], Du, Dv, DT, gu, gv, gT); break;
+            case SIDE_MPP_CA_U: side_column_vjp<SIDE_MPP_CA_U>(T.sc, du[r], dv[r], dT[r], Db[0][r], Db[1][r], Db[2][r], Du, Dv, DT, gu, gv, gT); break;
+            default: break;  // CA only: piecewise-constant diffusivity
+          }
+          float gq = qd == 0 ? gu : (qd == 1 ? gv : gT);
+          if (lane == 31) gq = 0.f;
+          float dn = __shfl_up_sync(0xffffffffu, gq, 1);
+          if (lane == 0) dn = 0.f;
+          xbar[r] = lam[r] + (dn - gq);
+        }
+      }
+      bar_sync_named(bar_id, 256);  // the side arrays are rewritten by the next sub-step's stages
+      if (sub == 0) {
+        const int fr = frame_of(nstep);
+        if (fr >= 0) loss_frame(xp, fr);  // the saved frame is the state before the step's first implicit solve
+      }
+    } else {
+      if (sub == 0) {  // X still holds the input of stage 0 = x_n
+        const int fr = frame_of(nstep);
+        if (fr >= 0) loss_frame(X, fr);
+      }
     }
   }
   if (qd < 3 && active) {

@@ -21,8 +21,8 @@ static int ensure_buf(DevBuf& b, size_t floats) {
   return CPZ_OK;
 }
 
-// The tensor-core adjoint covers what the tcgen05 forward solve covers, minus the implicit-diffusion step (its VJP lives
-// in the FP32 adjoint) and the mPP-parameter gradient. CPZ_NO_TC_ADJ=1 forces the FP32 SIMT adjoint for A/B runs.
+// The tensor-core adjoint covers what the tcgen05 forward solve covers (implicit-diffusion step included), minus the
+// mPP-parameter gradient. CPZ_NO_TC_ADJ=1 forces the FP32 SIMT adjoint for A/B runs.
 bool adjoint_tc_eligible(cpz_model* m, std::string* why_out) {
   std::string why;
   TcD T;
@@ -31,7 +31,6 @@ bool adjoint_tc_eligible(cpz_model* m, std::string* why_out) {
   if (getenv("CPZ_NO_TC") != nullptr || getenv("CPZ_NO_TC_ADJ") != nullptr) { why = "disabled by CPZ_NO_TC / CPZ_NO_TC_ADJ"; ok = false; }
   else if (getenv("CPZ_PROF") != nullptr) { why = "CPZ_PROF profiles the FP32 kernels"; ok = false; }
   else if (!tc_plan(m, T, why)) ok = false;
-  else if (m->desc.flags & CPZ_FLAG_IMPLICIT_DIFFUSION) { why = "implicit diffusion step"; ok = false; }
   else if (!tc_bwd_plan(T, B)) { why = "transposed weight images exceed tensor memory"; ok = false; }
   else {
     const TcBSmem L = tc_bwd_smem_layout(B, m->tab.n_stages);
@@ -48,7 +47,7 @@ template <int ACT>
 static int launch_reverse_t(cpz_model* m, const TcD& T, const TcB& B, const AdjTcArgs& aa, const TimeD& tm, int n_ctas, const WgradArgs& wa,
                             int wg_grid, size_t wg_smem, bool ref) {
   const TcBSmem L = tc_bwd_smem_layout(B, m->tab.n_stages);
-  auto kern = adjoint_tc_kernel<ACT>;
+  auto kern = (m->desc.flags & CPZ_FLAG_IMPLICIT_DIFFUSION) ? adjoint_tc_kernel<ACT, true> : adjoint_tc_kernel<ACT, false>;
   CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
   kern<<<n_ctas, TC_NT, L.total, m->ctx->stream>>>(m->fwd.M, T, B, m->tab, tm, aa);
   CPZ_CUDA(cudaGetLastError());
@@ -88,7 +87,10 @@ int loss_grad_tc(cpz_model* m, const float* x0, const float* bcs, const float* Q
   AuxD A{};
   tc_aux_rows(T, A);
   const size_t xz_rows = (size_t)A.rx + A.r1 + A.r2, d_rows = (size_t)A.r1 + A.r2 + A.r3;
-  const size_t xz_step = (size_t)n_tiles * epst * xz_rows * 32, d_step = (size_t)n_tiles * epst * d_rows * 32;  // floats per step
+  const bool implicit = (m->desc.flags & CPZ_FLAG_IMPLICIT_DIFFUSION) != 0;
+  // floats per step: x / z records of every stage evaluation (+ the pre-implicit state of every sub-step), d records
+  const size_t xp_step = implicit ? (size_t)n_tiles * nsub * A.rx * 32 : 0;
+  const size_t xz_step = (size_t)n_tiles * epst * xz_rows * 32 + xp_step, d_step = (size_t)n_tiles * epst * d_rows * 32;
   int rc;
   if ((rc = ensure_buf(m->b_ckpt, (size_t)n_tiles * n_ckpt * S * 32))) return rc;
   if ((rc = ensure_buf(m->b_bwimg, (size_t)B.n_wcols * 128))) return rc;
@@ -147,7 +149,9 @@ int loss_grad_tc(cpz_model* m, const float* x0, const float* bcs, const float* Q
   A.z2 = p; p += n_xz * A.r2 * 32;
   A.d1 = p; p += n_d * A.r1 * 32;
   A.d2 = p; p += n_d * A.r2 * 32;
-  A.d3 = p;
+  A.d3 = p; p += n_d * A.r3 * 32;
+  A.xp = implicit ? p : nullptr;
+  A.n_stages = ns;
   A.n_eval = seg_len * epst;
   A.n_eval_d = rs * epst;
 

@@ -114,10 +114,7 @@ static int launch_tc_t(cpz_model* m, const TcD& T, const SolveArgs& a, const TcA
                          : (seven ? solve_tc_kernel<ACT, K3S, false, false, 7> : solve_tc_kernel<ACT, K3S, false, false, 8>);
   if (aux) kern = solve_tc_kernel<ACT, K3S, false, false, 8, true>;
   const bool impl = (m->desc.flags & CPZ_FLAG_IMPLICIT_DIFFUSION) != 0 && !a.rhs_only;
-  if (impl) {
-    if (aux) return fail(CPZ_ERR_INVALID, "the tensor-core adjoint's segment pass has no implicit-diffusion step");
-    kern = solve_tc_kernel<ACT, K3S, false, false, 8, false, true>;
-  }
+  if (impl) kern = aux ? solve_tc_kernel<ACT, K3S, false, false, 8, true, true> : solve_tc_kernel<ACT, K3S, false, false, 8, false, true>;
   CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
   const int n_tiles = (seven ? t28 : t32) * ((aux && a.split) ? 2 : 1);  // split segment pass: two CTAs per tile
   if (getenv("CPZ_TC_PROF") != nullptr && !a.rhs_only && !seven && !aux && !(m->desc.flags & CPZ_FLAG_IMPLICIT_DIFFUSION)) {  // debug: per-phase cycle counters of CTA 0

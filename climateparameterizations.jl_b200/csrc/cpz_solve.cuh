@@ -15,6 +15,8 @@ namespace cpz {
 //   d1, d2: cotangents of z1, z2; d3: cotangent of the NN fluxes (row = 32*net + j, r3 = 96)   written by the reverse sweep
 struct AuxD {
   float *x, *z1, *z2, *d1, *d2, *d3;
+  float* xp;     // implicit diffusion: the state BEFORE the implicit step of every sub-step (rx rows; record of tile t, sub-step s at t*n_eval/n_stages + s)
+  int n_stages;  // stage evaluations per sub-step (xp index = evaluation index / n_stages)
   int rx, r1, r2, r3;
   int n_eval;    // stage evaluations per tile the x / z1 / z2 buffers hold (record of tile t, evaluation e at t*n_eval + e)
   int n_eval_d;  // the same for the d1 / d2 / d3 buffers (they only live from a reverse launch to its weight-gradient launch)

@@ -601,6 +601,14 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
   // cyclic reduction. The other two fields' profiles come from the full-precision stage-input copies in shared memory.
   auto implicit_step = [&](float hsub) {
     bar_sync_named(bar_id, 256);  // every field's X (= x) of this group is in shared memory
+    if constexpr (AUX) {  // the adjoint of this step needs the incoming state (its diffusivities are frozen there)
+      if (qd < 3 && ev >= 0) {
+        float4* dst = reinterpret_cast<float4*>(a.aux.xp + ((size_t)tile * (a.aux.n_eval / a.aux.n_stages) + ev / a.aux.n_stages) * (size_t)(32 * a.aux.rx)) +
+                      (size_t)(cg0 >> 2) * a.aux.rx + 32 * qd + lane;
+        dst[0] = make_float4(x[0], x[1], x[2], x[3]);
+        dst[a.aux.rx] = make_float4(x[4], x[5], x[6], x[7]);
+      }
+    }
     if (qd < 3) {
       float Xq[3][8];
 #pragma unroll

@@ -134,10 +134,18 @@ def test_implicit_gradient_uvT(ctx, ncol, variant, flags, kw, ckpt):
     d = syn.wind_mixing_desc(variant=variant, flags=flags | IMP, n_steps=12, save_stride=3, ckpt_stride=ckpt, n_substeps=1, **kw)
     th = syn.theta_random(d, scale=0.3)
     e_l, e_g, f_l, f_g = _grad_case(ctx, d, th, ncol, W_GRAD)
-    e_l2, e_g2, _, _ = _grad_case(ctx, d, th, ncol, W_GRAD, env=dict(CPZ_NO_KSTORE="1"))
-    print(f"implicit-diffusion gradient variant={variant} ncol={ncol} ckpt={ckpt}: loss {e_l:.2e} grad {e_g:.2e} (recompute path {e_g2:.2e}; fp32-oracle {f_g:.2e})")
-    assert e_l <= max(TOL, 3 * f_l) and e_l2 <= max(TOL, 3 * f_l)
-    assert e_g <= max(TOL, 3 * f_g) and e_g2 <= max(TOL, 3 * f_g)
+    # default: the tensor-core adjoint (its reverse sweep carries the VJP of the cyclic-reduction solve); CPZ_NO_TC_ADJ=1: the FP32
+    # adjoint with the tcgen05 forward pass's stored tendencies, and with CPZ_NO_KSTORE=1 on top the recomputing FP32 path
+    e_l2, e_g2, _, _ = _grad_case(ctx, d, th, ncol, W_GRAD, env=dict(CPZ_NO_TC_ADJ="1"))
+    e_l3, e_g3, _, _ = _grad_case(ctx, d, th, ncol, W_GRAD, env=dict(CPZ_NO_TC_ADJ="1", CPZ_NO_KSTORE="1"))
+    m = engine.Model(ctx, d, th)
+    desc = m.describe()
+    m.close()
+    print(f"implicit-diffusion gradient variant={variant} ncol={ncol} ckpt={ckpt}: loss {e_l:.2e} grad tensor-core {e_g:.2e} fp32 {e_g2:.2e} "
+          f"fp32 recompute {e_g3:.2e} (fp32-oracle {f_g:.2e})")
+    assert "adjoint kernels: tcgen05" in desc
+    assert e_l <= max(TOL, 3 * f_l) and e_l2 <= max(TOL, 3 * f_l) and e_l3 <= max(TOL, 3 * f_l)
+    assert e_g <= max(TOL, 3 * f_g) and e_g2 <= max(TOL, 3 * f_g) and e_g3 <= max(TOL, 3 * f_g)
 
 
 @pytest.mark.parametrize("ncol", [1, 70])
