@@ -26,6 +26,7 @@ struct ClosureUvtD {
 
 struct ClosureUvtArgs {
   const float* theta;
+  const float* wimg;  // the shared-memory weight arena as a device image (rebuilt when theta changes), or null
   const float* f[3];  // u, v, T: [Nz][Ny*Nx]
   float* dzf;         // [3][Nz][Ny*Nx]  dz_uw_NN, dz_vw_NN, dz_wT_NN
   float* out;         // [3][Nz][Ny*Nx]  u', v', T'
@@ -43,7 +44,7 @@ __host__ __device__ inline ClosureUvtSmem closure_uvt_smem_layout(const ModelD& 
   L.xin = o; o += 3 * M.Nz * CT;    // scaled NN input; after the MLP: Thomas d'
   L.arena = o; o += M.arena_floats * CT;
   L.cp = o; o += 3 * M.Nz * CT;     // Thomas c'
-  L.nu = o; o += 3 * M.Nz * CT;     // face diffusivities of each field (face f of column c at [q][f][c]; face 0 unused)
+  L.nu = o; o += 2 * M.Nz * CT;     // face diffusivities nu and nu_T (face f of column c at [f][c]; face 0 unused)
   L.model = o; o += (int)((sizeof(ModelD) + 15) / 16) * 4;
   L.total_floats = o + 4;
   return L;
@@ -74,7 +75,13 @@ __global__ void __launch_bounds__(NT, 1) closure_uvt_kernel(const __grid_constan
   float* cp = smem + L.cp;
   float* nus = smem + L.nu;
   const int N = M.Nz;
-  if (WS) load_weights_smem<NT>(M, wsm, a.theta);
+  if (WS) {
+    if (a.wimg != nullptr) {  // one coalesced copy of the prebuilt arena instead of the per-element gather (17 % of a call)
+      for (int i = threadIdx.x; i < M.smem_w_floats; i += NT) wsm[i] = __ldg(a.wimg + i);
+    } else {
+      load_weights_smem<NT>(M, wsm, a.theta);
+    }
+  }
   __syncthreads();
   PhaseCache pc;
   build_phase_cache<WS, CT, NT>(M, pc);
@@ -108,25 +115,26 @@ __global__ void __launch_bounds__(NT, 1) closure_uvt_kernel(const __grid_constan
       a.dzf[((size_t)q * N + k) * a.ncol + col0 + c] = (hi - lo) * cd.inv_dz;
     }
     __syncthreads();  // the d' sweep below reuses xin
-    // backward-Euler mPP step: one thread per (field, column). The thread first evaluates its field's diffusivity on the 31
-    // interior faces of its column (independent evaluations, kept in its own shared-memory column), then runs the recurrence.
+    // face diffusivities nu and nu_T of every interior face, all threads (the Thomas sweeps below only run the recurrence)
+    for (int i = threadIdx.x; i < (N - 1) * CT; i += NT) {
+      const int f = 1 + i / CT, c = i - (f - 1) * CT;
+      const float du = (st[f * CT + c] - st[(f - 1) * CT + c]) * cd.inv_dz;
+      const float dv = (st[(N + f) * CT + c] - st[(N + f - 1) * CT + c]) * cd.inv_dz;
+      const float dT = (st[(2 * N + f) * CT + c] - st[(2 * N + f - 1) * CT + c]) * cd.inv_dz;
+      // MUFU.RCP keeps the IEEE corner cases of the reference's division: +-Inf at zero shear, NaN at 0/0
+      const float Ri = cd.g_alpha * dT * uvt_rcp(du * du + dv * dv);
+      const float nu = cd.nu0 + cd.nu_m * (0.5f * (1.f - tanhf((Ri - cd.Ric) * cd.inv_dRi)));
+      nus[f * CT + c] = nu;
+      nus[(N + f) * CT + c] = (cd.ca && !(Ri > 0.f)) ? cd.kappa_ca : nu * cd.inv_Pr;
+    }
+    __syncthreads();
+    // backward-Euler mPP step: one thread per (field, column)
     if (threadIdx.x < 3 * CT) {
       const int q = threadIdx.x / CT, c = threadIdx.x - q * CT;
-      const float* su = st + c;
-      const float* sv = st + N * CT + c;
-      const float* sT = st + 2 * N * CT + c;
       const float* sq = st + q * N * CT + c;
-      float* nv = nus + q * N * CT + c;
+      const float* nv = nus + (q == 2 ? N * CT : 0) + c;
       float* dpv = xin + q * N * CT + c;
       float* cpv = cp + q * N * CT + c;
-      for (int f = 1; f < N; ++f) {
-        const float du = (su[f * CT] - su[(f - 1) * CT]) * cd.inv_dz, dv = (sv[f * CT] - sv[(f - 1) * CT]) * cd.inv_dz;
-        const float dT = (sT[f * CT] - sT[(f - 1) * CT]) * cd.inv_dz;
-        // MUFU.RCP keeps the IEEE corner cases of the reference's division: +-Inf at zero shear, NaN at 0/0
-        const float Ri = cd.g_alpha * dT * uvt_rcp(du * du + dv * dv);
-        const float nu = cd.nu0 + cd.nu_m * (0.5f * (1.f - tanhf((Ri - cd.Ric) * cd.inv_dRi)));
-        nv[f * CT] = q < 2 ? nu : ((cd.ca && !(Ri > 0.f)) ? cd.kappa_ca : nu * cd.inv_Pr);
-      }
       // diffusivity on face f (between levels f-1 and f); 0 on the boundary faces
       auto nuq = [&](int f) -> float { return (f <= 0 || f >= N) ? 0.f : nv[f * CT]; };
       float nk = nuq(0), nn1 = nuq(1);

@@ -146,8 +146,32 @@ static int launch_closure_uvt_t(cpz_model* m, const ClosureUvtD& cd, const Closu
   return CPZ_OK;
 }
 
-int launch_closure_uvt(cpz_model* m, const ClosureUvtD& cd, const ClosureUvtArgs& a) {
-  if (m->fwd.M.w_in_smem) return launch_closure_uvt_t<32, 256, true>(m, cd, a);
+// the shared-memory weight arena of the FP32 MLP phases as a device image (same gather as load_weights_smem, done once per theta)
+static __global__ void __launch_bounds__(256) closure_uvt_image_kernel(const __grid_constant__ ModelD M, const float* __restrict__ theta,
+                                                                       float* __restrict__ img) {
+  load_weights_smem<256>(M, img, theta);
+}
+
+int launch_closure_uvt(cpz_model* m, const ClosureUvtD& cd, const ClosureUvtArgs& a0) {
+  ClosureUvtArgs a = a0;
+  a.wimg = nullptr;
+  if (m->fwd.M.w_in_smem) {
+    const size_t need = (size_t)m->fwd.M.smem_w_floats;
+    if (m->b_cimg.cap < need) {
+      if (m->b_cimg.p) cudaFree(m->b_cimg.p);
+      m->b_cimg.p = nullptr; m->b_cimg.cap = 0; m->cimg_ver = 0;
+      CPZ_CUDA(cudaMalloc(&m->b_cimg.p, need * sizeof(float)));
+      m->b_cimg.cap = need;
+    }
+    if (m->cimg_ver != m->theta_ver) {  // weights changed since the image was built
+      closure_uvt_image_kernel<<<1, 256, 0, m->ctx->stream>>>(m->fwd.M, a.theta, m->b_cimg.p);
+      CPZ_CUDA(cudaGetLastError());
+      m->ctx->launches++;
+      m->cimg_ver = m->theta_ver;
+    }
+    a.wimg = m->b_cimg.p;
+    return launch_closure_uvt_t<32, 256, true>(m, cd, a);
+  }
   return launch_closure_uvt_t<32, 256, false>(m, cd, a);
 }
 

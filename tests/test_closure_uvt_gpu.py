@@ -96,3 +96,19 @@ def test_oceananigans_mirror_runs_the_callback_sequence(ctx):
     print(f"embedded u/v/T run, 12 transitions: worst {worst:.1e}")
     assert worst <= 1e-5
     assert np.abs(frames[-1][2] - frames[0][2]).max() > 1e-4
+
+
+def test_closure_uvt_weight_image_follows_theta_updates(ctx):
+    """The kernel copies a cached device image of the shared-memory weight arena; cpz_set_theta must invalidate it."""
+    d = syn.wind_mixing_desc(variant=RHS_INFER)
+    u, v, T = syn.uvt_fields(d, 40, 2)
+    cd = ClosureUvtDesc(Nx=40, Ny=2, Nz=32, dz=d.H / 32, dt=60.0, uw_top=-1e-4, wT_top=1e-5)
+    th1, th2 = syn.theta_random(d, scale=0.5, seed=1), syn.theta_random(d, scale=0.5, seed=2)
+    m = engine.Model(ctx, d, th1)
+    f1, _ = m.closure_step_uvt(cd, u, v, T)
+    m.set_theta(th2)
+    f2, _ = m.closure_step_uvt(cd, u, v, T)
+    m.close()
+    r2, _ = nde.closure_step_uvt(d, t64(th2), cd, t64(u), t64(v), t64(T))
+    assert rel_inf(f2, r2.numpy()) <= 1e-5
+    assert rel_inf(f1, r2.numpy()) > 1e-3
