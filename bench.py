@@ -583,7 +583,7 @@ def main():
                 "column_steps_per_s": NSTEPS / (ms1 * 1e-3),
                 "config": {"workload": f"BASELINE config 1: single-column T-only NDE (32->128->128->31 relu), convective adjustment + mPP base, 1152 steps x {d1.n_substeps} sub-steps (Tsit5), save every 9th, MSE loss gradient wrt 24735 parameters",
                            "kernel": "fc1_train_kernel: one CTA per column (512 threads), weights in shared memory, weight gradients in registers, "
-                                     "every sub-step start state stored by the forward pass; latency-bound on ONE SM by construction"},
+                                     "stage records streamed through HBM (cp.async double buffer), nothing recomputed; latency-bound on ONE SM by construction"},
                 "loss": float(l1_d[6].item())}
             m1.close()
             try:  # the same column with the diffusive / convective-adjustment flux implicit: 1 sub-step instead of 15
