@@ -18,15 +18,37 @@ from .flux import ADAM, Chain, destructure
 LOSS_KEYS = ("u", "v", "T", "∂u∂z", "∂v∂z", "∂T∂z")
 
 
+# One open history per path: the dictionary lives in memory between calls and is written back every `flush_every` appended
+# iterations (and by flush()), so that a long run does not re-read and re-write the whole archive per iteration.
+_OPEN: Dict[str, Dict[str, np.ndarray]] = {}
+_DIRTY: Dict[str, int] = {}
+
+
 def _load(path: str) -> Dict[str, np.ndarray]:
-    with np.load(path, allow_pickle=False) as z:
-        return {k: z[k] for k in z.files}
+    path = os.path.abspath(path)
+    if path not in _OPEN:
+        with np.load(path, allow_pickle=False) as z:
+            _OPEN[path] = {k: z[k] for k in z.files}
+        _DIRTY[path] = 0
+    return _OPEN[path]
 
 
-def _store(path: str, d: Dict[str, np.ndarray]) -> None:
-    tmp = path + ".tmp.npz"
-    np.savez(tmp, **d)
-    os.replace(tmp, path)
+def _store(path: str, d: Dict[str, np.ndarray], flush_every: int = 1) -> None:
+    path = os.path.abspath(path)
+    _OPEN[path] = d
+    _DIRTY[path] = _DIRTY.get(path, 0) + 1
+    if _DIRTY[path] >= flush_every:
+        flush(path)
+
+
+def flush(path: str) -> None:
+    """Write the in-memory history of `path` to disk (atomic replace)."""
+    path = os.path.abspath(path)
+    if path in _OPEN:
+        tmp = path + ".tmp.npz"
+        np.savez(tmp, **_OPEN[path])
+        os.replace(tmp, path)
+        _DIRTY[path] = 0
 
 
 def _put_chain(d: Dict[str, np.ndarray], key: str, nn: Chain) -> None:
@@ -50,12 +72,14 @@ def write_metadata_NDE_training(FILE_PATH: str, train_files: Sequence[str], trai
     _put_chain(d, "training_info/uw_neural_network", uw_NN)
     _put_chain(d, "training_info/vw_neural_network", vw_NN)
     _put_chain(d, "training_info/wT_neural_network", wT_NN)
+    _OPEN.pop(os.path.abspath(FILE_PATH), None)
     _store(FILE_PATH, d)
 
 
 def write_data_NDE_training(FILE_PATH: str, losses: Dict[str, float], loss_scalings: Dict[str, float], uw_NN: Chain, vw_NN: Chain,
-                            wT_NN: Chain, stage, optimizer: ADAM, state: Optional[dict] = None) -> int:
-    """data_writing.jl:28-78 — appends one iteration under .../<stage>/<count>; returns count (1-based, as in the reference)."""
+                            wT_NN: Chain, stage, optimizer: ADAM, state: Optional[dict] = None, flush_every: int = 1) -> int:
+    """data_writing.jl:28-78 — appends one iteration under .../<stage>/<count>; returns count (1-based, as in the reference).
+    The archive on disk is rewritten every `flush_every` calls (1 = every call, the reference's behaviour) and by flush()."""
     d = _load(FILE_PATH)
     profile_loss = losses["u"] + losses["v"] + losses["T"]
     gradient_loss = losses["∂u∂z"] + losses["∂v∂z"] + losses["∂T∂z"]
@@ -77,13 +101,14 @@ def write_data_NDE_training(FILE_PATH: str, losses: Dict[str, float], loss_scali
     if state:
         for k in ("m", "v", "beta_pow"):
             d[f"training_data/optimizer/state/{stage}/{count}/{k}"] = np.asarray(state[k], dtype=np.float32)
-    _store(FILE_PATH, d)
+    _store(FILE_PATH, d, flush_every)
     return count
 
 
 def read_training_history(FILE_PATH: str) -> Dict[str, np.ndarray]:
     """The whole file as a path -> array dictionary (what FileIO.load gives for a JLD2 history)."""
-    return _load(FILE_PATH)
+    flush(FILE_PATH)
+    return dict(_load(FILE_PATH))
 
 
 def loss_series(FILE_PATH: str, name: str = "total", stage=1) -> np.ndarray:

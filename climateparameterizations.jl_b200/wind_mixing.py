@@ -271,7 +271,7 @@ def train_NDE(uw_NN: Chain, vw_NN: Chain, wT_NN: Chain, data: ProfileData, tstep
                         data_writing.write_data_NDE_training(
                             FILE_PATH, losses, loss_scalings, NN_constructions["uw"](theta_before[NN_ranges["uw"]]),
                             NN_constructions["vw"](theta_before[NN_ranges["vw"]]), NN_constructions["wT"](theta_before[NN_ranges["wT"]]),
-                            stage, opt)
+                            stage, opt, flush_every=25)
                     if callback is not None:
                         callback(theta_before, total, losses, loss_scalings)
                 m_, v_, bp_ = model.adam_state()
@@ -287,6 +287,9 @@ def train_NDE(uw_NN: Chain, vw_NN: Chain, wT_NN: Chain, data: ProfileData, tstep
         model.close()
         if own_ctx:
             ctx.close()
+        if FILE_PATH is not None:
+            from . import data_writing
+            data_writing.flush(FILE_PATH)
     return (NN_constructions["uw"](weights[NN_ranges["uw"]]), NN_constructions["vw"](weights[NN_ranges["vw"]]),
             NN_constructions["wT"](weights[NN_ranges["wT"]]))
 
