@@ -45,11 +45,15 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("split", ["0", "1"])
 @pytest.mark.parametrize("case", list(CASES))
-def test_tc_adjoint_matches_the_oracle(ctx, case, monkeypatch):
+def test_tc_adjoint_matches_the_oracle(ctx, case, split, monkeypatch):
+    """split = 0: two column groups per CTA (what batches above 74 tiles run); split = 1: one group per CTA, two CTAs per tile
+    (the library's choice for these small batches)."""
     mk, ncol, use_q = CASES[case]
     d = mk()
     th, x0, bcs, Q, tgt = _problem(d, ncol, use_q)
+    monkeypatch.setenv("CPZ_TC_SPLIT", split)
     m = engine.Model(ctx, d, th)
     assert "adjoint kernels: tcgen05" in m.describe()
     loss, grad = m.loss_grad(x0, bcs, tgt, W_GRAD, Q=Q)
@@ -59,7 +63,7 @@ def test_tc_adjoint_matches_the_oracle(ctx, case, monkeypatch):
     tot, comps, g = oracle_loss_grad(d, th, x0, bcs, tgt, W_GRAD, Q)
     g32 = oracle_loss_grad(d, th, x0, bcs, tgt, W_GRAD, Q, dtype=torch.float32)[2]
     e_l, e_c, e_g, e_s, f_g = abs(loss[6] - tot) / abs(tot), np.abs(loss[:6] - comps).max() / abs(tot), _rel(grad, g), _rel(grad_s, g), _rel(g32, g)
-    print(f"tc adjoint {case}: loss {e_l:.2e} comps {e_c:.2e} grad {e_g:.2e} (fp32 simt adjoint {e_s:.2e}, fp32 oracle {f_g:.2e}; tc vs simt {_rel(grad, grad_s):.2e})")
+    print(f"tc adjoint {case} split={split}: loss {e_l:.2e} comps {e_c:.2e} grad {e_g:.2e} (fp32 simt adjoint {e_s:.2e}, fp32 oracle {f_g:.2e}; tc vs simt {_rel(grad, grad_s):.2e})")
     assert np.isfinite(grad).all() and np.linalg.norm(g) > 0
     assert e_l <= TOL and e_c <= TOL
     assert e_g <= max(TOL, f_g) and e_s <= max(TOL, f_g)

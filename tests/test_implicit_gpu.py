@@ -138,6 +138,8 @@ def test_implicit_gradient_uvT(ctx, ncol, variant, flags, kw, ckpt):
     # adjoint with the tcgen05 forward pass's stored tendencies, and with CPZ_NO_KSTORE=1 on top the recomputing FP32 path
     e_l2, e_g2, _, _ = _grad_case(ctx, d, th, ncol, W_GRAD, env=dict(CPZ_NO_TC_ADJ="1"))
     e_l3, e_g3, _, _ = _grad_case(ctx, d, th, ncol, W_GRAD, env=dict(CPZ_NO_TC_ADJ="1", CPZ_NO_KSTORE="1"))
+    e_l4, e_g4, _, _ = _grad_case(ctx, d, th, ncol, W_GRAD, env=dict(CPZ_TC_SPLIT="0"))  # two column groups per CTA (large batches)
+    assert e_l4 <= max(TOL, 3 * f_l) and e_g4 <= max(TOL, 3 * f_g), (e_l4, e_g4)
     m = engine.Model(ctx, d, th)
     desc = m.describe()
     m.close()
