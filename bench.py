@@ -600,7 +600,7 @@ def main():
                 c1.record()
                 barrier()
                 line["config1"]["implicit_diffusion"] = {"value": c0.elapsed_time(c1) / 2 * 1e-3, "unit": "s", "n_substeps": 1,
-                                                         "kernel": "4-column tile kernels (FP32 SIMT forward + adjoint with the Thomas-solve VJP)",
+                                                         "kernel": "fc1_train_kernel with the implicit step and its VJP on warp 0 (cyclic reduction across the lanes)",
                                                          "loss": float(l1_d[6].item())}
                 m1i.close()
             except Exception as e:  # noqa: BLE001

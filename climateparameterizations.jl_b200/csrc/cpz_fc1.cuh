@@ -18,6 +18,7 @@
 // sub-step ahead with cp.async into a double buffer and recomputes nothing.
 #pragma once
 #include "cpz_device.cuh"
+#include "cpz_tc.cuh"  // pcr32: tridiagonal solve across the lanes of a warp
 
 namespace cpz {
 
@@ -36,6 +37,7 @@ struct Fc1Args {
   size_t x0_stride;
   const float* bcs;      // [ncol][2]
   const float* targets;  // [ncol][n_saved][32]
+  float* xp;             // implicit diffusion: [ncol][n_sub][32] state before the implicit step of every sub-step
   float* records;        // [ncol][n_sub * n_stages][FC1_REC]: y (32), z1 (128), a1 (128), z2 (128), a2 (128) of every stage evaluation
   float* gpart;          // [ncol][P]: d(unnormalised loss of this column)/dtheta
   float* lpart;          // [ncol][8]: squared-error sum of the T profiles at index 2
@@ -99,6 +101,10 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
   const float* B3 = wsm + FC1_B3;
   const float Nf = M.rc.Nf, AN = M.rc.A[2] * M.rc.Nf;
   const bool mpp = (M.flags & F_MPP) != 0, ca = (M.flags & F_CA) != 0;
+  // CPZ_FLAG_IMPLICIT_DIFFUSION: the stages carry the NN and boundary fluxes only; the diffusive / convective-adjustment flux acts
+  // in a backward-Euler solve at the start of every sub-step (warp 0: lane <-> level, cyclic reduction across the warp)
+  const bool implicit = (M.flags & F_IMPLICIT) != 0;
+  const bool mpp_e = mpp && !implicit, ca_e = ca && !implicit;
   const float hstep = tm.dt / (float)nsub;
 
   for (int i = t; i < FC1_WTOT; i += FC1_NT) {
@@ -192,17 +198,41 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
     if (lane >= 1) {
       const float G = Nf * (y[lane] - y[lane - 1]);
       Fl = nns[lane - 1];
-      if (mpp) Fl -= fc_mpp_cnu(M, G) * G;
-      if (ca) Fl -= fminf(0.f, M.rc.K_ca * G);
+      if (mpp_e) Fl -= fc_mpp_cnu(M, G) * G;
+      if (ca_e) Fl -= fminf(0.f, M.rc.K_ca * G);
     }
     float Fu = __shfl_down_sync(0xffffffffu, Fl, 1);
     if (lane == 31) Fu = bc1;
     return -AN * (Fu - Fl);
   };
 
+  // diffusivity D at face lane+1 (flux -D G, G = Nf (x[lane+1] - x[lane])) and dD/dG: [mPP] c_T nu/Pr + [CA] K [G < 0]
+  auto face_D = [&](float G, float& dDdG) -> float {
+    float D = 0.f;
+    dDdG = 0.f;
+    if (mpp) D += fc_mpp_cnu(M, G, &dDdG);
+    if (ca && M.rc.K_ca * G < 0.f) D += M.rc.K_ca;
+    return D;
+  };
+  // x <- L(D(x))^-1 x over one sub-step (warp 0); the incoming state goes to gxp for the reverse sweep
+  auto implicit_fwd = [&](float* gxp) {
+    const float xv = xs[lane];
+    gxp[lane] = xv;
+    float dd;
+    const float G = Nf * (__shfl_down_sync(0xffffffffu, xv, 1) - xv);
+    const float rup = lane == 31 ? 0.f : hstep * AN * Nf * face_D(G, dd);
+    float rdn = __shfl_up_sync(0xffffffffu, rup, 1);
+    if (lane == 0) rdn = 0.f;
+    xs[lane] = pcr32(-rdn, 1.f + rdn + rup, -rup, xv);
+  };
+
   // one Runge–Kutta step from xs (in place); the record of stage i goes to g0 + i * FC1_REC
-  auto rk_step = [&](float* g0) {
+  auto rk_step = [&](float* g0, float* gxp) {
     float* y = recs + FC1_Y;
+    if (implicit) {
+      if (t < 32) implicit_fwd(gxp);
+      __syncwarp();
+    }
     for (int i = 0; i < ns; ++i) {
       float* g = g0 + (size_t)i * FC1_REC;
       if (t < 32) {
@@ -227,7 +257,8 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
 
   // ---- forward pass; every stage record goes to HBM ---------------------------------------------------------------------------
   float* grec = a.records + (size_t)col * a.n_sub * ns * FC1_REC;
-  for (int r = 0; r < a.n_sub; ++r) rk_step(grec + (size_t)r * ns * FC1_REC);
+  float* gxp0 = implicit ? a.xp + (size_t)col * a.n_sub * 32 : nullptr;
+  for (int r = 0; r < a.n_sub; ++r) rk_step(grec + (size_t)r * ns * FC1_REC, implicit ? gxp0 + (size_t)r * 32 : nullptr);
   __threadfence();  // the records are read back by other threads of this CTA through cp.async (L2)
 
   // ---- reverse sweep -------------------------------------------------------------------------------------------------------
@@ -262,6 +293,7 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
   };
   __syncthreads();
   if (a.n_sub > 0) prefetch(a.n_sub - 1, 0);
+  float xp_next = (implicit && t < 32 && a.n_sub > 0) ? gxp0[(size_t)(a.n_sub - 1) * 32 + t] : 0.f;  // written by this thread
   {
     for (int r = a.n_sub - 1; r >= 0; --r) {
       const int b = (a.n_sub - 1 - r) & 1;
@@ -269,6 +301,8 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
       __syncthreads();  // buffer b complete for every thread; nobody still reads buffer b ^ 1
       if (r > 0) prefetch(r - 1, b ^ 1);
       const float* rb = recs + (size_t)b * ns * FC1_REC;
+      const float xp_cur = xp_next;
+      if (implicit && t < 32 && r > 0) xp_next = gxp0[(size_t)(r - 1) * 32 + t];  // in flight during this sub-step's stages
       for (int i = ns - 1; i >= 0; --i) {
         const float* rec = rb + i * FC1_REC;
         const float* y = rec + FC1_Y;
@@ -283,8 +317,8 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
             Fb = -AN * (kbm - kb);
             const float G = Nf * (y[lane] - y[lane - 1]);
             float dFdG = 0.f;
-            if (mpp) { float dc; const float c = fc_mpp_cnu(M, G, &dc); dFdG -= fmaf(G, dc, c); }
-            if (ca && M.rc.K_ca * G < 0.f) dFdG -= M.rc.K_ca;
+            if (mpp_e) { float dc; const float c = fc_mpp_cnu(M, G, &dc); dFdG -= fmaf(G, dc, c); }
+            if (ca_e && M.rc.K_ca * G < 0.f) dFdG -= M.rc.K_ca;
             Gb = Fb * dFdG;
             d3s[lane - 1] = Fb;
           } else {
@@ -374,9 +408,33 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
         float s = xbar[t];
         for (int i = 0; i < ns; ++i) s += yb[i * 32 + t];
         xbar[t] = s;
+        if (implicit) {
+          // VJP of x' = L(D(x))^-1 x: L is symmetric, lambda = L^-1 xbar' with the same coefficients; cotangent of r at face
+          // lane+1 is -(lambda_up - lambda)(x'_up - x'); through D(G) to the level differences of the incoming state x
+          const float xq = rb[FC1_Y + lane];  // x' = the input of stage 0
+          float dd;
+          const float G = Nf * (__shfl_down_sync(0xffffffffu, xp_cur, 1) - xp_cur);
+          const float rup = lane == 31 ? 0.f : hstep * AN * Nf * face_D(G, dd);
+          float rdn = __shfl_up_sync(0xffffffffu, rup, 1);
+          if (lane == 0) rdn = 0.f;
+          const float lam = pcr32(-rdn, 1.f + rdn + rup, -rup, s);
+          const float lup = __shfl_down_sync(0xffffffffu, lam, 1), xup = __shfl_down_sync(0xffffffffu, xq, 1);
+          const float Gb = lane == 31 ? 0.f : -(lup - lam) * (xup - xq) * hstep * AN * Nf * dd;  // cotangent of G at face lane+1
+          float Gdn = __shfl_up_sync(0xffffffffu, Gb, 1);
+          if (lane == 0) Gdn = 0.f;
+          xbar[t] = lam + Nf * (Gdn - Gb);
+        }
         if (r % nsub == 0) {
           const int fr = frame_of(r / nsub);
-          if (fr >= 0) loss_frame(rb + FC1_Y, fr);  // the input of stage 0 is the sub-step's start state
+          if (fr >= 0) {
+            if (implicit) {  // the saved frame is the state before the step's first implicit solve
+              const float d = xp_cur - __ldg(a.targets + ((size_t)col * a.n_saved + fr) * 32 + lane);
+              sse = fmaf(d, d, sse);
+              xbar[lane] += a.wT * 2.f * a.inv_prof * d;
+            } else {
+              loss_frame(rb + FC1_Y, fr);  // the input of stage 0 is the sub-step's start state
+            }
+          }
         }
       }
     }

@@ -19,7 +19,7 @@ static int fc1_ensure(DevBuf& b, size_t floats) {
 static bool fc1_plan(const cpz_model* m, Fc1D& F) {
   const cpz_model_desc& d = m->desc;
   if (d.variant != CPZ_RHS_FREE_CONVECTION || d.n_fields != 1 || d.n_nets != 1 || d.Nz != 32) return false;
-  if (d.flags & ~(uint32_t)(CPZ_FLAG_MPP | CPZ_FLAG_CA)) return false;  // explicit diffusion, constant boundary fluxes
+  if (d.flags & ~(uint32_t)(CPZ_FLAG_MPP | CPZ_FLAG_CA | CPZ_FLAG_IMPLICIT_DIFFUSION)) return false;  // constant boundary fluxes
   const cpz_net_desc& n = d.nets[0];
   if (n.n_layers != 3 || n.sizes[0] != 32 || n.sizes[3] != 31 || n.act[2] != CPZ_ACT_IDENTITY) return false;
   if (n.sizes[1] < 1 || n.sizes[1] > 128 || n.sizes[2] < 1 || n.sizes[2] > 128) return false;
@@ -63,9 +63,11 @@ int loss_grad_fc1(cpz_model* m, const float* x0, const float* bcs, const float* 
   int rc;
   if ((rc = fc1_ensure(m->b_ckpt, ncol * (size_t)n_sub * m->tab.n_stages * FC1_REC))) return rc;
   if ((rc = fc1_ensure(m->b_part, ncol * ((size_t)P + 8)))) return rc;
+  const bool implicit = (m->desc.flags & CPZ_FLAG_IMPLICIT_DIFFUSION) != 0;
+  if (implicit && (rc = fc1_ensure(m->b_scr, ncol * (size_t)n_sub * 32))) return rc;
   Fc1Args a{};
   a.theta = m->d_theta; a.x0 = x0; a.x0_stride = 0; a.bcs = bcs; a.targets = targets;
-  a.records = m->b_ckpt.p; a.gpart = m->b_part.p; a.lpart = m->b_part.p + ncol * (size_t)P;
+  a.records = m->b_ckpt.p; a.xp = implicit ? m->b_scr.p : nullptr; a.gpart = m->b_part.p; a.lpart = m->b_part.p + ncol * (size_t)P;
   a.ncol = (int)ncol; a.n_saved = n_saved; a.n_sub = n_sub; a.wT = wT; a.inv_prof = inv_prof;
   const Fc1Smem L = fc1_smem_layout(m->tab.n_stages);
   const size_t smem = (size_t)L.total_floats * sizeof(float);

@@ -125,7 +125,8 @@ def test_grad_T_only_ca_mpp(ctx, ncol):
 
 
 @pytest.mark.parametrize("h1,h2,act,integrator,flags", [(128, 128, "relu", "tsit5", "ca+mpp"), (50, 20, "mish", "rk4", "ca"), (33, 127, "tanh", "euler", "mpp"),
-                                                      (8, 5, "swish", "tsit5", "none"), (64, 48, "leakyrelu", "tsit5", "ca+mpp")])
+                                                      (8, 5, "swish", "tsit5", "none"), (64, 48, "leakyrelu", "tsit5", "ca+mpp"),
+                                                      (128, 128, "relu", "tsit5", "ca+mpp+implicit"), (50, 20, "mish", "euler", "ca+implicit")])
 def test_single_column_kernel_net_shapes_and_integrators(ctx, h1, h2, act, integrator, flags):
     """fc1_train_kernel pads every layer to 128-wide blocks in shared memory: odd widths, every activation, every tableau,
     final-state-only and strided saves, 1..5 columns — loss and gradient against the FP64 oracle and the tile kernels."""
@@ -133,6 +134,10 @@ def test_single_column_kernel_net_shapes_and_integrators(ctx, h1, h2, act, integ
     for ncol, save in ((1, 3), (5, 0)):
         d = syn.free_convection_desc(ca="ca" in flags, mpp="mpp" in flags, n_steps=12, save_stride=save, ckpt_stride=4, integrator=integrator, net=None)
         d.nets = [NetDesc([32, h1, h2, 31], [act, act, "identity"])]
+        if "implicit" in flags:  # backward-Euler diffusion / convective adjustment at the start of every (single) sub-step
+            from cpz_b200.desc import FLAG_IMPLICIT_DIFFUSION
+            d.flags |= FLAG_IMPLICIT_DIFFUSION
+            d.n_substeps = 1
         th = syn.theta_random(d, scale=0.4)
         x0, bcs = syn.columns(d, ncol)
         x0 = _unstable(x0)
@@ -140,6 +145,11 @@ def test_single_column_kernel_net_shapes_and_integrators(ctx, h1, h2, act, integ
         _, e_gt, _, g_tile, _ = _grad_check(ctx, d, th, x0, bcs, W_T, env=dict(CPZ_FC1_MAX_NCOL="0"))
         print(f"single-column kernel {h1}x{h2} {act} {integrator} {flags} ncol={ncol} save={save}: loss {e_l:.2e} grad {e_g:.2e} (tiles {e_gt:.2e}, fp32-oracle {floor:.2e})")
         assert "one CTA per column" in desc
+        if "implicit" in flags:
+            # the K = 10 convective-adjustment rows make the backward-Euler solve ill-conditioned in FP32 (cyclic reduction here,
+            # Thomas sweeps in the tile kernels, both a few 1e-4 from the FP64 oracle): the implicit tests' 3 x floor rule
+            assert e_l <= 5e-4 and e_g <= max(TOL, 3 * floor) and e_gt <= max(TOL, 3 * floor)
+            continue
         assert e_l <= TOL and e_g <= max(TOL, 1.5 * floor)  # the FP32 oracle itself sits at 1.3e-4 on the mPP-only Euler case
         assert np.linalg.norm(g_fc1 - g_tile) <= max(TOL, 2 * floor) * max(np.linalg.norm(g_tile), 1e-30)
 
