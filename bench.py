@@ -764,7 +764,7 @@ def main():
                 "value": nx6 * ny6 * world / (us6 * 1e-6), "us_per_call": us6, "scaling": "weak",
                 "config": {"workload": "512 x 64 x 32 slab per GPU, three 96->50->20->31 mish nets, convective adjustment on; u, v, T read, "
                                        "three dz-flux fields and u', v', T' written every call (NDE_oceananigans.jl:380-405)",
-                           "kernel": "closure_uvt_kernel: FP32 SIMT MLP phases on 32-column tiles + one Thomas sweep per (field, column)"},
+                           "kernel": "solve_tc_kernel<CLOSURE>: one tcgen05 MLP evaluation + cyclic-reduction mPP step per 32-column tile, persistent CTAs (FP32 SIMT closure_uvt_kernel for other net shapes)"},
                 "roofline": {"bound": "hbm", "achieved": gb6, "peak": hbm_peak, "unit": "GB/s", "frac": gb6 / hbm_peak,
                              "algorithmic_bytes_per_colstep": 1152}}
             m6.close()

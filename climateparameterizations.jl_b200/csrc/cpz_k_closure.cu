@@ -153,6 +153,10 @@ static __global__ void __launch_bounds__(256) closure_uvt_image_kernel(const __g
 }
 
 int launch_closure_uvt(cpz_model* m, const ClosureUvtD& cd, const ClosureUvtArgs& a0) {
+  {  // production nets at Nz = 32: the tcgen05 kernel's CLOSURE instantiation (CPZ_NO_TC=1 keeps the FP32 SIMT kernel below)
+    const int rc = launch_closure_uvt_tc(m, cd, a0);
+    if (rc != 1) return rc;
+  }
   ClosureUvtArgs a = a0;
   a.wimg = nullptr;
   if (m->fwd.M.w_in_smem) {

@@ -171,6 +171,64 @@ int launch_solve_nnfree(cpz_model* m, const SolveArgs& a) {
   return CPZ_OK;
 }
 
+// u/v/T closure step on the tcgen05 kernel (CLOSURE instantiation): the MLP evaluation is solve_tc_kernel's, the implicit mPP
+// step its cyclic reduction; the face diffusivities are evaluated in the model's scaled variables with constants rebuilt for
+// the closure (no eps, kappa_ca, the closure's own dz). 1 = not eligible (the FP32 SIMT kernel takes it).
+template <int ACT, int K3S>
+static int launch_closure_tc_t(cpz_model* m, const ModelD& M2, const TcD& T, const TcArgs& ta, int grid) {
+  const TcSmem L = tc_smem_layout(T, m->tab.n_stages);
+  auto kern = solve_tc_kernel<ACT, K3S, false, false, 8, false, false, true>;
+  CPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  SolveArgs a{};
+  a.theta = m->d_theta;
+  kern<<<grid, TC_NT, L.total, m->ctx->stream>>>(M2, T, m->tab, m->tm, a, ta);
+  CPZ_CUDA(cudaGetLastError());
+  m->ctx->launches++;
+  return CPZ_OK;
+}
+
+int launch_closure_uvt_tc(cpz_model* m, const ClosureUvtD& cd, const ClosureUvtArgs& ca) {
+  if (getenv("CPZ_NO_TC") != nullptr) return 1;
+  TcD T;
+  std::string why;
+  if (!tc_plan(m, T, why)) return 1;
+  // the model description with the closure's rules: inference-style Richardson number (no eps), mPP always on, the
+  // convective-adjustment switch on dT/dz with kappa_ca, B_z built from the closure's own dz
+  ModelD M2 = m->fwd.M;
+  M2.variant = RHS_INFER;
+  M2.flags = F_MPP | (cd.ca ? F_CA : 0);
+  M2.rc.kappa = cd.kappa_ca;
+  M2.rc.BzC = (float)((double)cd.g_alpha * (double)cd.sig[2] * (double)M2.rc.Nf / (double)cd.inv_dz);
+  M2.rc.nu0 = cd.nu0; M2.rc.nu_m = cd.nu_m; M2.rc.Ric = cd.Ric; M2.rc.inv_dRi = cd.inv_dRi; M2.rc.inv_Pr = cd.inv_Pr;
+  side_constants(M2, T.side_mode, T.sc);
+  const size_t need = (size_t)TC_WCOLS * 128;
+  if (m->b_wimg.cap < need) {
+    if (m->b_wimg.p) cudaFree(m->b_wimg.p);
+    m->b_wimg.p = nullptr; m->b_wimg.cap = 0;
+    CPZ_CUDA(cudaMalloc(&m->b_wimg.p, need * sizeof(float)));
+    m->b_wimg.cap = need;
+  }
+  tc_image_kernel<<<(int)((need + 255) / 256), 256, 0, m->ctx->stream>>>(T, ca.theta, m->b_wimg.p);
+  CPZ_CUDA(cudaGetLastError());
+  m->ctx->launches++;
+  TcArgs ta{};
+  ta.wimg = m->b_wimg.p; ta.stagger_ns = 0;
+  TcClosure& C = ta.cl;
+  for (int q = 0; q < 3; ++q) { C.f[q] = ca.f[q]; C.top[q] = cd.top[q]; C.inv_sig[q] = cd.inv_sig[q]; }
+  for (int i = 0; i < 6; ++i) { C.mu[i] = cd.mu[i]; C.sig[i] = cd.sig[i]; }
+  C.dzf = ca.dzf; C.out = ca.out; C.ncol = ca.ncol; C.n_tiles = (ca.ncol + TC_CT - 1) / TC_CT;
+  C.inv_dz = cd.inv_dz;
+  // hsub A_q N (N c_q nu) = hsub tau N^2 nu / H^2 must equal dt nu / dz^2 = cd.r nu
+  const double H = m->desc.H, tau = m->desc.tau, N = M2.rc.Nf;
+  C.hsub = (float)((double)cd.r * H * H / (tau * N * N));
+  const int sms = m->ctx->sm_count > 0 ? m->ctx->sm_count : 148;
+  const int grid = std::min(C.n_tiles, sms);
+  const bool k3 = T.k3_steps == 3;
+  if (T.act1 == T.act2 && T.act1 == ACT_MISH) return k3 ? launch_closure_tc_t<ACT_MISH, 3>(m, M2, T, ta, grid) : launch_closure_tc_t<ACT_MISH, 4>(m, M2, T, ta, grid);
+  if (T.act1 == T.act2 && T.act1 == ACT_RELU) return k3 ? launch_closure_tc_t<ACT_RELU, 3>(m, M2, T, ta, grid) : launch_closure_tc_t<ACT_RELU, 4>(m, M2, T, ta, grid);
+  return k3 ? launch_closure_tc_t<-1, 3>(m, M2, T, ta, grid) : launch_closure_tc_t<-1, 4>(m, M2, T, ta, grid);
+}
+
 // true when launch_solve_tc would take a checkpointing solve of this model
 bool solve_tc_eligible(cpz_model* m) {
   if (getenv("CPZ_NO_TC") != nullptr) return false;
@@ -196,7 +254,8 @@ int launch_solve_tc(cpz_model* m, const SolveArgs& a) {
   CPZ_CUDA(cudaGetLastError());
   m->ctx->launches++;
   const char* stg = getenv("CPZ_TC_STAGGER");
-  TcArgs ta{m->b_wimg.p, stg ? atoi(stg) : 1600};
+  TcArgs ta{};
+  ta.wimg = m->b_wimg.p; ta.stagger_ns = stg ? atoi(stg) : 1600;
   const bool k3 = T.k3_steps == 3;
   if (T.act1 == T.act2 && T.act1 == ACT_MISH) return k3 ? launch_tc_t<ACT_MISH, 3>(m, T, a, ta) : launch_tc_t<ACT_MISH, 4>(m, T, a, ta);
   if (T.act1 == T.act2 && T.act1 == ACT_RELU) return k3 ? launch_tc_t<ACT_RELU, 3>(m, T, a, ta) : launch_tc_t<ACT_RELU, 4>(m, T, a, ta);

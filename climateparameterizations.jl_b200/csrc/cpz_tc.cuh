@@ -176,9 +176,24 @@ __device__ __forceinline__ void lds8(uint32_t a0, uint32_t a1, float* v) {
   v[0] = p.x; v[1] = p.y; v[2] = p.z; v[3] = p.w; v[4] = q.x; v[5] = q.y; v[6] = q.z; v[7] = q.w;
 }
 
+// CLOSURE mode of solve_tc_kernel: per-step closure of the u/v/T NDE embedded in a host ocean model (cpz_closure_uvt.cuh;
+// wind_mixing/src/NDE_oceananigans.jl:380-405) — dimensional (Nx,Ny,Nz) fields in, d/dz of the NN fluxes and the implicitly
+// diffused state out, one MLP evaluation and one implicit step per column
+struct TcClosure {
+  const float* f[3];   // u, v, T: [Nz][ncol]
+  float* dzf;          // [3][Nz][ncol]
+  float* out;          // [3][Nz][ncol]
+  int ncol, n_tiles;
+  float inv_dz;
+  float hsub;          // non-dimensional sub-step with hsub A_q N (N c_q nu) = dt nu / dz^2
+  float top[3];        // uw, vw, wT at the surface face
+  float mu[6], sig[6], inv_sig[3];
+};
+
 struct TcArgs {
   const float* wimg;  // [TC_WCOLS][128] TMEM image of the weights (hi/lo split), built by tc_image_kernel
   int stagger_ns;     // start delay of the second column group
+  TcClosure cl;       // CLOSURE instantiation only
 };
 
 // ---- weight image ---------------------------------------------------------------------------------------------
@@ -279,7 +294,8 @@ static __device__ __noinline__ float tc_diurnal_top(const ModelD& M, float Q, fl
 //      z1, z2 as operand-image records (AuxD, cpz_solve.cuh); the start state may come from a checkpoint (a.x0_tile)
 // IMPL: CPZ_FLAG_IMPLICIT_DIFFUSION solves — the backward-Euler step is compiled only into this instantiation (inlined into the
 //       explicit kernel it cost 6 registers + a spill and 8 % of the config-2 time)
-template <int ACT, int K3S, bool PROF = false, bool RHS_ONLY = false, int CPT = 8, bool AUX = false, bool IMPL = false>
+// CLOSURE: persistent over 32-column tiles of three (Nx,Ny,Nz) fields (TcArgs::cl): one MLP evaluation + one implicit step per tile
+template <int ACT, int K3S, bool PROF = false, bool RHS_ONLY = false, int CPT = 8, bool AUX = false, bool IMPL = false, bool CLOSURE = false>
 __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constant__ ModelD M, const __grid_constant__ TcD T,
                                                             const __grid_constant__ TableauD tab, const TimeD tm,
                                                             const SolveArgs a, const TcArgs ta) {
@@ -343,7 +359,7 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
 #pragma unroll
   for (int r = 0; r < 8; ++r) { x[r] = 0.f; X[r] = 0.f; bnd[r] = 0.f; }
 #pragma unroll
-  for (int r = 0; r < CPT; ++r) {
+  for (int r = 0; r < (CLOSURE ? 0 : CPT); ++r) {
     const int col = min(col0 + cg0 + r, a.ncol - 1);
     if (AUX && a.x0_tile != nullptr) x[r] = qd < 3 ? __ldcg(a.x0_tile + (size_t)tile * a.x0_tile_stride + (size_t)(32 * qd + lane) * TC_CT + cg0 + r) : 0.f;
     else x[r] = qd < 3 ? __ldg(a.x0 + (size_t)col * (a.x0_stride ? a.x0_stride : (size_t)96) + 32 * qd + lane) : 0.f;
@@ -382,7 +398,7 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
   // CPZ_FLAG_IMPLICIT_DIFFUSION: the Runge–Kutta stages see no diffusive flux (mode NONE); the diffusivities act in the
   // backward-Euler solve at the start of every sub-step instead
   const bool implicit = (M.flags & F_IMPLICIT) != 0;
-  const int side_mode = implicit ? (int)SIDE_NONE : T.side_mode;
+  const int side_mode = (implicit || CLOSURE) ? (int)SIDE_NONE : T.side_mode;
 
   auto write_X = [&]() {  // stage input -> B operand (hi/lo) + full-precision copy
     if (qd < 3) {
@@ -581,6 +597,11 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
       // ---- layer 3 epilogue + stencil: flux at face lane+1, divergence at level lane ----
       float nn[8], D[8];
       tmem_ld8(dg + ((uint32_t)(32 * qd) << 16) + 16 * qd + 8 * h, nn);
+      if constexpr (CLOSURE) {  // the caller wants the scaled NN flux at face lane+1 itself
+#pragma unroll
+        for (int r = 0; r < CPT; ++r) dx[r] = nn[r] + b3;
+        return;
+      }
       lds8(side_addr(qd, 2 * h), side_addr(qd, 2 * h + 1), D);
 #pragma unroll
       for (int r = 0; r < CPT; ++r) {
@@ -620,7 +641,7 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
           lds8(side_addr(3 + q, 2 * h), side_addr(3 + q, 2 * h + 1), Xq[q]);
         }
       }
-      float rup[8];
+      float rup[8], dqs[8];
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         const float du = __shfl_down_sync(0xffffffffu, Xq[0][r], 1) - Xq[0][r];
@@ -636,12 +657,16 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
         }
         const float D = qd == 0 ? Du : (qd == 1 ? Dv : DT);   // Nz c_q nu_q at face lane+1
         rup[r] = lane == 31 ? 0.f : hsub * Aq * D;
+        dqs[r] = qd == 0 ? du : (qd == 1 ? dv : dT);          // x[lane+1] - x[lane] of this thread's field
       }
+      // incremental form: L (x' - x) = x - L x = r_up (x_up - x) - r_dn (x - x_dn); the small right-hand side keeps the
+      // rounding of the solve relative to the increment, not to the state
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         float rdn = __shfl_up_sync(0xffffffffu, rup[r], 1);
+        const float dqdn = __shfl_up_sync(0xffffffffu, dqs[r], 1);
         if (lane == 0) rdn = 0.f;
-        x[r] = pcr32(-rdn, 1.f + rdn + rup[r], -rup[r], x[r]);
+        x[r] += pcr32(-rdn, 1.f + rdn + rup[r], -rup[r], rup[r] * dqs[r] - rdn * dqdn);
         X[r] = x[r];
       }
     }
@@ -649,7 +674,55 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
     write_X();
   };
 
-  if constexpr (RHS_ONLY) {
+  if constexpr (CLOSURE) {
+    const TcClosure& C = ta.cl;
+    for (int tl = blockIdx.x; tl < C.n_tiles; tl += gridDim.x) {
+      const int c0 = tl * TC_CT + cg0;  // first of this thread's 8 columns
+      float xin[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) xin[r] = 0.f;
+      if (qd < 3) {
+        const float* src = C.f[qd] + (size_t)lane * C.ncol;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          xin[r] = __ldg(src + min(c0 + r, C.ncol - 1));
+          x[r] = (xin[r] - C.mu[qd]) * C.inv_sig[qd];
+          X[r] = x[r];
+        }
+      }
+      write_X();
+      float nnv[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) nnv[r] = 0.f;
+      rhs_eval(0.f, nnv);
+      if (qd < 3) {
+        // F = [0; unscaled NN - shift; top flux] on the faces, d/dz at the centres (NDE_oceananigans.jl:281-344): the momentum
+        // chains subtract inv(scaling) of the already unscaled first output (:292,301), the temperature chain the first output
+        const float sg = C.sig[3 + qd], mu = C.mu[3 + qd];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const float un = fmaf(sg, nnv[r], mu);
+          const float u0 = __shfl_sync(0xffffffffu, un, 0);
+          const float shift = qd < 2 ? fmaf(sg, u0, mu) : u0;
+          const float Fup = lane == 31 ? C.top[qd] : un - shift;
+          float Fdn = __shfl_up_sync(0xffffffffu, Fup, 1);
+          if (lane == 0) Fdn = 0.f;
+          if (c0 + r < C.ncol) C.dzf[((size_t)qd * 32 + lane) * C.ncol + c0 + r] = (Fup - Fdn) * C.inv_dz;
+        }
+      }
+      implicit_step(C.hsub);  // x <- L(nu(x))^-1 x in the scaled variables (same system as modified_pacanowski_philander!, :61-101)
+      if (qd < 3) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          // the dimensional input plus the unscaled increment (not sigma x' + mu: the scale / unscale round trip of the state
+          // would cost an order of magnitude in accuracy)
+          float o = fmaf(C.sig[qd], x[r] - (xin[r] - C.mu[qd]) * C.inv_sig[qd], xin[r]);
+          if (qd == 2 && lane == 0) o = xin[r];  // T'[bottom] = T_bottom (:93)
+          if (c0 + r < C.ncol) C.out[((size_t)qd * 32 + lane) * C.ncol + c0 + r] = o;
+        }
+      }
+    }
+  } else if constexpr (RHS_ONLY) {
     write_X();
     float dx[8];
     dx[7] = 0.f;
