@@ -676,20 +676,46 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
 
   if constexpr (CLOSURE) {
     const TcClosure& C = ta.cl;
+    // 16-byte accesses when every row of every field is 16-byte aligned
+    const bool vec4 = (C.ncol & 3) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(C.f[0]) | reinterpret_cast<uintptr_t>(C.f[1]) | reinterpret_cast<uintptr_t>(C.f[2]) |
+                        reinterpret_cast<uintptr_t>(C.dzf) | reinterpret_cast<uintptr_t>(C.out)) & 15) == 0;
+    // this thread's 8 columns of field qd at level lane, tile tl2 (clamped past the last column)
+    auto load_tile = [&](int tl2, float* dst) {
+      const int c = tl2 * TC_CT + cg0;
+      const float* src = C.f[qd < 3 ? qd : 0] + (size_t)lane * C.ncol;
+      if (vec4 && c + 7 < C.ncol) {
+        const float4 p0 = __ldg(reinterpret_cast<const float4*>(src + c)), p1 = __ldg(reinterpret_cast<const float4*>(src + c) + 1);
+        dst[0] = p0.x; dst[1] = p0.y; dst[2] = p0.z; dst[3] = p0.w; dst[4] = p1.x; dst[5] = p1.y; dst[6] = p1.z; dst[7] = p1.w;
+      } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) dst[r] = __ldg(src + min(c + r, C.ncol - 1));
+      }
+    };
+    auto store_tile = [&](float* base, int c, const float* v) {
+      float* dst = base + ((size_t)qd * 32 + lane) * C.ncol + c;
+      if (vec4 && c + 7 < C.ncol) {
+        reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          if (c + r < C.ncol) dst[r] = v[r];
+      }
+    };
+    float xnx[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) xnx[r] = 0.f;
+    if (qd < 3 && (int)blockIdx.x < C.n_tiles) load_tile(blockIdx.x, xnx);
     for (int tl = blockIdx.x; tl < C.n_tiles; tl += gridDim.x) {
       const int c0 = tl * TC_CT + cg0;  // first of this thread's 8 columns
       float xin[8];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) xin[r] = 0.f;
-      if (qd < 3) {
-        const float* src = C.f[qd] + (size_t)lane * C.ncol;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          xin[r] = __ldg(src + min(c0 + r, C.ncol - 1));
-          x[r] = (xin[r] - C.mu[qd]) * C.inv_sig[qd];
-          X[r] = x[r];
-        }
+      for (int r = 0; r < 8; ++r) {
+        xin[r] = xnx[r];
+        if (qd < 3) { x[r] = (xin[r] - C.mu[qd]) * C.inv_sig[qd]; X[r] = x[r]; }
       }
+      if (qd < 3 && tl + (int)gridDim.x < C.n_tiles) load_tile(tl + gridDim.x, xnx);  // in flight during this tile's evaluation
       write_X();
       float nnv[8];
 #pragma unroll
@@ -707,19 +733,22 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
           const float Fup = lane == 31 ? C.top[qd] : un - shift;
           float Fdn = __shfl_up_sync(0xffffffffu, Fup, 1);
           if (lane == 0) Fdn = 0.f;
-          if (c0 + r < C.ncol) C.dzf[((size_t)qd * 32 + lane) * C.ncol + c0 + r] = (Fup - Fdn) * C.inv_dz;
+          nnv[r] = (Fup - Fdn) * C.inv_dz;
         }
+        store_tile(C.dzf, c0, nnv);
       }
       implicit_step(C.hsub);  // x <- L(nu(x))^-1 x in the scaled variables (same system as modified_pacanowski_philander!, :61-101)
       if (qd < 3) {
 #pragma unroll
+        float ov[8];
+#pragma unroll
         for (int r = 0; r < 8; ++r) {
           // the dimensional input plus the unscaled increment (not sigma x' + mu: the scale / unscale round trip of the state
           // would cost an order of magnitude in accuracy)
-          float o = fmaf(C.sig[qd], x[r] - (xin[r] - C.mu[qd]) * C.inv_sig[qd], xin[r]);
-          if (qd == 2 && lane == 0) o = xin[r];  // T'[bottom] = T_bottom (:93)
-          if (c0 + r < C.ncol) C.out[((size_t)qd * 32 + lane) * C.ncol + c0 + r] = o;
+          ov[r] = fmaf(C.sig[qd], x[r] - (xin[r] - C.mu[qd]) * C.inv_sig[qd], xin[r]);
+          if (qd == 2 && lane == 0) ov[r] = xin[r];  // T'[bottom] = T_bottom (:93)
         }
+        store_tile(C.out, c0, ov);
       }
     }
   } else if constexpr (RHS_ONLY) {
