@@ -60,6 +60,7 @@ struct cpz_model {
   DevBuf b_aux, b_bwimg, b_tcadj;  // tensor-core adjoint: per-stage records, transposed weight image, xbar + loss sums + accumulator images
   uint64_t theta_ver = 1;   // bumped whenever d_theta changes (set_theta, ADAM step)
   uint64_t cimg_ver = 0;    // theta_ver the closure weight image was built from
+  uint64_t wimg_ver = 0;    // theta_ver the tensor-memory weight image (b_wimg) was built from
 };
 
 namespace cpz {

@@ -207,10 +207,14 @@ int launch_closure_uvt_tc(cpz_model* m, const ClosureUvtD& cd, const ClosureUvtA
     m->b_wimg.p = nullptr; m->b_wimg.cap = 0;
     CPZ_CUDA(cudaMalloc(&m->b_wimg.p, need * sizeof(float)));
     m->b_wimg.cap = need;
+    m->wimg_ver = 0;
   }
-  tc_image_kernel<<<(int)((need + 255) / 256), 256, 0, m->ctx->stream>>>(T, ca.theta, m->b_wimg.p);
-  CPZ_CUDA(cudaGetLastError());
-  m->ctx->launches++;
+  if (m->wimg_ver != m->theta_ver || ca.theta != m->d_theta) {  // the image is a function of theta only: rebuilt when it changed
+    tc_image_kernel<<<(int)((need + 255) / 256), 256, 0, m->ctx->stream>>>(T, ca.theta, m->b_wimg.p);
+    CPZ_CUDA(cudaGetLastError());
+    m->ctx->launches++;
+    m->wimg_ver = ca.theta == m->d_theta ? m->theta_ver : 0;
+  }
   TcArgs ta{};
   ta.wimg = m->b_wimg.p; ta.stagger_ns = 0;
   TcClosure& C = ta.cl;
@@ -249,10 +253,14 @@ int launch_solve_tc(cpz_model* m, const SolveArgs& a) {
     m->b_wimg.p = nullptr; m->b_wimg.cap = 0;
     CPZ_CUDA(cudaMalloc(&m->b_wimg.p, need * sizeof(float)));
     m->b_wimg.cap = need;
+    m->wimg_ver = 0;
   }
-  tc_image_kernel<<<(int)((need + 255) / 256), 256, 0, m->ctx->stream>>>(T, a.theta, m->b_wimg.p);
-  CPZ_CUDA(cudaGetLastError());
-  m->ctx->launches++;
+  if (m->wimg_ver != m->theta_ver || a.theta != m->d_theta) {  // the image is a function of theta only: rebuilt when it changed
+    tc_image_kernel<<<(int)((need + 255) / 256), 256, 0, m->ctx->stream>>>(T, a.theta, m->b_wimg.p);
+    CPZ_CUDA(cudaGetLastError());
+    m->ctx->launches++;
+    m->wimg_ver = a.theta == m->d_theta ? m->theta_ver : 0;
+  }
   const char* stg = getenv("CPZ_TC_STAGGER");
   TcArgs ta{};
   ta.wimg = m->b_wimg.p; ta.stagger_ns = stg ? atoi(stg) : 1600;
