@@ -216,7 +216,8 @@ int launch_closure_uvt_tc(cpz_model* m, const ClosureUvtD& cd, const ClosureUvtA
     m->wimg_ver = ca.theta == m->d_theta ? m->theta_ver : 0;
   }
   TcArgs ta{};
-  ta.wimg = m->b_wimg.p; ta.stagger_ns = 0;
+  const char* cstg = getenv("CPZ_TC_CL_STAGGER");
+  ta.wimg = m->b_wimg.p; ta.stagger_ns = cstg ? atoi(cstg) : 0;
   TcClosure& C = ta.cl;
   for (int q = 0; q < 3; ++q) { C.f[q] = ca.f[q]; C.top[q] = cd.top[q]; C.inv_sig[q] = cd.inv_sig[q]; }
   for (int i = 0; i < 6; ++i) { C.mu[i] = cd.mu[i]; C.sig[i] = cd.sig[i]; }

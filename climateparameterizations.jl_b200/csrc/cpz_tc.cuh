@@ -707,6 +707,8 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
 #pragma unroll
     for (int r = 0; r < 8; ++r) xnx[r] = 0.f;
     if (qd < 3 && (int)blockIdx.x < C.n_tiles) load_tile(blockIdx.x, xnx);
+    // the second column group starts late: the groups loop independently, so one's implicit step then runs under the other's MLP
+    if (g == 1 && ta.stagger_ns > 0) __nanosleep(ta.stagger_ns);
     for (int tl = blockIdx.x; tl < C.n_tiles; tl += gridDim.x) {
       const int c0 = tl * TC_CT + cg0;  // first of this thread's 8 columns
       float xin[8];
