@@ -197,9 +197,15 @@ int cpz_solve_dev(cpz_model* m, const float* x0, const float* bcs, const float* 
  * targets: [ncol][n_saved][nf*Nz]; loss_w[6]: weights of (u,v,T,du/dz,dv/dz,dT/dz) (loss.jl:33-42);
  * loss_out[7]: the six weighted components then their sum; grad_out[P] (destructure order) or NULL for loss only.
  * With an allreduce hook set, sums are global over ranks (ncol_global = sum of ncol).
- * Device scratch kept by the model between calls: the step checkpoints, and -- when the tcgen05 solve runs and the
- * device has the room plus 8 GB to spare -- the stage tendencies of the forward pass
- * (ceil(ncol/32)*32 * n_steps * n_substeps * n_stages * nf*Nz floats; CPZ_NO_KSTORE=1 in the environment disables it). */
+ * Device scratch kept by the model between calls: the step checkpoints, and, depending on the path the model takes
+ * (cpz_model_describe names it):
+ *   - tensor-core adjoint (production u/v/T nets): per-stage records of as many steps as the free device memory minus 8 GB
+ *     holds (73 KB per column-step; all steps when they fit, otherwise one checkpoint-aligned segment at a time with
+ *     re-integration; CPZ_ADJ_AUX_GB in the environment sets the budget);
+ *   - FP32 adjoint behind the tcgen05 forward solve: the stage tendencies of the forward pass when they fit
+ *     (ceil(ncol/32)*32 * n_steps * n_substeps * n_stages * nf*Nz floats; CPZ_NO_KSTORE=1 disables it);
+ *   - single-column training kernel (T-only model, ncol <= 32): the record of every stage evaluation
+ *     (ncol * n_steps * n_substeps * n_stages * 544 floats, at most 8 GB; larger jobs take the tile kernels). */
 int cpz_loss_grad(cpz_model* m, const float* x0, const float* bcs, const float* diurnal_Q, const float* targets,
                   size_t ncol, const float* loss_w, float* loss_out, float* grad_out);
 int cpz_loss_grad_dev(cpz_model* m, const float* x0, const float* bcs, const float* diurnal_Q, const float* targets,
