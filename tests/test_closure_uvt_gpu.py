@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from cpz_b200 import engine, synthetic as syn
-from cpz_b200.desc import ClosureUvtDesc, RHS_INFER
+from cpz_b200.desc import ClosureUvtDesc, RHS_INFER, RHS_TRAIN
 from oracle import literal, nde
 from util import rel_inf, t64
 
@@ -120,3 +120,22 @@ def test_closure_uvt_weight_image_follows_theta_updates(ctx):
     r2, _ = nde.closure_step_uvt(d, t64(th2), cd, t64(u), t64(v), t64(T))
     assert rel_inf(f2, r2.numpy()) <= 1e-5
     assert rel_inf(f1, r2.numpy()) > 1e-3
+
+
+@pytest.mark.parametrize("kernel", ["tcgen05", "fp32-simt"])
+def test_closure_step_uvt_grid_spacing_and_time_step_differ_from_the_training_setup(ctx, kernel, monkeypatch):
+    """The host model's dz and dt are its own (NDE_oceananigans.jl:104,117), not H/Nz and the training step: the tcgen05 kernel
+    works in the model's scaled variables and must rebuild B_z and the non-dimensional sub-step from them."""
+    if kernel == "fp32-simt":
+        monkeypatch.setenv("CPZ_NO_TC", "1")
+    d = syn.wind_mixing_desc(variant=RHS_TRAIN)  # a training-variant description (eps on the gradients) must not leak into the closure
+    th = syn.theta_random(d, scale=0.5)
+    u, v, T = syn.uvt_fields(d, 40, 3, unstable_every=4)
+    cd = ClosureUvtDesc(Nx=40, Ny=3, Nz=32, dz=5.0, dt=600.0, uw_top=-2e-4, vw_top=1e-5, wT_top=-4e-5, convective_adjustment=True, kappa_ca=0.3)
+    dzf, out = _run(ctx, d, th, cd, u, v, T)
+    dzf_ref, out_ref = nde.closure_step_uvt(d, t64(th), cd, t64(u), t64(v), t64(T))
+    e_f, e_s = rel_inf(dzf, dzf_ref.numpy()), rel_inf(out, out_ref.numpy())
+    inc_ref = out_ref.numpy() - np.stack([u, v, T]).astype(np.float64)
+    e_i = float(np.abs(out - np.stack([u, v, T]) - inc_ref).max() / np.abs(inc_ref).max())
+    print(f"uvT closure [{kernel}] dz=5 dt=600 kappa_ca=0.3: dz_flux {e_f:.1e} state {e_s:.1e} increments {e_i:.1e}")
+    assert e_f <= 1e-5 and e_s <= 1e-5 and e_i <= 2e-4
