@@ -137,31 +137,36 @@ __global__ void __launch_bounds__(NT, 1) closure_uvt_kernel(const __grid_constan
       float* cpv = cp + q * N * CT + c;
       // diffusivity on face f (between levels f-1 and f); 0 on the boundary faces
       auto nuq = [&](int f) -> float { return (f <= 0 || f >= N) ? 0.f : nv[f * CT]; };
+      // incremental form: L (x' - x) = x - L x = r nu_k (x_{k-1} - x_k) + r nu_{k+1} (x_{k+1} - x_k); the small right-hand side keeps
+      // the rounding of the sweep relative to the increment, not to the state
       float nk = nuq(0), nn1 = nuq(1);
       float diag = 1.f + cd.r * (nk + nn1);
       float cprev = uvt_div(-cd.r * nn1, diag);
-      float dprev = uvt_div(sq[0], diag);
+      float xk = sq[0], xup = sq[CT];
+      float dprev = uvt_div(cd.r * nn1 * (xup - xk), diag);
       cpv[0] = cprev;
       dpv[0] = dprev;
       for (int k = 1; k < N; ++k) {
         nk = nn1;
         nn1 = nuq(k + 1);
+        const float xdn = xk;
+        xk = xup;
+        xup = k + 1 < N ? sq[(k + 1) * CT] : xk;
         const float lo = -cd.r * nk;
         diag = 1.f + cd.r * (nk + nn1);
         const float den = diag - lo * cprev;
         cprev = uvt_div(-cd.r * nn1, den);
-        dprev = uvt_div(sq[k * CT] - lo * dprev, den);
+        dprev = uvt_div(cd.r * (nk * (xdn - xk) + nn1 * (xup - xk)) - lo * dprev, den);
         cpv[k * CT] = cprev;
         dpv[k * CT] = dprev;
       }
-      const float bottom = sq[0];
       const bool live = col0 + c < a.ncol;
       float* o = a.out + (size_t)q * N * a.ncol + col0 + c;
-      float xn = dprev;
-      if (live) o[(size_t)(N - 1) * a.ncol] = xn;
+      float dn = dprev;  // increment of the top level
+      if (live) o[(size_t)(N - 1) * a.ncol] = sq[(N - 1) * CT] + dn;
       for (int k = N - 2; k >= 0; --k) {
-        xn = dpv[k * CT] - cpv[k * CT] * xn;
-        if (live) o[(size_t)k * a.ncol] = (q == 2 && k == 0) ? bottom : xn;  // T'[1] = T_bottom (:93)
+        dn = dpv[k * CT] - cpv[k * CT] * dn;
+        if (live) o[(size_t)k * a.ncol] = (q == 2 && k == 0) ? sq[0] : sq[k * CT] + dn;  // T'[1] = T_bottom (:93)
       }
     }
     __syncthreads();
