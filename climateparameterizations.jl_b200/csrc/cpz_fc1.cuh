@@ -219,11 +219,13 @@ __global__ void __launch_bounds__(FC1_NT, 1) fc1_train_kernel(const __grid_const
     const float xv = xs[lane];
     gxp[lane] = xv;
     float dd;
-    const float G = Nf * (__shfl_down_sync(0xffffffffu, xv, 1) - xv);
-    const float rup = lane == 31 ? 0.f : hstep * AN * Nf * face_D(G, dd);
+    const float dq = __shfl_down_sync(0xffffffffu, xv, 1) - xv;
+    const float rup = lane == 31 ? 0.f : hstep * AN * Nf * face_D(Nf * dq, dd);
     float rdn = __shfl_up_sync(0xffffffffu, rup, 1);
+    const float dqdn = __shfl_up_sync(0xffffffffu, dq, 1);
     if (lane == 0) rdn = 0.f;
-    xs[lane] = pcr32(-rdn, 1.f + rdn + rup, -rup, xv);
+    // incremental form: L (x' - x) = r_up (x_up - x) - r_dn (x - x_dn)
+    xs[lane] = xv + pcr32(-rdn, 1.f + rdn + rup, -rup, rup * dq - rdn * dqdn);
   };
 
   // one Runge–Kutta step from xs (in place); the record of stage i goes to g0 + i * FC1_REC

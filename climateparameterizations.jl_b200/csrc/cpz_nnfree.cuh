@@ -70,12 +70,15 @@ __global__ void __launch_bounds__(NF_WARPS * 32) solve_nnfree_kernel(const __gri
       float D[3];
       diffusivity(side_mode, du, dv, dT, D[0], D[1], D[2]);
       const float Aq[3] = {Au, Av, AT};
+      const float dq[3] = {du, dv, dT};
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         const float rup = lane == 31 ? 0.f : hsub * Aq[q] * D[q];
         float rdn = __shfl_up_sync(0xffffffffu, rup, 1);
+        const float dqdn = __shfl_up_sync(0xffffffffu, dq[q], 1);
         if (lane == 0) rdn = 0.f;
-        x[q][c] = pcr32(-rdn, 1.f + rdn + rup, -rup, x[q][c]);
+        // incremental form (see implicit_step in cpz_tc.cuh): L (x' - x) = r_up (x_up - x) - r_dn (x - x_dn)
+        x[q][c] += pcr32(-rdn, 1.f + rdn + rup, -rup, rup * dq[q] - rdn * dqdn);
         X[q][c] = x[q][c];
       }
     }
