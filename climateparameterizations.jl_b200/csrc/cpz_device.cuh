@@ -428,22 +428,28 @@ __device__ __noinline__ void implicit_diffusion_tile(const ModelD& M, float* __r
   for (int t = threadIdx.x; t < nf * CT; t += NT) {
     const int c = t % CT, q = t / CT;
     float* xq = x + q * N * CT + c;
-    const float* rq = r + q * N * CT + c;
+    float* rq = r + q * N * CT + c;
     float* cq = cp + q * N * CT + c;
-    float cprev = 0.f, dprev = 0.f;
+    // incremental form: L (x' - x) = x - L x = r_k (x_{k-1} - x_k) + r_{k+1} (x_{k+1} - x_k); the forward-sweep values of the
+    // increment go to the r slot of their row (already consumed), x itself is only touched by the final update
+    float cprev = 0.f, dprev = 0.f, xdn = 0.f, xk = xq[0];
     for (int k = 0; k < N; ++k) {
       const float rlo = rq[k * CT], rhi = k + 1 < N ? rq[(k + 1) * CT] : 0.f;
+      const float xup = k + 1 < N ? xq[(k + 1) * CT] : xk;
       const float den = 1.f + rlo + rhi + rlo * cprev;  // diag - lower * cp_{k-1}, lower = -rlo
       const float inv = 1.f / den;
       cprev = -rhi * inv;
-      dprev = (xq[k * CT] + rlo * dprev) * inv;
+      dprev = (rlo * (xdn - xk) + rhi * (xup - xk) + rlo * dprev) * inv;
       cq[k * CT] = cprev;
-      xq[k * CT] = dprev;
+      rq[k * CT] = dprev;
+      xdn = xk;
+      xk = xup;
     }
-    float y = xq[(N - 1) * CT];
+    float y = rq[(N - 1) * CT];
+    xq[(N - 1) * CT] += y;
     for (int k = N - 2; k >= 0; --k) {
-      y = xq[k * CT] - cq[k * CT] * y;
-      xq[k * CT] = y;
+      y = rq[k * CT] - cq[k * CT] * y;
+      xq[k * CT] += y;
     }
   }
 }
