@@ -268,8 +268,8 @@ __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_const
   const uint32_t side = gbase + L.side;
   auto side_addr = [&](int arr, int blk) { return side + (uint32_t)(((arr * 4 + blk) * 32 + lane) * 16); };
   const int tq = ((g * 2 + h) * 3 + qd) * 32 + lane;
-  const uint32_t ks_base = sbase + L.ks + (uint32_t)tq * 32;
-  const uint32_t ks_stride = (uint32_t)(TC_NG * 2 * 3 * 32) * 32;
+  const uint32_t ks_base = sbase + L.ks + (uint32_t)tq * 16;  // stage slots: [stage][column half][thread] float4 (16-byte thread stride: conflict-free 128-bit accesses)
+  const uint32_t ks_stride = (uint32_t)(TC_NG * 2 * 3 * 32) * 32, ks_half = ks_stride / 2;
   const uint32_t dg = tb + B.c_acc + 48 * g;
   const uint32_t id16 = tc_idesc(128, TC_GN);
   uint32_t parity = 0;
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_const
 #pragma unroll 1
         for (int j = i + 1; j < ns; ++j) {
           const float aji = tab.a[j][i];
-          const float4 p0 = lds_v4(ks_base + j * ks_stride), p1 = lds_v4(ks_base + j * ks_stride + 16);
+          const float4 p0 = lds_v4(ks_base + j * ks_stride), p1 = lds_v4(ks_base + j * ks_stride + ks_half);
           kb[0] = fmaf(aji, p0.x, kb[0]); kb[1] = fmaf(aji, p0.y, kb[1]); kb[2] = fmaf(aji, p0.z, kb[2]); kb[3] = fmaf(aji, p0.w, kb[3]);
           kb[4] = fmaf(aji, p1.x, kb[4]); kb[5] = fmaf(aji, p1.y, kb[5]); kb[6] = fmaf(aji, p1.z, kb[6]); kb[7] = fmaf(aji, p1.w, kb[7]);
         }
@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_const
 #pragma unroll
         for (int r = 0; r < 8; ++r) v[r] += direct[r];
         sts_v4(ks_base + i * ks_stride, v[0], v[1], v[2], v[3]);
-        sts_v4(ks_base + i * ks_stride + 16, v[4], v[5], v[6], v[7]);
+        sts_v4(ks_base + i * ks_stride + ks_half, v[4], v[5], v[6], v[7]);
       }
       tc_fence_before();
     }
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_const
     if (qd < 3) {
 #pragma unroll 1
       for (int i = 0; i < ns; ++i) {
-        const float4 p0 = lds_v4(ks_base + i * ks_stride), p1 = lds_v4(ks_base + i * ks_stride + 16);
+        const float4 p0 = lds_v4(ks_base + i * ks_stride), p1 = lds_v4(ks_base + i * ks_stride + ks_half);
         xbar[0] += p0.x; xbar[1] += p0.y; xbar[2] += p0.z; xbar[3] += p0.w; xbar[4] += p1.x; xbar[5] += p1.y; xbar[6] += p1.z; xbar[7] += p1.w;
       }
     }

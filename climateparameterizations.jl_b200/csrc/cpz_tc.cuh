@@ -384,8 +384,8 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
   const uint32_t side = gbase + L.side;                                                         // [array][column block][lane] float4
   auto side_addr = [&](int arr, int blk) { return side + (uint32_t)(((arr * 4 + blk) * 32 + lane) * 16); };
   const int tq = ((g * 2 + h) * 3 + qd) * 32 + lane;                // index among the stencil threads (qd < 3)
-  const uint32_t ks_base = sbase + L.ks + (uint32_t)tq * 32;
-  const uint32_t ks_stride = (uint32_t)(TC_NG * 2 * 3 * 32) * 32;
+  const uint32_t ks_base = sbase + L.ks + (uint32_t)tq * 16;  // stage slots: [stage][column half][thread] float4 (16-byte thread stride: conflict-free 128-bit accesses)
+  const uint32_t ks_stride = (uint32_t)(TC_NG * 2 * 3 * 32) * 32, ks_half = ks_stride / 2;
   const uint32_t dg = tb + 384 + 64 * g;                            // accumulator columns of this group
   const uint32_t id16 = tc_idesc(128, TC_GN);
   uint32_t parity = 0;
@@ -818,13 +818,13 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
 #pragma unroll 1
             for (int j = 0; j < i; ++j) {
               const float cj = last ? tab.b[j] : tab.a[(i + 1) % CPZ_MAX_STAGES][j];
-              const float4 p0 = lds_v4(ks_base + j * ks_stride), p1 = lds_v4(ks_base + j * ks_stride + 16);
+              const float4 p0 = lds_v4(ks_base + j * ks_stride), p1 = lds_v4(ks_base + j * ks_stride + ks_half);
               acc[0] = fmaf(cj, p0.x, acc[0]); acc[1] = fmaf(cj, p0.y, acc[1]); acc[2] = fmaf(cj, p0.z, acc[2]); acc[3] = fmaf(cj, p0.w, acc[3]);
               acc[4] = fmaf(cj, p1.x, acc[4]); acc[5] = fmaf(cj, p1.y, acc[5]); acc[6] = fmaf(cj, p1.z, acc[6]); acc[7] = fmaf(cj, p1.w, acc[7]);
             }
             if (!last) {
               sts_v4(ks_base + i * ks_stride, dx[0], dx[1], dx[2], dx[3]);
-              sts_v4(ks_base + i * ks_stride + 16, dx[4], dx[5], dx[6], dx[7]);
+              sts_v4(ks_base + i * ks_stride + ks_half, dx[4], dx[5], dx[6], dx[7]);
 #pragma unroll
               for (int r = 0; r < CPT; ++r) X[r] = fmaf(hstep, acc[r], x[r]);
             } else {
