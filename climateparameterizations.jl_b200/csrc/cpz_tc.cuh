@@ -384,8 +384,12 @@ __global__ void __launch_bounds__(TC_NT, 1) solve_tc_kernel(const __grid_constan
   const uint32_t side = gbase + L.side;                                                         // [array][column block][lane] float4
   auto side_addr = [&](int arr, int blk) { return side + (uint32_t)(((arr * 4 + blk) * 32 + lane) * 16); };
   const int tq = ((g * 2 + h) * 3 + qd) * 32 + lane;                // index among the stencil threads (qd < 3)
-  const uint32_t ks_base = sbase + L.ks + (uint32_t)tq * 16;  // stage slots: [stage][column half][thread] float4 (16-byte thread stride: conflict-free 128-bit accesses)
-  const uint32_t ks_stride = (uint32_t)(TC_NG * 2 * 3 * 32) * 32, ks_half = ks_stride / 2;
+  // stage slots: [stage][column half][thread] float4 — a 16-byte thread stride keeps the 128-bit accesses free of bank conflicts
+  // (config 2: 43.4 -> 42.8 ms). The implicit-diffusion forward kernel keeps [stage][thread][2 x float4]: measured 28.5 ms
+  // against 30.0 ms with the split layout (its two column groups fall into a worse relative phase)
+  constexpr bool KS_SPLIT = !(IMPL && !AUX);
+  const uint32_t ks_base = sbase + L.ks + (uint32_t)tq * (KS_SPLIT ? 16 : 32);
+  const uint32_t ks_stride = (uint32_t)(TC_NG * 2 * 3 * 32) * 32, ks_half = KS_SPLIT ? ks_stride / 2 : 16;
   const uint32_t dg = tb + 384 + 64 * g;                            // accumulator columns of this group
   const uint32_t id16 = tc_idesc(128, TC_GN);
   uint32_t parity = 0;
