@@ -108,11 +108,11 @@ __host__ __device__ inline TcBSmem tc_bwd_smem_layout(const TcB& B, int n_stages
   auto take = [&](int bytes) { int r = o; o += (bytes + 127) & ~127; return r; };
   L.d1h = take((B.K1 / 4) * TC_LBO); L.d1l = take((B.K1 / 4) * TC_LBO);
   L.d2h = take((3 * B.K2w / 4) * TC_LBO); L.d2l = take((3 * B.K2w / 4) * TC_LBO);
-  L.side = take(TCB_SIDE_ARRAYS * 4 * 32 * 16);
+  L.side = take(TCB_SIDE_ARRAYS * (4 * 32 * 16 + 16));  // 16-byte pad per array: the broadcast reads of two nets' arrays in one warp (S1) hit different banks
   L.grp_bytes = o;
   o = TC_NG * L.grp_bytes;
   L.ks = take(n_stages * (TC_NG * 2 * 3 * 32) * 8 * 4);
-  L.w3 = take(3 * 31 * 32 * 4);
+  L.w3 = take(31 * 64 * 4);
   L.misc = take(256);
   L.total = o;
   return L;
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_const
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_tcb + L.misc) + g;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_tcb + L.misc + 64);
   float* red = reinterpret_cast<float*>(smem_tcb + L.misc + 128);  // [16 warps][2]
-  float* w3s = reinterpret_cast<float*>(smem_tcb + L.w3);          // [net][j][32]: W3_net[j][o] at o
+  float* w3s = reinterpret_cast<float*>(smem_tcb + L.w3);          // [j][64]: W3_net[j][o] at row net*h2 + o (the S1 thread's own row: conflict-free)
   const bool active = !a.split || g == (int)(blockIdx.x & 1);
   const int tile = a.split ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, col0 = tile * TC_CT;
   const int cg0 = 16 * g + 8 * h;
@@ -196,9 +196,9 @@ __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_const
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = tid; i < 3 * 31 * 32; i += TC_NT) {
-    const int o = i & 31, j = (i >> 5) % 31, q = i / (31 * 32);
-    w3s[i] = o < T.h2 ? __ldg(a.theta + T.w_off[q][2] + o * T.nout + j) : 0.f;
+  for (int i = tid; i < 31 * 64; i += TC_NT) {
+    const int r = i & 63, j = i >> 6, q = min(r / T.h2, 2), o = r - q * T.h2;
+    w3s[i] = (r < 3 * T.h2 && j < T.nout) ? __ldg(a.theta + T.w_off[q][2] + o * T.nout + j) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_const
   tc_fence_after();
 
   const uint32_t side = gbase + L.side;
-  auto side_addr = [&](int arr, int blk) { return side + (uint32_t)(((arr * 4 + blk) * 32 + lane) * 16); };
+  auto side_addr = [&](int arr, int blk) { return side + (uint32_t)(((arr * 4 + blk) * 32 + lane) * 16 + arr * 16); };
   const int tq = ((g * 2 + h) * 3 + qd) * 32 + lane;
   const uint32_t ks_base = sbase + L.ks + (uint32_t)tq * 16;  // stage slots: [stage][column half][thread] float4 (16-byte thread stride: conflict-free 128-bit accesses)
   const uint32_t ks_stride = (uint32_t)(TC_NG * 2 * 3 * 32) * 32, ks_half = ks_stride / 2;
@@ -362,11 +362,11 @@ __global__ void __launch_bounds__(TC_NT, 1) adjoint_tc_kernel(const __grid_const
       // ---- S1: delta2 = (W3 delta3) .* act2'(z2) in FP32 ------------------------------------------------------------
       if (d2valid) {
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        const float* wp = w3s + (d2q * 31) * 32 + d2o;
-        const uint32_t dp = side + (uint32_t)((((3 + d2q) * 4 + d2quad) * 32) * 16);
+        const float* wp = w3s + d2row;
+        const uint32_t dp = side + (uint32_t)((((3 + d2q) * 4 + d2quad) * 32) * 16 + (3 + d2q) * 16);
 #pragma unroll 8
         for (int j = 0; j < 31; ++j) {
-          const float w = wp[j * 32];
+          const float w = wp[j * 64];
           const float4 p0 = lds_v4(dp + j * 16);
           acc[0] = fmaf(w, p0.x, acc[0]); acc[1] = fmaf(w, p0.y, acc[1]); acc[2] = fmaf(w, p0.z, acc[2]); acc[3] = fmaf(w, p0.w, acc[3]);
         }
